@@ -1,0 +1,138 @@
+/*
+ * peprml.h -- C ABI of the B200-native maximum-likelihood engine that replaces the raxmlHPC / raxmlHPC-PTHREADS /
+ * FastTree_WAG executions PEPR performs through its tool runners.
+ *
+ * The reference crosses into native code ONLY by fork/exec with files in the CWD
+ * (src/edu/vt/vbi/ci/pepr/util/ExecUtilities.java:23-42,80-119); there is no FFI to copy.  Each entry point below
+ * names the reference interface whose work it takes over.  All functions return 0 on success and a negative
+ * PML_E* code on failure; the message is available from pml_last_error() of the context that was used.
+ * Plain pointers and sizes only; no C++ / torch types.  All arrays are caller-allocated.
+ *
+ * Threading: a pml_ctx owns one GPU, one CUDA stream and (optionally) one NCCL rank.  Distinct contexts may be
+ * used from distinct host threads concurrently (PEPR runs up to `tree_threads` runners in one JVM,
+ * PhylogenomicPipeline2.java:1233-1254); one context must not be used from two threads at once.
+ * There is no CPU fallback: without a usable CUDA device pml_ctx_create fails with PML_ENODEVICE.
+ */
+#ifndef PEPRML_H
+#define PEPRML_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PML_OK 0
+#define PML_EINVAL (-1)    /* bad argument / malformed newick / unknown taxon */
+#define PML_ENODEVICE (-2) /* no CUDA device, or CUDA runtime error (see pml_last_error) */
+#define PML_ENOMEM (-3)
+#define PML_ECOMM (-4)     /* NCCL error */
+#define PML_ESTATE (-5)    /* call order (e.g. evaluate before model_set) */
+
+#define PML_UNIQUE_ID_BYTES 128
+
+typedef struct pml_ctx pml_ctx;
+typedef struct pml_aln pml_aln;
+typedef struct pml_tree pml_tree;
+
+const char *pml_version(void);
+
+/* ---- context: one GPU (+ one rank of a site-sharded group) -------------------------------------------------
+ * Replaces `-T n` of raxmlHPC-PTHREADS (RAxMLRunner.java:130-132): the pthread workers over alignment patterns
+ * become `nranks` contexts over pattern shards; the masterBarrier reduction becomes an NCCL allreduce of 1-3 doubles.
+ * nranks == 1: unique_id may be NULL.  nranks > 1: every rank passes the same id obtained from pml_comm_unique_id
+ * on one rank (distributed by the host: a Java array shared by threads, torch.distributed broadcast, a file ...). */
+int pml_comm_unique_id(unsigned char id[PML_UNIQUE_ID_BYTES]);
+int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char *unique_id, pml_ctx **out);
+void pml_ctx_destroy(pml_ctx *);
+const char *pml_last_error(const pml_ctx *); /* ctx may be NULL: last creation error of this thread */
+int pml_ctx_sync(pml_ctx *);
+
+/* ---- alignment -------------------------------------------------------------------------------------------
+ * Replaces the phylip hand-off SequenceAlignment.getAlignmentAsExtendedPhylipUsingTaxonNames -> `-s file`
+ * (SequenceAlignment.java:489-522; RAxMLRunner.java:100-107) and raxmlHPC's getinput/makevalues/sitesort:
+ * chars = ntax x nsites raw residue letters, row-major; letters ARNDCQEGHILKMFPSTWYV (any case), B, Z; every other
+ * byte (X ? * - ...) is "undetermined".  site_weights (NULL = all 1) replaces `-a weightFile`.
+ * Identical columns are merged (lexicographic column sort in taxon order) exactly as the reference does, so pattern
+ * order and pattern weights equal raxmlHPC's.  With nranks > 1 each rank passes the FULL alignment and keeps its
+ * contiguous block of patterns on its GPU. */
+int pml_aln_load(pml_ctx *, int ntax, int64_t nsites, const char *const *names, const uint8_t *chars,
+                 const int32_t *site_weights, pml_aln **out);
+int pml_aln_load_phylip(pml_ctx *, const char *path, const char *weights_path /* NULL */, pml_aln **out);
+void pml_aln_free(pml_aln *);
+int pml_aln_dims(const pml_aln *, int *ntax, int64_t *nsites, int64_t *npatterns, int64_t *npatterns_local);
+/* weights: npatterns int32 (global pattern order); site_to_pattern: nsites int64 (-1 for columns of weight 0) */
+int pml_aln_patterns(const pml_aln *, int32_t *weights, int64_t *site_to_pattern);
+const char *pml_aln_name(const pml_aln *, int taxon);
+/* host-only pattern crunch (no GPU, no context): the same code pml_aln_load runs.  codes_out: ntax x nsites bytes
+ * capacity, filled as ntax x *npatterns row-major; weights_out / site_to_pattern as above. */
+int pml_crunch_patterns(int ntax, int64_t nsites, const uint8_t *chars, const int32_t *site_weights, uint8_t *codes_out,
+                        int32_t *weights_out, int64_t *site_to_pattern, int64_t *npatterns);
+
+/* ---- model: `-m PROTGAMMAWAG` (PhylogenomicPipeline2.java:248-250) -----------------------------------------
+ * WAG exchangeabilities + fixed WAG frequencies, 4 mean-Gamma categories with shape alpha. */
+int pml_model_set(pml_aln *, const char *model, double alpha);
+int pml_model_get(const pml_aln *, double *alpha, double rates4[4]);
+/* host-only helpers (no GPU needed) used by data generators and tests */
+int pml_wag_pmatrix(double t, double rate, double P[400]);     /* row-major P(i->j) */
+int pml_wag_frequencies(double pi[20]);
+int pml_gamma_rates(double alpha, int ncat, double *rates);
+
+/* ---- tree ------------------------------------------------------------------------------------------------
+ * newick as BasicTree prints / parses it (BasicTree.java:131-409,450-520): rooted-binary or trifurcating top,
+ * optional inner labels, optional branch lengths (missing -> 0.1 substitutions/site). Replaces `-t tree`. */
+int pml_tree_load(pml_aln *, const char *newick, pml_tree **out);
+void pml_tree_free(pml_tree *);
+int pml_tree_num_branches(const pml_tree *);
+int pml_tree_branch(const pml_tree *, int branch, int *node_a, int *node_b, double *length); /* nodes < ntax are tips */
+int pml_tree_set_branch(pml_tree *, int branch, double length);
+/* writes the tree as raxmlHPC's RAxML_result file does: trifurcation at the inner node next to the first taxon,
+ * lengths with 20 decimals, terminated by ":0.0;" ; returns needed size if cap is too small */
+int64_t pml_tree_newick(const pml_tree *, char *buf, size_t cap);
+
+/* ---- likelihood: newview traversal + root evaluate (raxmlHPC newviewGTRGAMMAPROT / evaluateGTRGAMMAPROT) ---
+ * Replaces `-f g` / `-f n` scoring (RAxMLRunner.runRaxmlPerSiteLL, RAxMLRunner.java:162-213) at FIXED parameters.
+ * weights: NULL = alignment's pattern weights, else npatterns int32 (e.g. one bootstrap replicate).
+ * per_site: NULL or nsites doubles in ORIGINAL column order (what PhylogenomicPipeline2.getTreeScore sums, :1482-1500);
+ * with nranks > 1 per_site is filled with this rank's patterns only and 0 elsewhere (sum over ranks = full vector). */
+int pml_evaluate(pml_tree *, const int32_t *weights, double *lnl, double *per_site);
+/* forces every inner CLV to be recomputed on the next call (full traversal) */
+int pml_tree_invalidate(pml_tree *);
+/* counters since tree creation: CLV site-updates by case (0 tip-tip, 1 tip-inner, 2 inner-inner) and kernel launches */
+int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_launches);
+
+/* ---- Newton-Raphson branch-length derivatives (sumGAMMAPROT + coreGTRGAMMAPROT) ----------------------------
+ * lnL and d lnL/dt, d2 lnL/dt2 of `branch` at length t (other parameters fixed). */
+int pml_branch_derivs(pml_tree *, int branch, double t, const int32_t *weights, double *lnl, double *d1, double *d2);
+
+/* ---- `-f e`: optimise all branch lengths (+ alpha) on the fixed topology (treeEvaluate/optAlpha/modOpt) -----
+ * Replaces RAxMLRunner.runRaxmlParsimonyWithBranchLengths (RAxMLRunner.java:215-280) and
+ * FastTreeRunner.getRaxmlBranchLengths (FastTreeRunner.java:142-199).  eps = raxml `-e` (default 0.1 lnL units). */
+int pml_optimize(pml_tree *, int opt_alpha, double eps, const int32_t *weights, double *lnl, double *alpha);
+/* one smoothing sweep (one guarded NR step on every branch); returns 1 in *converged when no branch moved */
+int pml_smooth_branches(pml_tree *, int sweeps, const int32_t *weights, int *converged);
+
+/* ---- bootstrap replicates as integer site-weight vectors (computeNextReplicate + randum) -------------------
+ * Replaces `-x seed -N reps` / `-b seed` weight generation (RAxMLRunner.java:112-124).  out: nrep x npatterns int32,
+ * bit-identical to raxmlHPC for the same seed; *seed is advanced so that consecutive calls continue the stream. */
+int pml_bootstrap_weights(const pml_aln *, int64_t *seed, int nrep, int32_t *out);
+/* same stream from explicit pattern weights (host-only; no context needed) */
+int pml_bootstrap_weights_host(const int32_t *pattern_weights, int64_t npatterns, int64_t *seed, int nrep, int32_t *out);
+/* lnL of `nrep` weight vectors on the current tree/parameters in one pass (W: nrep x npatterns, global order) */
+int pml_evaluate_replicates(pml_tree *, const int32_t *W, int nrep, double *lnl);
+
+/* ---- support estimation (integer, bit exact) --------------------------------------------------------------
+ * TreeSupportDecorator.addSupportValues (TreeSupportDecorator.java:86-163) with Bipartition canonical form
+ * (Bipartition.java:41-64): writes the main tree with, for every inner node, the NUMBER of support trees that
+ * contain the same bipartition.  as_percent != 0 gives raxmlHPC `-f b` labels instead (round-half-up integer %,
+ * RAxMLRunner.getSupportDecoratedTree, RAxMLRunner.java:453-516).  Host-only; ctx may be NULL. */
+int64_t pml_support_tree(const char *main_newick, const char *const *trees, int ntrees, int as_percent, char *buf,
+                         size_t cap);
+/* counts per non-trivial split of the main tree in the order the labels appear in pml_support_tree's output */
+int pml_support_counts(const char *main_newick, const char *const *trees, int ntrees, int32_t *counts, int *nsplits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

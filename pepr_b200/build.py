@@ -1,0 +1,52 @@
+"""In-tree build of the engine: nvcc -> pepr_b200/libpeprml.so (sm_100a only) and the raxmlHPC-compatible CLI shim."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpeprml.so")
+CLI = os.path.join(HERE, "bin", "peprml")
+SOURCES = ["model.cpp", "host.cpp", "kernels.cu", "engine.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-I", os.path.join(HERE, "..", "include")]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "peprml.h"), __file__]
+    if force or _stale(LIB, deps):
+        objs = []
+        os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+        for s in SOURCES:
+            o = os.path.join(HERE, "build", s + ".o")
+            if force or _stale(o, deps):
+                cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-dc" if False else "-c", os.path.join(CSRC, s), "-o", o]
+                if verbose:
+                    print(" ".join(cmd))
+                subprocess.run(cmd, check=True)
+            objs.append(o)
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    cli_src = os.path.join(HERE, "cli", "peprml_main.cpp")
+    if os.path.exists(cli_src) and (force or _stale(CLI, [cli_src, LIB])):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        cmd = [NVCC] + ARCH + ["-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", CLI,
+                               "-L", HERE, "-lpeprml", "-Xlinker", "-rpath,$ORIGIN/.."]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,894 @@
+// Engine: contexts, resident alignments, trees with their CLV arenas, the likelihood / Newton-Raphson / optimisation
+// drivers, and the extern "C" surface declared in include/peprml.h.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/peprml.h"
+#include "host.h"
+#include "kernels.h"
+#include "model.h"
+
+using namespace pml;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// NCCL is bound at run time and only when a context joins a group of ranks: single-GPU use has no NCCL dependency.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) {
+            err = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return false;
+        }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
+            err = "libnccl.so.2 lacks required symbols";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct pml_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    std::string err;
+    // pinned staging for small host->device parameter blocks and device->host results
+    uint8_t* h_stage = nullptr;
+    size_t stage_cap = 0, stage_used = 0;
+    double* h_result = nullptr;
+
+    bool cuda(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return true;
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    }
+    bool bind() { return cuda(cudaSetDevice(device), "cudaSetDevice"); }
+    bool sync() {
+        if (!cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize")) return false;
+        stage_used = 0;
+        return true;
+    }
+    // bump allocator over the pinned block; a wrap-around waits for the stream so in-flight copies are never overwritten
+    void* stage(size_t bytes) {
+        bytes = (bytes + 63) & ~size_t(63);
+        if (stage_used + bytes > stage_cap) {
+            if (!sync() || bytes > stage_cap) return nullptr;
+        }
+        void* p = h_stage + stage_used;
+        stage_used += bytes;
+        return p;
+    }
+    // sums n doubles at d_buf over all ranks (no-op for a single rank)
+    bool allreduce(double* d_buf, int n) {
+        if (nranks == 1) return true;
+        ncclResult_t r = g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, comm, stream);
+        if (r != ncclSuccess) {
+            err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+            return false;
+        }
+        return true;
+    }
+};
+
+struct pml_aln {
+    pml_ctx* ctx = nullptr;
+    Patterns pat;
+    int64_t p0 = 0, nloc = 0, npad = 0;  // this rank's pattern range [p0, p0+nloc), padded row count
+    uint8_t* d_codes = nullptr;          // ntax x npad
+    int32_t* d_weights = nullptr;        // npad (alignment's own)
+    int32_t* d_wcustom = nullptr;        // npad (caller-supplied replicate)
+    DeviceModel* d_model = nullptr;
+    bool model_set = false;
+    double alpha = 1.0, rates[kCats] = {1, 1, 1, 1};
+    double* d_site_lnl = nullptr;
+    double* d_partials = nullptr;
+    double* d_result = nullptr;  // 16 doubles
+    double* d_scalar = nullptr;  // branch length handed to the NR core
+    double* d_sumtable = nullptr;
+    int32_t* d_sumscale = nullptr;
+    int ntrees = 0;
+};
+
+struct pml_tree {
+    pml_aln* aln = nullptr;
+    Topology topo;
+    ViewState views;
+    double* d_clv = nullptr;      // (ntax-2) x npad x 80
+    int32_t* d_scale = nullptr;   // (ntax-2) x npad
+    PBlock* d_pblocks = nullptr;
+    int pblock_cap = 0;
+    double* d_lengths = nullptr;
+    uint8_t* d_wanttip = nullptr;
+    int prepared_branch = -1;     // branch whose sumtable is resident
+    int64_t site_updates[3] = {0, 0, 0};
+    int64_t launches = 0;
+
+    double* clv(int v) const { return d_clv + (size_t)(v - topo.ntax) * aln->npad * kRow; }
+    int32_t* scale(int v) const { return d_scale + (size_t)(v - topo.ntax) * aln->npad; }
+    Side side(int v) const {
+        Side s{};
+        if (topo.is_tip(v)) s.codes = aln->d_codes + (size_t)v * aln->npad;
+        else {
+            s.clv = clv(v);
+            s.scale = scale(v);
+        }
+        return s;
+    }
+};
+
+namespace {
+
+constexpr int kPad = 128;            // pattern rows are padded to a multiple of this (tile height of the CLV kernels)
+constexpr int kOpsPerBatch = 512;    // traversal entries whose P blocks are built by one launch
+constexpr double kZmin = 1.0e-15, kZmax = 1.0 - 1.0e-6;  // NR bounds on z = exp(-t) (raxmlHPC topLevelMakenewz)
+constexpr double kDefaultLen = 0.1;
+
+bool upload_model(pml_aln* a) {
+    pml_ctx* c = a->ctx;
+    const Eigensystem& es = wag_eigensystem();
+    auto* h = (DeviceModel*)c->stage(sizeof(DeviceModel));
+    if (!h) return false;
+    std::memcpy(h->lambda, es.lambda, sizeof es.lambda);
+    std::memcpy(h->V, es.V, sizeof es.V);
+    std::memcpy(h->Vinv, es.Vinv, sizeof es.Vinv);
+    std::memcpy(h->pi, es.pi, sizeof es.pi);
+    std::memcpy(h->rates, a->rates, sizeof a->rates);
+    for (int i = 0; i < kStates; ++i)
+        for (int k = 0; k < kStates; ++k) h->piV[i][k] = es.pi[i] * es.V[i][k];
+    return c->cuda(cudaMemcpyAsync(a->d_model, h, sizeof(DeviceModel), cudaMemcpyHostToDevice, c->stream), "model upload");
+}
+
+// uploads a caller weight vector (global pattern order) for this rank's slice; returns the device pointer to use
+const int32_t* device_weights(pml_aln* a, const int32_t* weights) {
+    if (!weights) return a->d_weights;
+    pml_ctx* c = a->ctx;
+    if (a->nloc > 0) {
+        // pageable source: cudaMemcpyAsync stages it before returning, so the caller's buffer may be reused at once
+        if (!c->cuda(cudaMemcpyAsync(a->d_wcustom, weights + a->p0, sizeof(int32_t) * a->nloc, cudaMemcpyHostToDevice, c->stream),
+                     "weights upload"))
+            return nullptr;
+    }
+    return a->d_wcustom;
+}
+
+// executes a traversal descriptor: P blocks for every entry in one launch, then one CLV kernel per entry
+bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    for (size_t base = 0; base < ops.size(); base += kOpsPerBatch) {
+        const int n = (int)std::min<size_t>(kOpsPerBatch, ops.size() - base);
+        auto* hl = (double*)c->stage(sizeof(double) * 2 * n + 2 * n);
+        if (!hl) return false;
+        auto* ht = (uint8_t*)(hl + 2 * n);
+        for (int i = 0; i < n; ++i) {
+            const ViewOp& op = ops[base + i];
+            for (int k = 0; k < 2; ++k) {
+                hl[2 * i + k] = t->topo.len[op.cedge[k]];
+                ht[2 * i + k] = t->topo.is_tip(op.child[k]) ? 1 : 0;
+            }
+        }
+        if (!c->cuda(cudaMemcpyAsync(t->d_lengths, hl, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream), "lengths upload") ||
+            !c->cuda(cudaMemcpyAsync(t->d_wanttip, ht, 2 * n, cudaMemcpyHostToDevice, c->stream), "flags upload"))
+            return false;
+        launch_make_p(a->d_model, t->d_lengths, t->d_wanttip, t->d_pblocks, 2 * n, c->stream);
+        ++t->launches;
+        for (int i = 0; i < n; ++i) {
+            const ViewOp& op = ops[base + i];
+            NewviewOp nv{};
+            nv.left = t->side(op.child[0]);
+            nv.right = t->side(op.child[1]);
+            nv.pleft = t->d_pblocks + 2 * i;
+            nv.pright = t->d_pblocks + 2 * i + 1;
+            nv.out = t->clv(op.node);
+            nv.out_scale = t->scale(op.node);
+            launch_newview(nv, a->npad, c->stream);
+            ++t->launches;
+            const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+            t->site_updates[2 - ntip] += a->nloc;
+        }
+    }
+    return c->cuda(cudaGetLastError(), "CLV kernels");
+}
+
+// one extra P block (slot after the batch area) for the branch a likelihood is evaluated on
+PBlock* single_pblock(pml_tree* t, double len) {
+    pml_ctx* c = t->aln->ctx;
+    auto* hl = (double*)c->stage(sizeof(double) + 8);
+    if (!hl) return nullptr;
+    hl[0] = len;
+    ((uint8_t*)(hl + 1))[0] = 0;
+    double* dl = t->d_lengths + 2 * kOpsPerBatch;
+    uint8_t* dt = t->d_wanttip + 2 * kOpsPerBatch;
+    if (!c->cuda(cudaMemcpyAsync(dl, hl, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload") ||
+        !c->cuda(cudaMemcpyAsync(dt, hl + 1, 1, cudaMemcpyHostToDevice, c->stream), "flag upload"))
+        return nullptr;
+    PBlock* pb = t->d_pblocks + 2 * kOpsPerBatch;
+    launch_make_p(t->aln->d_model, dl, dt, pb, 1, c->stream);
+    ++t->launches;
+    return pb;
+}
+
+// brings both ends of branch e up to date; (a, b) is returned with b inner and a the tip end if there is one
+bool orient_branch(pml_tree* t, int e, int& a, int& b) {
+    a = t->topo.ea[e];
+    b = t->topo.eb[e];
+    if (t->topo.is_tip(b)) std::swap(a, b);
+    std::vector<ViewOp> ops;
+    t->views.plan(t->topo, a, b, ops);
+    t->views.plan(t->topo, b, a, ops);
+    return run_ops(t, ops);
+}
+
+bool fetch_result(pml_ctx* c, const double* d_result, int n, double* out) {
+    if (!c->cuda(cudaMemcpyAsync(c->h_result, d_result, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), "result download"))
+        return false;
+    if (!c->sync()) return false;
+    std::memcpy(out, c->h_result, sizeof(double) * n);
+    return true;
+}
+
+int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    const int32_t* dw = device_weights(a, weights);
+    if (!dw) return PML_ENODEVICE;
+    int x, y;
+    if (!orient_branch(t, e, x, y)) return PML_ENODEVICE;
+    PBlock* pb = single_pblock(t, t->topo.len[e]);
+    if (!pb) return PML_ENODEVICE;
+    launch_evaluate(a->d_model, t->side(x), t->side(y), pb, dw, a->npad, a->d_site_lnl, a->d_partials, a->d_result, c->stream);
+    t->launches += 2;
+    if (!c->cuda(cudaGetLastError(), "evaluate kernel")) return PML_ENODEVICE;
+    if (!c->allreduce(a->d_result, 1)) return PML_ECOMM;
+    return fetch_result(c, a->d_result, 1, lnl) ? PML_OK : PML_ENODEVICE;
+}
+
+bool ensure_sumtable(pml_aln* a) {
+    pml_ctx* c = a->ctx;
+    if (a->d_sumtable) return true;
+    return c->cuda(cudaMalloc(&a->d_sumtable, sizeof(double) * a->npad * kRow), "sumtable alloc") &&
+           c->cuda(cudaMalloc(&a->d_sumscale, sizeof(int32_t) * a->npad), "sumtable scale alloc");
+}
+
+bool prepare_branch(pml_tree* t, int e) {
+    pml_aln* a = t->aln;
+    if (!ensure_sumtable(a)) return false;
+    int x, y;
+    if (!orient_branch(t, e, x, y)) return false;
+    launch_sumtable(a->d_model, t->side(x), t->side(y), a->npad, a->d_sumtable, a->d_sumscale, a->ctx->stream);
+    ++t->launches;
+    t->prepared_branch = e;
+    return a->ctx->cuda(cudaGetLastError(), "sumtable kernel");
+}
+
+// lnL, dlnL/dt, d2lnL/dt2 of the prepared branch at length len
+bool core_at(pml_tree* t, const int32_t* dw, double len, double out[3]) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    auto* h = (double*)c->stage(sizeof(double));
+    if (!h) return false;
+    h[0] = len;
+    if (!c->cuda(cudaMemcpyAsync(a->d_scalar, h, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload")) return false;
+    launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, a->d_scalar, a->d_partials, a->d_result, c->stream);
+    t->launches += 2;
+    if (!c->cuda(cudaGetLastError(), "core kernel")) return false;
+    if (!c->allreduce(a->d_result, 3)) return false;
+    return fetch_result(c, a->d_result, 3, out);
+}
+
+void set_branch(pml_tree* t, int e, double len) {
+    if (t->topo.len[e] == len) return;
+    t->topo.len[e] = len;
+    t->views.branch_changed(t->topo, e);
+    t->prepared_branch = -1;
+}
+
+// guarded Newton-Raphson on z = exp(-t) in log z, constants and control flow of raxmlHPC topLevelMakenewz:
+// bad curvature -> z = 0.37 z + 0.63; step z *= exp(-d1/d2) when that exponent is < 100; cap z <= 0.25 zprev + 0.75
+bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z_out) {
+    if (!prepare_branch(t, e)) return false;
+    double z = std::exp(-t->topo.len[e]);
+    z = std::min(std::max(z, kZmin), kZmax);
+    double zprev = z, zstep = 0.0;
+    bool curvature_ok = true, done = false;
+    while (!done) {
+        if (curvature_ok) {
+            curvature_ok = false;
+            zprev = z;
+            zstep = (1.0 - kZmax) * z + kZmin;
+        }
+        z = std::min(std::max(z, kZmin), kZmax);
+        double r[3];
+        if (!core_at(t, dw, -std::log(z), r)) return false;
+        const double d1 = -r[1], d2 = r[2];  // derivatives in lz = log z = -t
+        if (d2 >= 0.0 && z < kZmax) zprev = z = 0.37 * z + 0.63;
+        else curvature_ok = true;
+        if (curvature_ok) {
+            if (d2 < 0.0) {
+                const double step = -d1 / d2;
+                if (step < 100.0) {
+                    z *= std::exp(step);
+                    z = std::max(z, kZmin);
+                    z = std::min(z, 0.25 * zprev + 0.75);
+                } else {
+                    z = 0.25 * zprev + 0.75;
+                }
+            }
+            z = std::min(z, kZmax);
+            --maxiter;
+            done = !(maxiter > 0 && std::fabs(z - zprev) > zstep);
+        }
+    }
+    z_out = z;
+    return true;
+}
+
+// one sweep: depth-first over all branches starting at taxon 0's branch, one guarded NR step each (raxmlHPC smoothTree/update)
+bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
+    smoothed = true;
+    const Topology& T = t->topo;
+    std::vector<std::pair<int, int>> stack;  // (branch, far node)
+    stack.push_back({T.edge[0][0], T.nbr[0][0]});
+    while (!stack.empty()) {
+        const auto [e, far] = stack.back();
+        stack.pop_back();
+        const double z0 = std::min(std::max(std::exp(-T.len[e]), kZmin), kZmax);
+        double z;
+        if (!newton_branch(t, e, dw, 1, z)) return false;
+        if (std::fabs(z - z0) > 1.0e-5) smoothed = false;
+        set_branch(t, e, -std::log(z));
+        if (!T.is_tip(far)) {
+            const int near = T.ea[e] == far ? T.eb[e] : T.ea[e];
+            for (int s = 2; s >= 0; --s)
+                if (T.nbr[far][s] != near) stack.push_back({T.edge[far][s], T.nbr[far][s]});
+        }
+    }
+    return true;
+}
+
+bool tree_evaluate(pml_tree* t, const int32_t* weights, const int32_t* dw, double factor, double* lnl) {
+    int sweeps = (int)(32 * factor);
+    while (--sweeps >= 0) {
+        bool smoothed;
+        if (!smooth_sweep(t, dw, smoothed)) return false;
+        if (smoothed) break;
+    }
+    return evaluate_branch(t, t->topo.edge[0][0], weights, lnl) == PML_OK;
+}
+
+bool set_alpha(pml_tree* t, double alpha) {
+    pml_aln* a = t->aln;
+    a->alpha = alpha;
+    gamma_mean_rates(alpha, kCats, a->rates);
+    if (!upload_model(a)) return false;
+    t->views.reset(t->topo);
+    t->prepared_branch = -1;
+    return true;
+}
+
+// Brent's minimiser on log(alpha) for -lnL with every other parameter fixed; each trial is a full traversal + evaluate
+bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* best_lnl) {
+    pml_aln* a = t->aln;
+    const int root_branch = t->topo.edge[0][0];
+    bool ok = true;
+    auto f = [&](double la) {
+        double l = 0.0;
+        if (!set_alpha(t, std::exp(la)) || evaluate_branch(t, root_branch, weights, &l) != PML_OK) ok = false;
+        return -l;
+    };
+    const double lmin = std::log(kAlphaMin), lmax = std::log(kAlphaMax), gold = 1.6180339887498949, cgold = 0.3819660112501051;
+    auto clamp = [&](double v) { return std::min(std::max(v, lmin), lmax); };
+    double xa = std::log(a->alpha), xb = clamp(xa + 0.1), fa = f(xa), fb = f(xb);
+    if (fb > fa) {
+        std::swap(xa, xb);
+        std::swap(fa, fb);
+    }
+    double xc = clamp(xb + gold * (xb - xa)), fc = f(xc);
+    for (int guard = 0; ok && fb > fc && guard < 64; ++guard) {
+        xa = xb;
+        fa = fb;
+        xb = xc;
+        fb = fc;
+        xc = clamp(xb + gold * (xb - xa));
+        if (xc == xb) break;
+        fc = f(xc);
+    }
+    double lo = std::min(xa, xc), hi = std::max(xa, xc), x = xb, w = xb, v = xb, fx = fb, fw = fb, fv = fb, d = 0.0, e = 0.0;
+    for (int it = 0; ok && it < 100; ++it) {
+        const double mid = 0.5 * (lo + hi), tol1 = tol * std::fabs(x) + 1e-10, tol2 = 2.0 * tol1;
+        if (std::fabs(x - mid) <= tol2 - 0.5 * (hi - lo)) break;
+        bool golden = true;
+        if (std::fabs(e) > tol1) {
+            double r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), p = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = std::fabs(q);
+            const double eprev = e;
+            e = d;
+            if (!(std::fabs(p) >= std::fabs(0.5 * q * eprev) || p <= q * (lo - x) || p >= q * (hi - x))) {
+                d = p / q;
+                const double u = x + d;
+                if (u - lo < tol2 || hi - u < tol2) d = mid >= x ? tol1 : -tol1;
+                golden = false;
+            }
+        }
+        if (golden) {
+            e = x >= mid ? lo - x : hi - x;
+            d = cgold * e;
+        }
+        const double u = std::fabs(d) >= tol1 ? x + d : x + (d >= 0 ? tol1 : -tol1), fu = f(u);
+        if (fu <= fx) {
+            if (u >= x) lo = x; else hi = x;
+            v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+        } else {
+            if (u < x) lo = u; else hi = u;
+            if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+    }
+    if (!ok) return false;
+    if (!set_alpha(t, std::exp(x))) return false;
+    *best_lnl = -fx;
+    return true;
+}
+
+int fail(pml_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI ======
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* pml_version(void) { return "peprml-b200 0.1 (WAG+G4, FP64, sm_100a)"; }
+
+int pml_comm_unique_id(unsigned char id[PML_UNIQUE_ID_BYTES]) {
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, PML_ECOMM, err);
+    ncclUniqueId u;
+    if (g_nccl.GetUniqueId(&u) != ncclSuccess) return fail(nullptr, PML_ECOMM, "ncclGetUniqueId failed");
+    static_assert(sizeof(u) == PML_UNIQUE_ID_BYTES, "unique id size");
+    std::memcpy(id, &u, sizeof u);
+    return PML_OK;
+}
+
+int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique_id, pml_ctx** out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, PML_EINVAL, "bad rank/nranks");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PML_ENODEVICE,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU path");
+    if (gpu_id < 0 || gpu_id >= ndev) return fail(nullptr, PML_EINVAL, "gpu_id out of range");
+    auto c = std::make_unique<pml_ctx>();
+    c->device = gpu_id;
+    c->rank = rank;
+    c->nranks = nranks;
+    if (!c->bind() || !c->cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create"))
+        return fail(nullptr, PML_ENODEVICE, c->err);
+    c->stage_cap = 1 << 20;
+    if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
+        !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc"))
+        return fail(nullptr, PML_ENOMEM, c->err);
+    if (nranks > 1) {
+        if (!unique_id) return fail(nullptr, PML_EINVAL, "unique_id required when nranks > 1");
+        std::string err;
+        if (!g_nccl.load(err)) return fail(nullptr, PML_ECOMM, err);
+        ncclUniqueId u;
+        std::memcpy(&u, unique_id, sizeof u);
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
+        if (r != ncclSuccess) return fail(nullptr, PML_ECOMM, "ncclCommInitRank failed");
+    }
+    *out = c.release();
+    return PML_OK;
+}
+
+void pml_ctx_destroy(pml_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    delete c;
+}
+
+const char* pml_last_error(const pml_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int pml_ctx_sync(pml_ctx* c) {
+    if (!c) return PML_EINVAL;
+    return c->bind() && c->sync() ? PML_OK : PML_ENODEVICE;
+}
+
+int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names, const uint8_t* chars,
+                 const int32_t* site_weights, pml_aln** out) {
+    if (!c || !out || ntax < 3 || nsites < 1 || !names || !chars) return fail(c, PML_EINVAL, "pml_aln_load: bad arguments");
+    *out = nullptr;
+    if (!c->bind()) return PML_ENODEVICE;
+    auto a = std::make_unique<pml_aln>();
+    a->ctx = c;
+    crunch_patterns(ntax, nsites, chars, site_weights, a->pat);
+    for (int i = 0; i < ntax; ++i) a->pat.names.emplace_back(names[i]);
+    if (a->pat.npat == 0) return fail(c, PML_EINVAL, "alignment has no column with positive weight");
+    const int64_t np = a->pat.npat;
+    a->p0 = np * c->rank / c->nranks;
+    a->nloc = np * (c->rank + 1) / c->nranks - a->p0;
+    a->npad = std::max<int64_t>(kPad, (a->nloc + kPad - 1) / kPad * kPad);
+    // device copies of this rank's slice; padded rows are "undetermined" with weight 0
+    std::vector<uint8_t> hc((size_t)ntax * a->npad, 22);
+    for (int t = 0; t < ntax; ++t)
+        std::memcpy(hc.data() + (size_t)t * a->npad, a->pat.codes.data() + (size_t)t * np + a->p0, a->nloc);
+    std::vector<int32_t> hw(a->npad, 0);
+    std::copy(a->pat.weight.begin() + a->p0, a->pat.weight.begin() + a->p0 + a->nloc, hw.begin());
+    bool ok = c->cuda(cudaMalloc(&a->d_codes, hc.size()), "codes alloc") &&
+              c->cuda(cudaMalloc(&a->d_weights, sizeof(int32_t) * a->npad), "weights alloc") &&
+              c->cuda(cudaMalloc(&a->d_wcustom, sizeof(int32_t) * a->npad), "weights alloc") &&
+              c->cuda(cudaMalloc(&a->d_model, sizeof(DeviceModel)), "model alloc") &&
+              c->cuda(cudaMalloc(&a->d_site_lnl, sizeof(double) * a->npad), "site lnl alloc") &&
+              c->cuda(cudaMalloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
+              c->cuda(cudaMalloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
+              c->cuda(cudaMalloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
+              c->cuda(cudaMemcpy(a->d_codes, hc.data(), hc.size(), cudaMemcpyHostToDevice), "codes upload") &&
+              c->cuda(cudaMemcpy(a->d_weights, hw.data(), sizeof(int32_t) * a->npad, cudaMemcpyHostToDevice), "weights upload") &&
+              c->cuda(cudaMemset(a->d_wcustom, 0, sizeof(int32_t) * a->npad), "weights clear");
+    if (!ok) {
+        pml_aln_free(a.release());
+        return PML_ENOMEM;
+    }
+    *out = a.release();
+    return PML_OK;
+}
+
+int pml_aln_load_phylip(pml_ctx* c, const char* path, const char* weights_path, pml_aln** out) {
+    if (!c || !path || !out) return fail(c, PML_EINVAL, "pml_aln_load_phylip: bad arguments");
+    std::vector<std::string> names;
+    std::vector<uint8_t> chars;
+    int64_t nsites = 0;
+    std::string err;
+    if (!read_phylip(path, names, chars, nsites, err)) return fail(c, PML_EINVAL, err);
+    std::vector<int32_t> w;
+    if (weights_path) {
+        std::ifstream in(weights_path);
+        long v;
+        while (in >> v) w.push_back((int32_t)v);
+        if ((int64_t)w.size() != nsites) return fail(c, PML_EINVAL, "weight file must hold one integer per alignment column");
+    }
+    std::vector<const char*> np;
+    for (auto& s : names) np.push_back(s.c_str());
+    return pml_aln_load(c, (int)names.size(), nsites, np.data(), chars.data(), w.empty() ? nullptr : w.data(), out);
+}
+
+void pml_aln_free(pml_aln* a) {
+    if (!a) return;
+    a->ctx->bind();
+    cudaStreamSynchronize(a->ctx->stream);
+    cudaFree(a->d_codes);
+    cudaFree(a->d_weights);
+    cudaFree(a->d_wcustom);
+    cudaFree(a->d_model);
+    cudaFree(a->d_site_lnl);
+    cudaFree(a->d_partials);
+    cudaFree(a->d_result);
+    cudaFree(a->d_scalar);
+    cudaFree(a->d_sumtable);
+    cudaFree(a->d_sumscale);
+    delete a;
+}
+
+int pml_aln_dims(const pml_aln* a, int* ntax, int64_t* nsites, int64_t* npat, int64_t* nloc) {
+    if (!a) return PML_EINVAL;
+    if (ntax) *ntax = a->pat.ntax;
+    if (nsites) *nsites = a->pat.nsites;
+    if (npat) *npat = a->pat.npat;
+    if (nloc) *nloc = a->nloc;
+    return PML_OK;
+}
+
+int pml_aln_patterns(const pml_aln* a, int32_t* weights, int64_t* site_to_pattern) {
+    if (!a) return PML_EINVAL;
+    if (weights) std::copy(a->pat.weight.begin(), a->pat.weight.end(), weights);
+    if (site_to_pattern) std::copy(a->pat.site_to_pat.begin(), a->pat.site_to_pat.end(), site_to_pattern);
+    return PML_OK;
+}
+
+const char* pml_aln_name(const pml_aln* a, int taxon) {
+    return (a && taxon >= 0 && taxon < a->pat.ntax) ? a->pat.names[taxon].c_str() : nullptr;
+}
+
+int pml_model_set(pml_aln* a, const char* model, double alpha) {
+    if (!a) return PML_EINVAL;
+    pml_ctx* c = a->ctx;
+    if (model && std::strcmp(model, "PROTGAMMAWAG") != 0)
+        return fail(c, PML_EINVAL, std::string("unsupported model '") + model + "' (only PROTGAMMAWAG)");
+    if (!(alpha >= kAlphaMin && alpha <= kAlphaMax)) return fail(c, PML_EINVAL, "alpha must lie in [0.02, 1000]");
+    if (!c->bind()) return PML_ENODEVICE;
+    a->alpha = alpha;
+    gamma_mean_rates(alpha, kCats, a->rates);
+    if (!upload_model(a)) return PML_ENODEVICE;
+    a->model_set = true;
+    return PML_OK;
+}
+
+int pml_model_get(const pml_aln* a, double* alpha, double rates4[4]) {
+    if (!a) return PML_EINVAL;
+    if (alpha) *alpha = a->alpha;
+    if (rates4) std::memcpy(rates4, a->rates, sizeof a->rates);
+    return PML_OK;
+}
+
+int pml_wag_pmatrix(double t, double rate, double P[400]) {
+    wag_pmatrix(t, rate, P);
+    return PML_OK;
+}
+int pml_wag_frequencies(double pi[20]) {
+    std::memcpy(pi, wag_eigensystem().pi, sizeof(double) * 20);
+    return PML_OK;
+}
+int pml_gamma_rates(double alpha, int ncat, double* rates) {
+    if (!(alpha > 0) || ncat < 1 || !rates) return PML_EINVAL;
+    gamma_mean_rates(alpha, ncat, rates);
+    return PML_OK;
+}
+
+int pml_tree_load(pml_aln* a, const char* newick, pml_tree** out) {
+    if (!a || !newick || !out) return PML_EINVAL;
+    pml_ctx* c = a->ctx;
+    *out = nullptr;
+    if (!a->model_set) return fail(c, PML_ESTATE, "pml_model_set must be called before pml_tree_load");
+    if (!c->bind()) return PML_ENODEVICE;
+    auto t = std::make_unique<pml_tree>();
+    t->aln = a;
+    std::string err;
+    if (!parse_newick(newick, a->pat.names, kDefaultLen, t->topo, err)) return fail(c, PML_EINVAL, err);
+    t->views.reset(t->topo);
+    const size_t inner = (size_t)a->pat.ntax - 2;
+    t->pblock_cap = 2 * kOpsPerBatch + 1;
+    bool ok = c->cuda(cudaMalloc(&t->d_clv, sizeof(double) * inner * a->npad * kRow), "CLV arena alloc") &&
+              c->cuda(cudaMalloc(&t->d_scale, sizeof(int32_t) * inner * a->npad), "scaler alloc") &&
+              c->cuda(cudaMalloc(&t->d_pblocks, sizeof(PBlock) * t->pblock_cap), "P block alloc") &&
+              c->cuda(cudaMalloc(&t->d_lengths, sizeof(double) * t->pblock_cap), "lengths alloc") &&
+              c->cuda(cudaMalloc(&t->d_wanttip, t->pblock_cap), "flags alloc");
+    if (!ok) {
+        pml_tree_free(t.release());
+        return PML_ENOMEM;
+    }
+    ++a->ntrees;
+    *out = t.release();
+    return PML_OK;
+}
+
+void pml_tree_free(pml_tree* t) {
+    if (!t) return;
+    t->aln->ctx->bind();
+    cudaStreamSynchronize(t->aln->ctx->stream);
+    cudaFree(t->d_clv);
+    cudaFree(t->d_scale);
+    cudaFree(t->d_pblocks);
+    cudaFree(t->d_lengths);
+    cudaFree(t->d_wanttip);
+    delete t;
+}
+
+int pml_tree_num_branches(const pml_tree* t) { return t ? t->topo.nedges() : PML_EINVAL; }
+
+int pml_tree_branch(const pml_tree* t, int e, int* a, int* b, double* len) {
+    if (!t || e < 0 || e >= t->topo.nedges()) return PML_EINVAL;
+    if (a) *a = t->topo.ea[e];
+    if (b) *b = t->topo.eb[e];
+    if (len) *len = t->topo.len[e];
+    return PML_OK;
+}
+
+int pml_tree_set_branch(pml_tree* t, int e, double len) {
+    if (!t || e < 0 || e >= t->topo.nedges() || !(len >= 0.0)) return PML_EINVAL;
+    set_branch(t, e, len);
+    return PML_OK;
+}
+
+int64_t pml_tree_newick(const pml_tree* t, char* buf, size_t cap) {
+    if (!t) return PML_EINVAL;
+    const std::string s = write_newick_result(t->topo, t->aln->pat.names);
+    if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size() + 1;
+}
+
+int pml_tree_invalidate(pml_tree* t) {
+    if (!t) return PML_EINVAL;
+    t->views.reset(t->topo);
+    t->prepared_branch = -1;
+    return PML_OK;
+}
+
+int pml_tree_stats(const pml_tree* t, int64_t site_updates[3], int64_t* launches) {
+    if (!t) return PML_EINVAL;
+    if (site_updates) std::memcpy(site_updates, t->site_updates, sizeof t->site_updates);
+    if (launches) *launches = t->launches;
+    return PML_OK;
+}
+
+int pml_evaluate(pml_tree* t, const int32_t* weights, double* lnl, double* per_site) {
+    if (!t || !lnl) return PML_EINVAL;
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    const int rc = evaluate_branch(t, t->topo.edge[0][0], weights, lnl);
+    if (rc != PML_OK || !per_site) return rc;
+    std::vector<double> pp(a->npad);
+    if (!c->cuda(cudaMemcpy(pp.data(), a->d_site_lnl, sizeof(double) * a->npad, cudaMemcpyDeviceToHost), "site lnL download"))
+        return PML_ENODEVICE;
+    for (int64_t s = 0; s < a->pat.nsites; ++s) {
+        const int64_t p = a->pat.site_to_pat[s];
+        per_site[s] = (p >= a->p0 && p < a->p0 + a->nloc) ? pp[p - a->p0] : 0.0;
+    }
+    return PML_OK;
+}
+
+int pml_branch_derivs(pml_tree* t, int branch, double len, const int32_t* weights, double* lnl, double* d1, double* d2) {
+    if (!t || branch < 0 || branch >= t->topo.nedges() || !(len >= 0.0)) return PML_EINVAL;
+    pml_ctx* c = t->aln->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    const int32_t* dw = device_weights(t->aln, weights);
+    if (!dw) return PML_ENODEVICE;
+    if (t->prepared_branch != branch && !prepare_branch(t, branch)) return PML_ENODEVICE;
+    double r[3];
+    if (!core_at(t, dw, len, r)) return PML_ENODEVICE;
+    if (lnl) *lnl = r[0];
+    if (d1) *d1 = r[1];
+    if (d2) *d2 = r[2];
+    return PML_OK;
+}
+
+int pml_smooth_branches(pml_tree* t, int sweeps, const int32_t* weights, int* converged) {
+    if (!t || sweeps < 1) return PML_EINVAL;
+    pml_ctx* c = t->aln->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    const int32_t* dw = device_weights(t->aln, weights);
+    if (!dw) return PML_ENODEVICE;
+    bool smoothed = false;
+    for (int s = 0; s < sweeps && !smoothed; ++s)
+        if (!smooth_sweep(t, dw, smoothed)) return PML_ENODEVICE;
+    if (converged) *converged = smoothed ? 1 : 0;
+    return PML_OK;
+}
+
+int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights, double* lnl, double* alpha) {
+    if (!t) return PML_EINVAL;
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    if (!(eps > 0.0)) eps = 0.1;
+    const int32_t* dw = device_weights(a, weights);
+    if (!dw) return PML_ENODEVICE;
+    // modOpt: { smooth (2 sweeps max), Brent on alpha, smooth (3 sweeps max) } until a round gains <= eps
+    double cur, best = 0.0;
+    if (evaluate_branch(t, t->topo.edge[0][0], weights, &best) != PML_OK) return PML_ENODEVICE;
+    int rounds = 0;
+    do {
+        cur = best;
+        if (!tree_evaluate(t, weights, dw, 0.0625, &best)) return PML_ENODEVICE;
+        if (opt_alpha) {
+            if (!optimise_alpha(t, weights, 1.0e-4, &best)) return PML_ENODEVICE;
+        }
+        if (!tree_evaluate(t, weights, dw, 0.1, &best)) return PML_ENODEVICE;
+    } while (std::fabs(cur - best) > eps && ++rounds < 200);
+    if (lnl) *lnl = best;
+    if (alpha) *alpha = a->alpha;
+    return PML_OK;
+}
+
+int pml_bootstrap_weights(const pml_aln* a, int64_t* seed, int nrep, int32_t* out) {
+    if (!a || !seed || nrep < 0 || !out) return PML_EINVAL;
+    bootstrap_replicates(seed, a->pat.weight, nrep, out);
+    return PML_OK;
+}
+
+int pml_bootstrap_weights_host(const int32_t* pw, int64_t npat, int64_t* seed, int nrep, int32_t* out) {
+    if (!pw || npat < 1 || !seed || nrep < 0 || !out) return PML_EINVAL;
+    bootstrap_replicates(seed, std::vector<int32_t>(pw, pw + npat), nrep, out);
+    return PML_OK;
+}
+
+int pml_crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_weights, uint8_t* codes_out,
+                        int32_t* weights_out, int64_t* site_to_pattern, int64_t* npatterns) {
+    if (ntax < 1 || nsites < 1 || !chars || !npatterns) return PML_EINVAL;
+    Patterns p;
+    crunch_patterns(ntax, nsites, chars, site_weights, p);
+    *npatterns = p.npat;
+    if (codes_out) std::copy(p.codes.begin(), p.codes.end(), codes_out);
+    if (weights_out) std::copy(p.weight.begin(), p.weight.end(), weights_out);
+    if (site_to_pattern) std::copy(p.site_to_pat.begin(), p.site_to_pat.end(), site_to_pattern);
+    return PML_OK;
+}
+
+int pml_evaluate_replicates(pml_tree* t, const int32_t* W, int nrep, double* lnl) {
+    if (!t || !W || nrep < 1 || !lnl) return PML_EINVAL;
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    double base;
+    const int rc = evaluate_branch(t, t->topo.edge[0][0], nullptr, &base);  // fills d_site_lnl
+    if (rc != PML_OK) return rc;
+    int32_t* dW = nullptr;
+    double* dl = nullptr;
+    const int64_t np = a->pat.npat;
+    bool ok = c->cuda(cudaMalloc(&dW, sizeof(int32_t) * (size_t)nrep * a->npad), "replicate weights alloc") &&
+              c->cuda(cudaMalloc(&dl, sizeof(double) * nrep), "replicate lnL alloc") &&
+              c->cuda(cudaMemsetAsync(dW, 0, sizeof(int32_t) * (size_t)nrep * a->npad, c->stream), "replicate weights clear") &&
+              c->cuda(cudaMemcpy2DAsync(dW, sizeof(int32_t) * a->npad, W + a->p0, sizeof(int32_t) * np, sizeof(int32_t) * a->nloc,
+                                        nrep, cudaMemcpyHostToDevice, c->stream),
+                      "replicate weights upload");
+    if (ok) {
+        launch_replicate_lnl(dW, nrep, a->npad, a->npad, a->d_site_lnl, dl, c->stream);
+        ++t->launches;
+        ok = c->cuda(cudaGetLastError(), "replicate kernel") && c->allreduce(dl, nrep) &&
+             c->cuda(cudaMemcpyAsync(lnl, dl, sizeof(double) * nrep, cudaMemcpyDeviceToHost, c->stream), "replicate lnL download") &&
+             c->sync();
+    }
+    cudaFree(dW);
+    cudaFree(dl);
+    return ok ? PML_OK : PML_ENODEVICE;
+}
+
+int64_t pml_support_tree(const char* main_newick, const char* const* trees, int ntrees, int as_percent, char* buf, size_t cap) {
+    if (!main_newick || ntrees < 0 || (ntrees > 0 && !trees)) return PML_EINVAL;
+    std::vector<std::string> ts;
+    for (int i = 0; i < ntrees; ++i) ts.emplace_back(trees[i]);
+    std::string err;
+    const std::string s = support_tree(main_newick, ts, as_percent != 0, nullptr, err);
+    if (s.empty()) return fail(nullptr, PML_EINVAL, err);
+    if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size() + 1;
+}
+
+int pml_support_counts(const char* main_newick, const char* const* trees, int ntrees, int32_t* counts, int* nsplits) {
+    if (!main_newick || ntrees < 0 || (ntrees > 0 && !trees)) return PML_EINVAL;
+    std::vector<std::string> ts;
+    for (int i = 0; i < ntrees; ++i) ts.emplace_back(trees[i]);
+    std::string err;
+    std::vector<int32_t> cs;
+    if (support_tree(main_newick, ts, false, &cs, err).empty()) return fail(nullptr, PML_EINVAL, err);
+    if (nsplits) *nsplits = (int)cs.size();
+    if (counts) std::copy(cs.begin(), cs.end(), counts);
+    return PML_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,543 @@
+#include "host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <numeric>
+#include <sstream>
+
+#include "model.h"
+
+namespace pml {
+
+// =========================================================================================== alignment ======
+void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out) {
+    out.ntax = ntax;
+    out.nsites = nsites;
+    // column-major copy of the residue codes so that one column is one contiguous key of ntax bytes
+    std::vector<uint8_t> cols((size_t)ntax * (size_t)nsites);
+    for (int t = 0; t < ntax; ++t) {
+        const uint8_t* row = chars + (size_t)t * nsites;
+        for (int64_t s = 0; s < nsites; ++s) cols[(size_t)s * ntax + t] = (uint8_t)residue_code(row[s]);
+    }
+    std::vector<int64_t> order;
+    order.reserve(nsites);
+    for (int64_t s = 0; s < nsites; ++s)
+        if (!site_w || site_w[s] > 0) order.push_back(s);
+    const uint8_t* base = cols.data();
+    std::sort(order.begin(), order.end(), [base, ntax](int64_t a, int64_t b) {
+        const int c = std::memcmp(base + (size_t)a * ntax, base + (size_t)b * ntax, ntax);
+        return c != 0 ? c < 0 : a < b;
+    });
+    out.site_to_pat.assign(nsites, -1);
+    std::vector<int64_t> first;  // representative column of each pattern
+    out.weight.clear();
+    for (size_t k = 0; k < order.size(); ++k) {
+        const int64_t s = order[k];
+        if (k == 0 || std::memcmp(base + (size_t)s * ntax, base + (size_t)order[k - 1] * ntax, ntax) != 0) {
+            first.push_back(s);
+            out.weight.push_back(0);
+        }
+        out.weight.back() += site_w ? site_w[s] : 1;
+        out.site_to_pat[s] = (int64_t)first.size() - 1;
+    }
+    out.npat = (int64_t)first.size();
+    out.codes.assign((size_t)ntax * out.npat, 22);
+    for (int64_t p = 0; p < out.npat; ++p)
+        for (int t = 0; t < ntax; ++t) out.codes[(size_t)t * out.npat + p] = cols[(size_t)first[p] * ntax + t];
+}
+
+bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,
+                 std::string& err) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) {
+        err = "cannot open alignment file " + path;
+        return false;
+    }
+    long ntax = 0, len = 0;
+    if (!(in >> ntax >> len) || ntax < 1 || len < 1) {
+        err = "bad phylip header in " + path;
+        return false;
+    }
+    nsites = len;
+    names.clear();
+    chars.assign((size_t)ntax * len, '?');
+    for (long t = 0; t < ntax; ++t) {
+        std::string name;
+        if (!(in >> name)) {
+            err = "phylip: missing taxon " + std::to_string(t + 1);
+            return false;
+        }
+        names.push_back(name);
+        int64_t got = 0;
+        char ch;
+        while (got < len && in.get(ch)) {
+            if (ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r') continue;
+            chars[(size_t)t * len + got++] = (uint8_t)ch;
+        }
+        if (got != len) {
+            err = "phylip: sequence of " + name + " is shorter than " + std::to_string(len);
+            return false;
+        }
+    }
+    return true;
+}
+
+// =========================================================================================== newick =========
+namespace {
+
+struct RawNode {
+    std::vector<int> kids;
+    std::string label;
+    std::string length;  // textual, empty when absent
+    int parent = -1;
+};
+
+struct RawTree {
+    std::vector<RawNode> nodes;
+    int top = -1;
+};
+
+bool parse_raw(const std::string& s, RawTree& out, std::string& err) {
+    size_t pos = 0;
+    auto skip = [&] {
+        while (pos < s.size() && (s[pos] == ' ' || s[pos] == '\n' || s[pos] == '\t' || s[pos] == '\r')) ++pos;
+    };
+    std::function<int()> node = [&]() -> int {
+        skip();
+        const int id = (int)out.nodes.size();
+        out.nodes.emplace_back();
+        if (pos < s.size() && s[pos] == '(') {
+            ++pos;
+            for (;;) {
+                const int k = node();
+                if (k < 0) return -1;
+                out.nodes[k].parent = id;
+                out.nodes[id].kids.push_back(k);
+                skip();
+                if (pos < s.size() && s[pos] == ',') {
+                    ++pos;
+                    continue;
+                }
+                if (pos < s.size() && s[pos] == ')') {
+                    ++pos;
+                    break;
+                }
+                err = "newick: expected ',' or ')' at offset " + std::to_string(pos);
+                return -1;
+            }
+        }
+        skip();
+        size_t st = pos;
+        while (pos < s.size() && !std::strchr(":,();[ \n\t\r", s[pos])) ++pos;
+        out.nodes[id].label = s.substr(st, pos - st);
+        skip();
+        if (pos < s.size() && s[pos] == ':') {
+            ++pos;
+            skip();
+            st = pos;
+            while (pos < s.size() && !std::strchr(",();[ \n\t\r", s[pos])) ++pos;
+            out.nodes[id].length = s.substr(st, pos - st);
+            skip();
+        }
+        if (pos < s.size() && s[pos] == '[') {  // `:len[support]` form
+            const size_t close = s.find(']', pos);
+            if (close == std::string::npos) {
+                err = "newick: unterminated '['";
+                return -1;
+            }
+            if (out.nodes[id].label.empty()) out.nodes[id].label = s.substr(pos + 1, close - pos - 1);
+            pos = close + 1;
+        }
+        return id;
+    };
+    out.nodes.clear();
+    out.top = node();
+    if (out.top < 0) return false;
+    if (out.nodes[out.top].kids.empty()) {
+        err = "newick: no tree found";
+        return false;
+    }
+    return true;
+}
+
+std::string fixed20(double v) {
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%.20f", v);
+    return buf;
+}
+
+// shortest decimal that round-trips, printed the way Java's Double.toString lays it out
+std::string java_double(double v) {
+    if (v == 0.0) return "0.0";
+    char buf[64];
+    int prec = 1;
+    for (; prec <= 17; ++prec) {
+        std::snprintf(buf, sizeof buf, "%.*e", prec - 1, v);
+        if (std::strtod(buf, nullptr) == v) break;
+    }
+    std::string m(buf);
+    const size_t epos = m.find('e');
+    int ex = std::atoi(m.c_str() + epos + 1);
+    std::string digits;
+    bool neg = false;
+    for (size_t i = 0; i < epos; ++i) {
+        if (m[i] == '-') neg = true;
+        else if (m[i] != '.') digits.push_back(m[i]);
+    }
+    std::string out = neg ? "-" : "";
+    if (ex >= -3 && ex < 7) {
+        if (ex >= 0) {
+            while ((int)digits.size() < ex + 2) digits.push_back('0');
+            out += digits.substr(0, ex + 1) + "." + digits.substr(ex + 1);
+        } else {
+            out += "0." + std::string(-ex - 1, '0') + digits;
+        }
+    } else {
+        out += digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : std::string("0")) + "E" + std::to_string(ex);
+    }
+    return out;
+}
+
+}  // namespace
+
+bool parse_newick(const std::string& text, const std::vector<std::string>& names, double default_len, Topology& T,
+                  std::string& err) {
+    RawTree raw;
+    if (!parse_raw(text, raw, err)) return false;
+    const int ntax = (int)names.size();
+    if (ntax < 3) {
+        err = "need at least 3 taxa";
+        return false;
+    }
+    std::unordered_map<std::string, int> index;
+    for (int i = 0; i < ntax; ++i) index[names[i]] = i;
+    T = Topology();
+    T.ntax = ntax;
+    T.nbr.assign(T.nnodes(), {-1, -1, -1});
+    T.edge.assign(T.nnodes(), {-1, -1, -1});
+    std::vector<int> deg(T.nnodes(), 0), seen(ntax, 0);
+    int next_inner = ntax;
+    bool ok = true;
+    auto connect = [&](int a, int b, double l) {
+        if (a < 0 || b < 0) return;
+        if (deg[a] >= 3 || deg[b] >= 3 || (int)T.ea.size() >= T.nedges()) {
+            ok = false;
+            return;
+        }
+        const int e = (int)T.ea.size();
+        T.ea.push_back(a);
+        T.eb.push_back(b);
+        T.len.push_back(l);
+        T.nbr[a][deg[a]] = b;
+        T.edge[a][deg[a]++] = e;
+        T.nbr[b][deg[b]] = a;
+        T.edge[b][deg[b]++] = e;
+    };
+    auto length_of = [&](const RawNode& n, bool& has) {
+        has = !n.length.empty();
+        return has ? std::strtod(n.length.c_str(), nullptr) : 0.0;
+    };
+    // returns the engine node id of raw node r (below the top)
+    std::function<int(int)> build = [&](int r) -> int {
+        const RawNode& n = raw.nodes[r];
+        if (n.kids.empty()) {
+            auto it = index.find(n.label);
+            if (it == index.end()) {
+                err = "newick: taxon '" + n.label + "' is not in the alignment";
+                ok = false;
+                return -1;
+            }
+            if (seen[it->second]++) {
+                err = "newick: taxon '" + n.label + "' appears twice";
+                ok = false;
+                return -1;
+            }
+            return it->second;
+        }
+        if (n.kids.size() != 2) {
+            err = "newick: only bifurcating trees are supported below the top node";
+            ok = false;
+            return -1;
+        }
+        if (next_inner >= T.nnodes()) {
+            ok = false;
+            return -1;
+        }
+        const int v = next_inner++;
+        for (int k : n.kids) {
+            const int c = build(k);
+            if (!ok) return -1;
+            bool has;
+            const double l = length_of(raw.nodes[k], has);
+            connect(v, c, has ? l : default_len);
+        }
+        return v;
+    };
+    const RawNode& top = raw.nodes[raw.top];
+    if (top.kids.size() == 3) {
+        const int v = next_inner++;
+        for (int k : top.kids) {
+            const int c = build(k);
+            if (!ok) break;
+            bool has;
+            const double l = length_of(raw.nodes[k], has);
+            connect(v, c, has ? l : default_len);
+        }
+    } else if (top.kids.size() == 2) {
+        const int a = build(top.kids[0]);
+        const int b = ok ? build(top.kids[1]) : -1;
+        bool ha, hb;
+        const double la = length_of(raw.nodes[top.kids[0]], ha), lb = length_of(raw.nodes[top.kids[1]], hb);
+        if (ok) connect(a, b, (ha && hb) ? la + lb : (ha ? la : (hb ? lb : default_len)));
+    } else {
+        err = "newick: top node must have 2 or 3 children";
+        return false;
+    }
+    if (!ok || next_inner != T.nnodes() || (int)T.ea.size() != T.nedges()) {
+        if (err.empty()) err = "newick: tree is not a binary tree over exactly the alignment's taxa";
+        return false;
+    }
+    for (int i = 0; i < ntax; ++i)
+        if (!seen[i]) {
+            err = "newick: taxon '" + names[i] + "' is missing from the tree";
+            return false;
+        }
+    for (double& l : T.len)
+        if (!(l >= 0.0)) l = default_len;
+    return true;
+}
+
+std::string write_newick_result(const Topology& T, const std::vector<std::string>& names) {
+    std::string out;
+    std::function<void(int, int)> sub = [&](int v, int from) {
+        if (T.is_tip(v)) {
+            out += names[v];
+            return;
+        }
+        out += "(";
+        bool first = true;
+        for (int s = 0; s < 3; ++s) {
+            if (T.nbr[v][s] == from) continue;
+            if (!first) out += ",";
+            first = false;
+            sub(T.nbr[v][s], v);
+            out += ":" + fixed20(T.len[T.edge[v][s]]);
+        }
+        out += ")";
+    };
+    const int root = T.nbr[0][0];
+    out += "(";
+    bool first = true;
+    for (int s = 0; s < 3; ++s) {
+        if (T.nbr[root][s] == 0) continue;
+        if (!first) out += ",";
+        first = false;
+        sub(T.nbr[root][s], root);
+        out += ":" + fixed20(T.len[T.edge[root][s]]);
+    }
+    out += "," + names[0] + ":" + fixed20(T.len[T.edge[0][0]]) + "):0.0;";
+    return out;
+}
+
+// =========================================================================================== traversal ======
+void ViewState::plan(const Topology& T, int v, int toward_node, std::vector<ViewOp>& ops) {
+    if (T.is_tip(v)) return;
+    const int s = T.slot_of(v, toward_node);
+    if (orient[v - T.ntax] == s) return;
+    ViewOp op{};
+    op.node = v;
+    op.toward = s;
+    int k = 0;
+    for (int q = 0; q < 3; ++q) {
+        if (q == s) continue;
+        op.child[k] = T.nbr[v][q];
+        op.cedge[k] = T.edge[v][q];
+        ++k;
+    }
+    plan(T, op.child[0], v, ops);
+    plan(T, op.child[1], v, ops);
+    ops.push_back(op);
+    orient[v - T.ntax] = s;
+}
+
+void ViewState::branch_changed(const Topology& T, int e) {
+    // walk away from the branch on both sides; a stored CLV at x (reached from y) contains the branch unless it faces y
+    std::vector<std::pair<int, int>> stack{{T.ea[e], T.eb[e]}, {T.eb[e], T.ea[e]}};
+    while (!stack.empty()) {
+        const auto [x, y] = stack.back();
+        stack.pop_back();
+        if (T.is_tip(x)) continue;
+        int& o = orient[x - T.ntax];
+        if (o >= 0 && T.nbr[x][o] != y) o = -1;
+        for (int s = 0; s < 3; ++s)
+            if (T.nbr[x][s] != y) stack.push_back({T.nbr[x][s], x});
+    }
+}
+
+// =========================================================================================== bootstrap ======
+double randum(int64_t* seed) {
+    // 36-bit multiplicative congruential generator held in limbs of 12/12/12(8) bits; multiplier limbs 1549 and 406
+    const int64_t lo = *seed & 0xFFF, mid = (*seed >> 12) & 0xFFF, hi = (*seed >> 24) & 0xFF;
+    int64_t acc = 1549 * lo;
+    const int64_t nlo = acc & 0xFFF;
+    acc = (acc >> 12) + 1549 * mid + 406 * lo;
+    const int64_t nmid = acc & 0xFFF;
+    acc = (acc >> 12) + 1549 * hi + 406 * mid;
+    const int64_t nhi = acc & 0xFF;
+    *seed = (nhi << 24) | (nmid << 12) | nlo;
+    return 0.00390625 * ((double)nhi + 0.000244140625 * ((double)nmid + 0.000244140625 * (double)nlo));
+}
+
+void bootstrap_replicates(int64_t* seed, const std::vector<int32_t>& pw, int nrep, int32_t* out) {
+    const int64_t npat = (int64_t)pw.size();
+    int64_t total = 0;
+    for (int32_t w : pw) total += w;
+    // draws land on expanded-site slots; slot -> pattern through a prefix table
+    std::vector<int64_t> slot_pat((size_t)total);
+    {
+        int64_t pos = 0;
+        for (int64_t p = 0; p < npat; ++p)
+            for (int32_t k = 0; k < pw[p]; ++k) slot_pat[pos++] = p;
+    }
+    for (int r = 0; r < nrep; ++r) {
+        int32_t* w = out + (int64_t)r * npat;
+        std::fill(w, w + npat, 0);
+        for (int64_t j = 0; j < total; ++j) {
+            const int64_t slot = (int64_t)((double)total * randum(seed));
+            ++w[slot_pat[slot]];
+        }
+    }
+}
+
+// =========================================================================================== support ========
+namespace {
+
+using Bits = std::vector<uint64_t>;
+struct BitsHash {
+    size_t operator()(const Bits& b) const {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint64_t w : b) h = (h ^ w) * 0xff51afd7ed558ccdull + (h >> 29);
+        return (size_t)h;
+    }
+};
+
+int popcount_bits(const Bits& b) {
+    int c = 0;
+    for (uint64_t w : b) c += __builtin_popcountll(w);
+    return c;
+}
+int lowest_bit(const Bits& b) {
+    for (size_t i = 0; i < b.size(); ++i)
+        if (b[i]) return (int)(i * 64 + __builtin_ctzll(b[i]));
+    return 1 << 30;
+}
+
+// canonical side of a split: the smaller one; on a tie the side holding the lowest taxon index (Bipartition.java:41-64;
+// when the given side does not own the lowest index the complement is taken, matching the `else` branch there)
+Bits canonical(const Bits& side, int ntax) {
+    Bits comp(side.size());
+    for (size_t i = 0; i < side.size(); ++i) comp[i] = ~side[i];
+    if (ntax % 64) comp.back() &= (~0ull) >> (64 - ntax % 64);
+    const int a = popcount_bits(side), b = ntax - a;
+    if (a < b) return side;
+    if (a > b) return comp;
+    return lowest_bit(side) < lowest_bit(comp) ? side : comp;
+}
+
+// PEPR's unroot (BasicTree.java:669-717): a bifurcating top is dissolved, its first non-leaf child becomes the top and
+// adopts the other child, whose branch absorbs the new top's former branch.  Returns true if the tree was rooted.
+bool unroot(RawTree& t) {
+    RawNode& top = t.nodes[t.top];
+    if (top.kids.size() != 2) return false;
+    int keep = top.kids[0], move = top.kids[1];
+    if (t.nodes[keep].kids.size() < 2) std::swap(keep, move);
+    const double sum = std::strtod(t.nodes[move].length.c_str(), nullptr) + std::strtod(t.nodes[keep].length.c_str(), nullptr);
+    if (!t.nodes[move].length.empty() || !t.nodes[keep].length.empty()) t.nodes[move].length = java_double(sum);
+    t.nodes[keep].length.clear();
+    t.nodes[keep].kids.push_back(move);
+    t.nodes[move].parent = keep;
+    t.nodes[keep].parent = -1;
+    top.kids.clear();
+    t.top = keep;
+    return true;
+}
+
+}  // namespace
+
+std::string support_tree(const std::string& main_newick, const std::vector<std::string>& trees, bool as_percent,
+                         std::vector<int32_t>* counts, std::string& err) {
+    RawTree main;
+    if (!parse_raw(main_newick, main, err)) return "";
+    unroot(main);
+    std::vector<std::string> taxa;
+    for (const RawNode& n : main.nodes)
+        if (n.kids.empty() && !n.label.empty()) taxa.push_back(n.label);
+    std::sort(taxa.begin(), taxa.end());
+    const int ntax = (int)taxa.size();
+    const size_t words = (size_t)(ntax + 63) / 64;
+    auto taxon_index = [&](const std::string& s) {
+        auto it = std::lower_bound(taxa.begin(), taxa.end(), s);
+        return (it != taxa.end() && *it == s) ? (int)(it - taxa.begin()) : -1;
+    };
+    // leaf set of every node of a tree (children before parents because ids are assigned in preorder)
+    auto leafsets = [&](const RawTree& t) {
+        std::vector<Bits> sets(t.nodes.size(), Bits(words, 0));
+        for (int v = (int)t.nodes.size() - 1; v >= 0; --v) {
+            const RawNode& n = t.nodes[v];
+            if (n.kids.empty()) {
+                const int ix = n.label.empty() ? -1 : taxon_index(n.label);
+                if (ix >= 0) sets[v][ix / 64] |= 1ull << (ix % 64);
+            }
+            for (int k : n.kids)
+                for (size_t w = 0; w < words; ++w) sets[v][w] |= sets[k][w];
+        }
+        return sets;
+    };
+    std::unordered_map<Bits, int32_t, BitsHash> tally;
+    for (const std::string& text : trees) {
+        RawTree st;
+        if (!parse_raw(text, st, err)) return "";
+        unroot(st);
+        // every node of the support tree adds its split once, the dissolved root included (it contributes the empty set),
+        // exactly as TreeSupportDecorator.java:124-140 does
+        for (const Bits& s : leafsets(st)) ++tally[canonical(s, ntax)];
+    }
+    const std::vector<Bits> msets = leafsets(main);
+    const int ntrees = (int)trees.size();
+    std::string out;
+    if (counts) counts->clear();
+    std::function<void(int)> emit = [&](int v) {
+        const RawNode& n = main.nodes[v];
+        if (n.kids.empty()) {
+            out += n.label;
+            return;
+        }
+        if (n.kids.size() > 1) out += "(";
+        for (size_t k = 0; k < n.kids.size(); ++k) {
+            if (k) out += ",";
+            emit(n.kids[k]);
+            const std::string& l = main.nodes[n.kids[k]].length;
+            if (as_percent) out += ":" + (l.empty() ? std::string("0.0") : l);
+            else out += ":" + java_double(l.empty() ? 0.0 : std::strtod(l.c_str(), nullptr));
+        }
+        if (n.kids.size() > 1) out += ")";
+        auto it = tally.find(canonical(msets[v], ntax));
+        int32_t c = it == tally.end() ? 0 : it->second;
+        if (as_percent) {
+            if (v == main.top) return;  // raxmlHPC -f b leaves the top node unlabelled
+            c = ntrees > 0 ? (int32_t)std::floor(100.0 * c / ntrees + 0.5) : 0;
+        }
+        if (counts && v != main.top) counts->push_back(c);
+        out += std::to_string(c);
+    };
+    emit(main.top);
+    out += ";";
+    return out;
+}
+
+}  // namespace pml

@@ -1,0 +1,66 @@
+// Device-side interface of the engine: every function enqueues work on `stream` and returns immediately.
+// One "PBlock" per (traversal entry, child) carries the four 20x20 transition matrices of that branch and, for tip
+// children, the 23 x 80 lookup of P applied to each residue code's indicator vector.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "model.h"
+
+namespace pml {
+
+struct PBlock {
+    double P[kCats][kStates][kStates];  // P_c(i->j)
+    double tip[kCodes][kRow];           // tip[code][c*20+i] = sum_j P_c[i][j] * indicator(code)[j]
+};
+
+// model constants in device memory, one copy per alignment (eigenvalues, V, Vinv, pi, rates)
+struct DeviceModel {
+    double lambda[kStates];
+    double V[kStates][kStates];
+    double Vinv[kStates][kStates];
+    double pi[kStates];
+    double rates[kCats];
+    double piV[kStates][kStates];   // pi_i * V[i][k]
+};
+
+// one side of a branch: an inner node's CLV (+ cumulative scaling counts) or a tip's residue codes
+struct Side {
+    const double* clv;      // nullptr for a tip
+    const int32_t* scale;   // nullptr for a tip
+    const uint8_t* codes;   // tip residue codes (0..22), nullptr for inner
+};
+
+struct NewviewOp {
+    Side left, right;
+    const PBlock* pleft;
+    const PBlock* pright;
+    double* out;
+    int32_t* out_scale;
+};
+
+// P(t) for `nblocks` branches: lengths[b] in expected substitutions per site; tips[b] != 0 also fills PBlock::tip
+void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t* d_want_tip, PBlock* d_blocks, int nblocks, cudaStream_t stream);
+
+// CLV update for np patterns (np padded rows must exist in every buffer)
+void launch_newview(const NewviewOp& op, int64_t np, cudaStream_t stream);
+
+// lnL at a branch: per-pattern lnL into site_lnl[np]; partial weighted sums -> result[0]
+void launch_evaluate(const DeviceModel* dm, const Side& a, const Side& b, const PBlock* p, const int32_t* weights, int64_t np,
+                     double* site_lnl, double* partials, double* result, cudaStream_t stream);
+
+// eigen-space product table of the two ends of a branch (np x 80) and combined scaling counts
+void launch_sumtable(const DeviceModel* dm, const Side& a, const Side& b, int64_t np, double* sumtable, int32_t* sum_scale, cudaStream_t stream);
+
+// result[0..2] = lnL, dlnL/dt, d2lnL/dt2 at branch length *d_t (device scalar) from a sumtable
+void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np, const double* d_t,
+                 double* partials, double* result, cudaStream_t stream);
+
+// lnl[r] = sum_p W[r][p] * site_lnl[p]
+void launch_replicate_lnl(const int32_t* W, int nrep, int64_t np, int64_t ldw, const double* site_lnl, double* lnl,
+                          cudaStream_t stream);
+
+int64_t reduce_partials_capacity(int64_t np);  // doubles needed in `partials`
+
+}  // namespace pml

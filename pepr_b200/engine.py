@@ -1,0 +1,303 @@
+"""ctypes binding of include/peprml.h (the same binding a JNI / Panama stub would make)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """loads pepr_b200/libpeprml.so; raises if it has not been built (python -m pepr_b200.build)"""
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, "libpeprml.so")
+        if not os.path.exists(so):
+            raise EngineError("pepr_b200/libpeprml.so is missing: run `python -m pepr_b200.build` (nvcc, sm_100a); "
+                              "there is no CPU fallback")
+        L = C.CDLL(so)
+        L.pml_version.restype = C.c_char_p
+        L.pml_last_error.restype = C.c_char_p
+        L.pml_last_error.argtypes = [C.c_void_p]
+        L.pml_aln_name.restype = C.c_char_p
+        L.pml_tree_newick.restype = C.c_int64
+        L.pml_support_tree.restype = C.c_int64
+        L.pml_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.pml_ctx_destroy.argtypes = [C.c_void_p]
+        L.pml_ctx_sync.argtypes = [C.c_void_p]
+        L.pml_aln_load.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_void_p)]
+        L.pml_aln_load_phylip.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.pml_aln_free.argtypes = [C.c_void_p]
+        L.pml_aln_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int), c_i64p, c_i64p, c_i64p]
+        L.pml_aln_patterns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pml_aln_name.argtypes = [C.c_void_p, C.c_int]
+        L.pml_model_set.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.pml_model_get.argtypes = [C.c_void_p, c_f64p, c_f64p]
+        L.pml_wag_pmatrix.argtypes = [C.c_double, C.c_double, C.c_void_p]
+        L.pml_wag_frequencies.argtypes = [C.c_void_p]
+        L.pml_gamma_rates.argtypes = [C.c_double, C.c_int, C.c_void_p]
+        L.pml_tree_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.pml_tree_free.argtypes = [C.c_void_p]
+        L.pml_tree_num_branches.argtypes = [C.c_void_p]
+        L.pml_tree_branch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p]
+        L.pml_tree_set_branch.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.pml_tree_newick.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.pml_tree_invalidate.argtypes = [C.c_void_p]
+        L.pml_tree_stats.argtypes = [C.c_void_p, c_i64p, c_i64p]
+        L.pml_evaluate.argtypes = [C.c_void_p, C.c_void_p, c_f64p, C.c_void_p]
+        L.pml_branch_derivs.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, c_f64p, c_f64p, c_f64p]
+        L.pml_optimize.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, c_f64p, c_f64p]
+        L.pml_smooth_branches.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.pml_bootstrap_weights.argtypes = [C.c_void_p, c_i64p, C.c_int, C.c_void_p]
+        L.pml_evaluate_replicates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pml_support_tree.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.pml_support_counts.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.pml_comm_unique_id.argtypes = [C.c_char_p]
+        L.pml_bootstrap_weights_host.argtypes = [C.c_void_p, C.c_int64, c_i64p, C.c_int, C.c_void_p]
+        L.pml_crunch_patterns.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
+        _LIB = L
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _weights(w):
+    return None if w is None else np.ascontiguousarray(w, np.int32)
+
+
+def unique_id():
+    buf = C.create_string_buffer(128)
+    if lib().pml_comm_unique_id(buf) != 0:
+        raise EngineError(lib().pml_last_error(None).decode())
+    return buf.raw
+
+
+class Context:
+    """one GPU + one CUDA stream (+ one NCCL rank of a site-sharded group)"""
+
+    def __init__(self, gpu=0, rank=0, nranks=1, uid=None):
+        h = C.c_void_p()
+        rc = lib().pml_ctx_create(gpu, rank, nranks, uid, C.byref(h))
+        if rc != 0:
+            raise EngineError("pml_ctx_create failed (%d): %s" % (rc, lib().pml_last_error(None).decode()))
+        self.h, self.rank, self.nranks = h, rank, nranks
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed (%d): %s" % (what, rc, lib().pml_last_error(self.h).decode()))
+
+    def sync(self):
+        self.check(lib().pml_ctx_sync(self.h), "pml_ctx_sync")
+
+    def close(self):
+        if self.h:
+            lib().pml_ctx_destroy(self.h)
+            self.h = None
+
+
+class Alignment:
+    """resident, pattern-compressed alignment; `seqs` are equal-length strings (or a uint8 [ntax, nsites] array)"""
+
+    def __init__(self, ctx, names=None, seqs=None, site_weights=None, phylip=None, weights_file=None, alpha=1.0,
+                 model="PROTGAMMAWAG"):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if phylip is not None:
+            ctx.check(lib().pml_aln_load_phylip(ctx.h, phylip.encode(), None if weights_file is None else weights_file.encode(),
+                                                C.byref(h)), "pml_aln_load_phylip")
+        else:
+            if isinstance(seqs, np.ndarray):
+                chars = np.ascontiguousarray(seqs, np.uint8)
+            else:
+                chars = np.stack([np.frombuffer(s.encode(), np.uint8) for s in seqs])
+            arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            sw = _weights(site_weights)
+            ctx.check(lib().pml_aln_load(ctx.h, chars.shape[0], chars.shape[1], arr, _ptr(chars), _ptr(sw), C.byref(h)),
+                      "pml_aln_load")
+        self.h = h
+        nt, ns, npat, nloc = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        lib().pml_aln_dims(h, C.byref(nt), C.byref(ns), C.byref(npat), C.byref(nloc))
+        self.ntax, self.nsites, self.npatterns, self.npatterns_local = nt.value, ns.value, npat.value, nloc.value
+        self.names = [lib().pml_aln_name(h, i).decode() for i in range(self.ntax)]
+        self.set_model(alpha, model)
+
+    def set_model(self, alpha, model="PROTGAMMAWAG"):
+        self.ctx.check(lib().pml_model_set(self.h, model.encode(), alpha), "pml_model_set")
+
+    @property
+    def alpha(self):
+        a = C.c_double()
+        lib().pml_model_get(self.h, C.byref(a), None)
+        return a.value
+
+    def patterns(self):
+        w = np.zeros(self.npatterns, np.int32)
+        s2p = np.zeros(self.nsites, np.int64)
+        lib().pml_aln_patterns(self.h, _ptr(w), _ptr(s2p))
+        return w, s2p
+
+    def bootstrap_weights(self, seed, nrep):
+        out = np.zeros((nrep, self.npatterns), np.int32)
+        s = C.c_int64(seed)
+        self.ctx.check(lib().pml_bootstrap_weights(self.h, C.byref(s), nrep, _ptr(out)), "pml_bootstrap_weights")
+        return out, s.value
+
+    def close(self):
+        if self.h:
+            lib().pml_aln_free(self.h)
+            self.h = None
+
+
+class Tree:
+    def __init__(self, aln, newick):
+        self.aln, self.ctx = aln, aln.ctx
+        h = C.c_void_p()
+        self.ctx.check(lib().pml_tree_load(aln.h, newick.encode(), C.byref(h)), "pml_tree_load")
+        self.h = h
+
+    @property
+    def num_branches(self):
+        return lib().pml_tree_num_branches(self.h)
+
+    def branch(self, e):
+        a, b, l = C.c_int(), C.c_int(), C.c_double()
+        self.ctx.check(lib().pml_tree_branch(self.h, e, C.byref(a), C.byref(b), C.byref(l)), "pml_tree_branch")
+        return a.value, b.value, l.value
+
+    def set_branch(self, e, length):
+        self.ctx.check(lib().pml_tree_set_branch(self.h, e, length), "pml_tree_set_branch")
+
+    def invalidate(self):
+        lib().pml_tree_invalidate(self.h)
+
+    def stats(self):
+        su = (C.c_int64 * 3)()
+        ln = C.c_int64()
+        lib().pml_tree_stats(self.h, su, C.byref(ln))
+        return list(su), ln.value
+
+    def evaluate(self, weights=None, per_site=False):
+        w = _weights(weights)
+        lnl = C.c_double()
+        ps = np.zeros(self.aln.nsites) if per_site else None
+        self.ctx.check(lib().pml_evaluate(self.h, _ptr(w), C.byref(lnl), _ptr(ps)), "pml_evaluate")
+        return (lnl.value, ps) if per_site else lnl.value
+
+    def branch_derivs(self, branch, t, weights=None):
+        w = _weights(weights)
+        l, d1, d2 = C.c_double(), C.c_double(), C.c_double()
+        self.ctx.check(lib().pml_branch_derivs(self.h, branch, t, _ptr(w), C.byref(l), C.byref(d1), C.byref(d2)),
+                       "pml_branch_derivs")
+        return l.value, d1.value, d2.value
+
+    def smooth(self, sweeps=1, weights=None):
+        w = _weights(weights)
+        conv = C.c_int()
+        self.ctx.check(lib().pml_smooth_branches(self.h, sweeps, _ptr(w), C.byref(conv)), "pml_smooth_branches")
+        return bool(conv.value)
+
+    def optimize(self, opt_alpha=True, eps=0.1, weights=None):
+        w = _weights(weights)
+        lnl, alpha = C.c_double(), C.c_double()
+        self.ctx.check(lib().pml_optimize(self.h, int(opt_alpha), eps, _ptr(w), C.byref(lnl), C.byref(alpha)), "pml_optimize")
+        return lnl.value, alpha.value
+
+    def evaluate_replicates(self, W):
+        W = np.ascontiguousarray(W, np.int32)
+        out = np.zeros(W.shape[0])
+        self.ctx.check(lib().pml_evaluate_replicates(self.h, _ptr(W), W.shape[0], _ptr(out)), "pml_evaluate_replicates")
+        return out
+
+    def newick(self):
+        n = lib().pml_tree_newick(self.h, None, 0)
+        buf = C.create_string_buffer(n)
+        lib().pml_tree_newick(self.h, buf, n)
+        return buf.value.decode()
+
+    def close(self):
+        if self.h:
+            lib().pml_tree_free(self.h)
+            self.h = None
+
+
+# ---- host-only entry points (no GPU needed) ----------------------------------------------------------------
+def wag_pmatrix(t, rate=1.0):
+    P = np.zeros((20, 20))
+    lib().pml_wag_pmatrix(t, rate, _ptr(P))
+    return P
+
+
+def wag_frequencies():
+    pi = np.zeros(20)
+    lib().pml_wag_frequencies(_ptr(pi))
+    return pi
+
+
+def gamma_rates(alpha, ncat=4):
+    r = np.zeros(ncat)
+    if lib().pml_gamma_rates(alpha, ncat, _ptr(r)) != 0:
+        raise EngineError("pml_gamma_rates: bad arguments")
+    return r
+
+
+def bootstrap_weights(pattern_weights, seed, nrep):
+    """host-only: replicate weight vectors from explicit pattern weights; returns (int32 [nrep, npat], next seed)"""
+    pw = np.ascontiguousarray(pattern_weights, np.int32)
+    out = np.zeros((nrep, len(pw)), np.int32)
+    s = C.c_int64(seed)
+    if lib().pml_bootstrap_weights_host(_ptr(pw), C.c_int64(len(pw)), C.byref(s), nrep, _ptr(out)) != 0:
+        raise EngineError("pml_bootstrap_weights_host: bad arguments")
+    return out, s.value
+
+
+def crunch_patterns(seqs, site_weights=None):
+    """host-only pattern crunch: (codes uint8 [ntax, npat], weights int32 [npat], site_to_pattern int64 [nsites])"""
+    chars = seqs if isinstance(seqs, np.ndarray) else np.stack([np.frombuffer(s.encode(), np.uint8) for s in seqs])
+    chars = np.ascontiguousarray(chars, np.uint8)
+    ntax, nsites = chars.shape
+    codes = np.zeros(ntax * nsites, np.uint8)
+    w = np.zeros(nsites, np.int32)
+    s2p = np.zeros(nsites, np.int64)
+    npat = C.c_int64()
+    sw = _weights(site_weights)
+    if lib().pml_crunch_patterns(ntax, C.c_int64(nsites), _ptr(chars), _ptr(sw), _ptr(codes), _ptr(w), _ptr(s2p), C.byref(npat)) != 0:
+        raise EngineError("pml_crunch_patterns: bad arguments")
+    n = npat.value
+    return codes[: ntax * n].reshape(ntax, n).copy(), w[:n].copy(), s2p
+
+
+def pattern_range(npatterns, rank, nranks):
+    """this rank's contiguous block of patterns: [p0, p1) -- the same split pml_aln_load applies"""
+    return npatterns * rank // nranks, npatterns * (rank + 1) // nranks
+
+
+def support_tree(main_newick, trees, as_percent=False):
+    arr = (C.c_char_p * len(trees))(*[t.encode() for t in trees])
+    n = lib().pml_support_tree(main_newick.encode(), arr, len(trees), int(as_percent), None, 0)
+    if n < 0:
+        raise EngineError("pml_support_tree: " + lib().pml_last_error(None).decode())
+    buf = C.create_string_buffer(n)
+    lib().pml_support_tree(main_newick.encode(), arr, len(trees), int(as_percent), buf, n)
+    return buf.value.decode()
+
+
+def support_counts(main_newick, trees):
+    arr = (C.c_char_p * len(trees))(*[t.encode() for t in trees])
+    n = C.c_int()
+    if lib().pml_support_counts(main_newick.encode(), arr, len(trees), None, C.byref(n)) != 0:
+        raise EngineError("pml_support_counts: " + lib().pml_last_error(None).decode())
+    out = np.zeros(n.value, np.int32)
+    lib().pml_support_counts(main_newick.encode(), arr, len(trees), _ptr(out), C.byref(n))
+    return out

@@ -1,0 +1,162 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the reference binary's golden outputs.
+Tolerances: FP64 mode, total lnL relative error <= 1e-6 against raxmlHPC (BASELINE.json north_star); against the oracle
+(same arithmetic, different summation order) we hold 1e-10 relative; integer paths are bit exact."""
+import numpy as np
+import pytest
+
+import pepr_b200 as pb
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+REL_REF = 1e-6      # vs raxmlHPC (north_star tolerance)
+REL_ORACLE = 1e-10  # vs the oracle restatement
+
+
+def _load(gpu_ctx, g, alpha, newick, site_weights=None):
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, site_weights=site_weights, alpha=alpha)
+    return aln, pb.Tree(aln, newick)
+
+
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide"])
+def test_lnl_matches_reference_and_oracle(gpu_ctx, golden, case):
+    g = golden(case)
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    assert aln.npatterns == fe["patterns"]
+    lnl = tree.evaluate()
+    ref = orc.evaluate(orc.Model(), orc.Tree(fe["tree"], g.names), g.pat, g.w, fe["alpha"])
+    assert abs(lnl - fe["lnl"]) / abs(fe["lnl"]) < REL_REF
+    assert abs(lnl - ref) / abs(ref) < REL_ORACLE
+    tree.close(); aln.close()
+
+
+def test_per_site_lnl_in_original_column_order(gpu_ctx, golden):
+    g = golden("small")
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    lnl, ps = tree.evaluate(per_site=True)
+    assert np.abs(ps - np.array(g.meta["fg"]["per_site"])).max() < 2e-6      # raxmlHPC prints 6 decimals
+    _, pp = orc.evaluate(orc.Model(), orc.Tree(fe["tree"], g.names), g.pat, g.w, fe["alpha"], per_pattern=True)
+    assert np.abs(ps - pp[g.s2p]).max() < 1e-10
+    assert abs(ps.sum() - lnl) < 1e-8
+    tree.close(); aln.close()
+
+
+def test_column_weights(gpu_ctx, golden):
+    g = golden("small")
+    fw = g.meta["fw"]
+    aln, tree = _load(gpu_ctx, g, fw["alpha"], fw["tree"], site_weights=np.array(fw["weights"], np.int32))
+    assert aln.npatterns == fw["patterns"]
+    assert abs(tree.evaluate() - fw["lnl"]) / abs(fw["lnl"]) < REL_REF
+    tree.close(); aln.close()
+
+
+def test_replicate_weight_vectors(gpu_ctx, golden):
+    g = golden("small")
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    W, seed = aln.bootstrap_weights(g.meta["fj"]["seed"], 3)
+    assert W.tolist() == g.meta["fj"]["replicate_weights"]                  # bit exact with raxmlHPC -f j
+    _, pp = orc.evaluate(orc.Model(), orc.Tree(fe["tree"], g.names), g.pat, g.w, fe["alpha"], per_pattern=True)
+    want = W.astype(np.float64) @ pp
+    got = tree.evaluate_replicates(W)
+    assert np.abs(got - want).max() / np.abs(want).max() < REL_ORACLE
+    for r in range(3):                                                      # the one-vector entry point agrees
+        assert abs(tree.evaluate(weights=W[r]) - want[r]) / abs(want[r]) < REL_ORACLE
+    tree.close(); aln.close()
+
+
+def test_lnl_independent_of_traversal_state(gpu_ctx, golden):
+    """partial traversals after branch edits must give what a full traversal gives"""
+    g = golden("wide")
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    base = tree.evaluate()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        e = int(rng.integers(0, tree.num_branches))
+        _, _, l = tree.branch(e)
+        tree.set_branch(e, l * 1.7 + 0.01)
+        tree.branch_derivs(int(rng.integers(0, tree.num_branches)), 0.1)   # re-orients CLVs somewhere else
+        partial = tree.evaluate()
+        tree.invalidate()
+        full = tree.evaluate()
+        assert abs(partial - full) <= 1e-9 * abs(full)
+        tree.set_branch(e, l)
+    assert abs(tree.evaluate() - base) <= 1e-9 * abs(base)
+    tree.close(); aln.close()
+
+
+@pytest.mark.parametrize("case,edges", [("small", [0, 3, 7, 12]), ("deep", [0, 10, 100, 316])])
+def test_branch_derivatives_match_oracle(gpu_ctx, golden, case, edges):
+    g = golden(case)
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    ot = orc.Tree(fe["tree"], g.names)
+    m = orc.Model()
+    # branch numbering differs between the two parsers: match branches by their end nodes' leaf sets via lengths
+    olen = {round(ot.get_bl(e), 15): e for e in range(ot.nedge)}
+    for e in edges:
+        a, b, l = tree.branch(e)
+        oe = olen[round(l, 15)]
+        for t in (l, 0.5 * l + 0.01, 2.0 * l + 0.05):
+            got = tree.branch_derivs(e, t)
+            want = orc.branch_derivs(m, ot, g.pat, g.w, fe["alpha"], oe, t)
+            assert abs(got[0] - want[0]) <= 1e-10 * abs(want[0])
+            assert abs(got[1] - want[1]) <= 1e-8 * max(1.0, abs(want[1]))
+            assert abs(got[2] - want[2]) <= 1e-8 * max(1.0, abs(want[2]))
+    tree.close(); aln.close()
+
+
+@pytest.mark.parametrize("case", ["small", "dup", "deep"])
+def test_optimize_reaches_reference_optimum(gpu_ctx, golden, case):
+    """`-f e` from the unoptimised input tree: raxmlHPC stops at dlnL <= 0.1, so that is the comparison tolerance."""
+    g = golden(case)
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, 1.0, g.meta["tree_in"])
+    lnl, alpha = tree.optimize(opt_alpha=True, eps=0.1)
+    assert lnl > fe["lnl"] - 0.1, (lnl, fe["lnl"])
+    assert abs(lnl - fe["lnl"]) < 0.5
+    assert abs(alpha - fe["alpha"]) / fe["alpha"] < 0.05
+    # the optimised tree scores the same on the oracle (engine result is self-consistent)
+    ot = orc.Tree(tree.newick().replace("):0.0;", ");"), g.names)
+    chk = orc.evaluate(orc.Model(), ot, g.pat, g.w, alpha)
+    assert abs(chk - lnl) / abs(lnl) < 1e-9
+    tree.close(); aln.close()
+
+
+def test_optimize_wide_matches_reference(gpu_ctx, golden):
+    g = golden("wide")
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, 1.0, g.meta["tree_in"])
+    lnl, alpha = tree.optimize(opt_alpha=True, eps=0.1)
+    assert lnl > fe["lnl"] - 0.1 and abs(lnl - fe["lnl"]) < 0.5, (lnl, fe["lnl"])
+    assert abs(alpha - fe["alpha"]) / fe["alpha"] < 0.02
+    tree.close(); aln.close()
+
+
+def test_errors_are_reported_not_swallowed(gpu_ctx, golden):
+    g = golden("small")
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs)
+    with pytest.raises(pb.EngineError, match="not in the alignment"):
+        pb.Tree(aln, "((TaxA,Nope),(TaxC,TaxD),((TaxE,TaxF),(TaxG,TaxH)));")
+    with pytest.raises(pb.EngineError, match="missing from the tree|binary tree"):
+        pb.Tree(aln, "((TaxA,TaxB),(TaxC,TaxD),(TaxE,TaxF));")
+    with pytest.raises(pb.EngineError, match="PROTGAMMAWAG"):
+        aln.set_model(1.0, "GTRGAMMA")
+    aln.close()
+
+
+def test_ragged_pattern_counts(gpu_ctx, golden):
+    """pattern counts that are not multiples of the tile height, down to a single column"""
+    g = golden("small")
+    fe = g.meta["fe"]
+    m = orc.Model()
+    for ncol in (1, 31, 33, 129, 257):
+        seqs = [s[:ncol] for s in g.seqs]
+        pat, w, _ = orc.compress(orc.encode(seqs))
+        aln = pb.Alignment(gpu_ctx, g.names, seqs, alpha=fe["alpha"])
+        tree = pb.Tree(aln, fe["tree"])
+        want = orc.evaluate(m, orc.Tree(fe["tree"], g.names), pat, w, fe["alpha"])
+        assert abs(tree.evaluate() - want) <= 1e-10 * abs(want)
+        tree.close(); aln.close()

@@ -1,0 +1,117 @@
+"""Host-side logic of the engine (no GPU): model construction, pattern crunch, bootstrap stream, support counting,
+newick handling, and the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pepr_b200 as pb
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "peprml.h")).read()
+    names = set(re.findall(r"\b(pml_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    L = ctypes.CDLL(os.path.join(ROOT, "pepr_b200", "libpeprml.so"))
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_context_creation_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pb.EngineError, match="no CPU path"):
+        pb.Context(0)
+
+
+def test_transition_matrices_match_oracle():
+    m = orc.Model()
+    for t, r in [(1e-6, 1.0), (0.05, 0.137), (0.37, 1.3), (2.5, 2.386), (34.0, 4.0)]:
+        P = pb.wag_pmatrix(t, r)
+        assert np.abs(P - m.pmatrix(t, r)).max() < 1e-13
+        assert np.abs(P.sum(1) - 1).max() < 1e-12
+    pi = pb.wag_frequencies()
+    assert abs(pi.sum() - 1.0) < 1e-12
+    P = pb.wag_pmatrix(0.3, 1.0)
+    assert np.abs(pi[:, None] * P - (pi[:, None] * P).T).max() < 1e-14   # detailed balance
+
+
+def test_gamma_rates_match_oracle_and_have_mean_one():
+    for a in (0.02, 0.155636, 0.5, 1.0, 3.705783, 142.7, 1000.0):
+        r = pb.gamma_rates(a)
+        assert np.abs(r - orc.gamma_rates(a)).max() < 1e-11
+        assert abs(r.mean() - 1.0) < 1e-12
+        assert (np.diff(r) > 0).all()
+
+
+@pytest.mark.parametrize("case", ["small", "dup", "wide"])
+def test_pattern_crunch_matches_oracle_and_reference_count(golden, case):
+    g = golden(case)
+    codes, w, s2p = pb.crunch_patterns(g.seqs)
+    assert codes.shape[1] == g.meta["fe"]["patterns"]
+    assert (codes == g.pat).all() and (w == g.w).all() and (s2p == g.s2p).all()
+    assert w.sum() == len(g.seqs[0])
+
+
+def test_pattern_crunch_with_column_weights(golden):
+    g = golden("small")
+    sw = np.array(g.meta["fw"]["weights"], np.int32)
+    codes, w, s2p = pb.crunch_patterns(g.seqs, sw)
+    c2, w2, s2 = orc.compress(g.codes, sw)
+    assert codes.shape[1] == g.meta["fw"]["patterns"]
+    assert (codes == c2).all() and (w == w2).all() and (s2p == s2).all()
+    assert (s2p[sw == 0] == -1).all()
+
+
+def test_bootstrap_weights_bit_exact_with_reference(golden):
+    g = golden("small")
+    fj = g.meta["fj"]
+    w, seed = pb.bootstrap_weights(g.w, fj["seed"], 3)
+    assert w.tolist() == fj["replicate_weights"]
+    # the stream continues across calls exactly like consecutive replicates of one run
+    w1, s1 = pb.bootstrap_weights(g.w, fj["seed"], 1)
+    w2, s2 = pb.bootstrap_weights(g.w, s1, 2)
+    assert (np.vstack([w1, w2]) == w).all() and s2 == seed
+    assert (w.sum(1) == g.w.sum()).all()
+
+
+def test_bootstrap_stream_matches_oracle_on_weighted_patterns(golden):
+    g = golden("dup")
+    a, sa = pb.bootstrap_weights(g.w, 977, 5)
+    b, sb = orc.bootstrap_weights(977, g.w, 5)
+    assert (a == b).all() and sa == sb
+
+
+def test_support_tree_matches_oracle_counts_and_raxml_percent(golden):
+    from tests.test_oracle_golden import _labels
+    g = golden("small")
+    main, sup = g.meta["fe"]["tree"], g.meta["fb"]["support_trees"]
+    counts = orc.support_counts(main, sup)
+    got = _labels(pb.support_tree(main, sup, as_percent=False))
+    assert got == {k: v for k, v in counts.items()}
+    pct = _labels(pb.support_tree(main, sup, as_percent=True))
+    assert pct == _labels(g.meta["fb"]["bipartitions"])
+    assert sorted(pb.support_counts(main, sup).tolist()) == sorted(counts.values())
+
+
+def test_support_tree_top_label_and_rooted_inputs():
+    main = "((A:0.1,B:0.2):0.05,(C:0.3,D:0.4):0.05,E:0.1);"
+    sup = ["((A,B),(C,D),E);", "(((A,B),E),(C,D));", "((A,C),(B,D),E);"]
+    s = pb.support_tree(main, sup)
+    # every inner node is labelled with a raw count; rooted support trees add their dissolved root to the tally of the
+    # empty split, exactly as TreeSupportDecorator does (3 trees + 1 rooted one = 4 at the top)
+    assert s == "((A:0.1,B:0.2)2:0.05,(C:0.3,D:0.4)2:0.05,E:0.1)4;"
+    assert pb.support_counts(main, sup).tolist() == [2, 2]
+
+
+def test_support_tie_break_uses_lowest_taxon_index():
+    # 4 taxa: {A,B}|{C,D} has equal sides; both spellings must hit the same canonical split
+    main = "((A:1.0,B:1.0):1.0,C:1.0,D:1.0);"
+    sup = ["((C,D),A,B);", "((A,B),C,D);", "((A,C),B,D);"]
+    assert pb.support_counts(main, sup).tolist() == [2]
