@@ -102,6 +102,19 @@ int pml_tree_invalidate(pml_tree *);
 /* counters since tree creation: CLV site-updates by case (0 tip-tip, 1 tip-inner, 2 inner-inner) and kernel launches */
 int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_launches);
 
+/* ---- device-side timing of the engine's own kernels (CUDA events on the context's stream) -------------------
+ * Between begin and end every launch of kind k is bracketed by a pair of events; end() synchronises and returns, per
+ * kind, the summed device milliseconds, the launch count and the pattern rows processed.
+ * kinds: 0 newview tip-tip, 1 newview tip-inner, 2 newview inner-inner, 3 evaluate, 4 sumtable, 5 NR core. */
+#define PML_NKINDS 6
+int pml_profile_begin(pml_ctx *);
+int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
+
+/* stopwatch on the context's stream: start records an event, stop records another, synchronises and returns the
+ * device milliseconds in between (host control flow between the two is included, as it should be for a step time) */
+int pml_timer_start(pml_ctx *);
+int pml_timer_stop(pml_ctx *, double *ms);
+
 /* ---- Newton-Raphson branch-length derivatives (sumGAMMAPROT + coreGTRGAMMAPROT) ----------------------------
  * lnL and d lnL/dt, d2 lnL/dt2 of `branch` at length t (other parameters fixed). */
 int pml_branch_derivs(pml_tree *, int branch, double t, const int32_t *weights, double *lnl, double *d1, double *d2);

@@ -66,6 +66,26 @@ struct pml_ctx {
     uint8_t* h_stage = nullptr;
     size_t stage_cap = 0, stage_used = 0;
     double* h_result = nullptr;
+    // optional per-launch device timing (pml_profile_begin/end)
+    struct Timed { int kind; int64_t rows; cudaEvent_t t0, t1; };
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    bool profiling = false;
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> spare_events;
+    cudaEvent_t event() {
+        cudaEvent_t e;
+        if (!spare_events.empty()) { e = spare_events.back(); spare_events.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    int tick(int kind, int64_t rows) {  // call before a launch; returns index for tock()
+        if (!profiling) return -1;
+        Timed t{kind, rows, event(), event()};
+        cudaEventRecord(t.t0, stream);
+        timed.push_back(t);
+        return (int)timed.size() - 1;
+    }
+    void tock(int idx) { if (idx >= 0) cudaEventRecord(timed[idx].t1, stream); }
 
     bool cuda(cudaError_t e, const char* what) {
         if (e == cudaSuccess) return true;
@@ -211,9 +231,11 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
             nv.pright = t->d_pblocks + 2 * i + 1;
             nv.out = t->clv(op.node);
             nv.out_scale = t->scale(op.node);
-            launch_newview(nv, a->npad, c->stream);
-            ++t->launches;
             const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+            const int tk = c->tick(2 - ntip, a->nloc);
+            launch_newview(nv, a->npad, c->stream);
+            c->tock(tk);
+            ++t->launches;
             t->site_updates[2 - ntip] += a->nloc;
         }
     }
@@ -266,7 +288,9 @@ int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
     if (!orient_branch(t, e, x, y)) return PML_ENODEVICE;
     PBlock* pb = single_pblock(t, t->topo.len[e]);
     if (!pb) return PML_ENODEVICE;
+    const int tk = c->tick(3, a->nloc);
     launch_evaluate(a->d_model, t->side(x), t->side(y), pb, dw, a->npad, a->d_site_lnl, a->d_partials, a->d_result, c->stream);
+    c->tock(tk);
     t->launches += 2;
     if (!c->cuda(cudaGetLastError(), "evaluate kernel")) return PML_ENODEVICE;
     if (!c->allreduce(a->d_result, 1)) return PML_ECOMM;
@@ -285,7 +309,9 @@ bool prepare_branch(pml_tree* t, int e) {
     if (!ensure_sumtable(a)) return false;
     int x, y;
     if (!orient_branch(t, e, x, y)) return false;
+    const int tk = a->ctx->tick(4, a->nloc);
     launch_sumtable(a->d_model, t->side(x), t->side(y), a->npad, a->d_sumtable, a->d_sumscale, a->ctx->stream);
+    a->ctx->tock(tk);
     ++t->launches;
     t->prepared_branch = e;
     return a->ctx->cuda(cudaGetLastError(), "sumtable kernel");
@@ -299,7 +325,9 @@ bool core_at(pml_tree* t, const int32_t* dw, double len, double out[3]) {
     if (!h) return false;
     h[0] = len;
     if (!c->cuda(cudaMemcpyAsync(a->d_scalar, h, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload")) return false;
+    const int tk = c->tick(5, a->nloc);
     launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, a->d_scalar, a->d_partials, a->d_result, c->stream);
+    c->tock(tk);
     t->launches += 2;
     if (!c->cuda(cudaGetLastError(), "core kernel")) return false;
     if (!c->allreduce(a->d_result, 3)) return false;
@@ -528,6 +556,8 @@ void pml_ctx_destroy(pml_ctx* c) {
     }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
+    for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
+    for (auto e : c->spare_events) cudaEventDestroy(e);
     delete c;
 }
 
@@ -536,6 +566,53 @@ const char* pml_last_error(const pml_ctx* c) { return c ? c->err.c_str() : g_cre
 int pml_ctx_sync(pml_ctx* c) {
     if (!c) return PML_EINVAL;
     return c->bind() && c->sync() ? PML_OK : PML_ENODEVICE;
+}
+
+int pml_timer_start(pml_ctx* c) {
+    if (!c || !c->bind()) return PML_EINVAL;
+    if (!c->timer0) { cudaEventCreate(&c->timer0); cudaEventCreate(&c->timer1); }
+    return c->cuda(cudaEventRecord(c->timer0, c->stream), "timer start") ? PML_OK : PML_ENODEVICE;
+}
+
+int pml_timer_stop(pml_ctx* c, double* ms) {
+    if (!c || !ms || !c->timer0 || !c->bind()) return PML_EINVAL;
+    float f = 0.f;
+    if (!c->cuda(cudaEventRecord(c->timer1, c->stream), "timer stop") || !c->cuda(cudaEventSynchronize(c->timer1), "timer sync") ||
+        !c->cuda(cudaEventElapsedTime(&f, c->timer0, c->timer1), "timer read"))
+        return PML_ENODEVICE;
+    *ms = f;
+    return PML_OK;
+}
+
+int pml_profile_begin(pml_ctx* c) {
+    if (!c) return PML_EINVAL;
+    if (!c->bind() || !c->sync()) return PML_ENODEVICE;
+    for (auto& t : c->timed) { c->spare_events.push_back(t.t0); c->spare_events.push_back(t.t1); }
+    c->timed.clear();
+    c->profiling = true;
+    return PML_OK;
+}
+
+int pml_profile_end(pml_ctx* c, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]) {
+    if (!c) return PML_EINVAL;
+    c->profiling = false;
+    if (!c->bind() || !c->sync()) return PML_ENODEVICE;
+    for (int k = 0; k < PML_NKINDS; ++k) {
+        if (ms) ms[k] = 0.0;
+        if (launches) launches[k] = 0;
+        if (rows) rows[k] = 0;
+    }
+    for (auto& t : c->timed) {
+        float f = 0.f;
+        cudaEventElapsedTime(&f, t.t0, t.t1);
+        if (ms) ms[t.kind] += f;
+        if (launches) ++launches[t.kind];
+        if (rows) rows[t.kind] += t.rows;
+        c->spare_events.push_back(t.t0);
+        c->spare_events.push_back(t.t1);
+    }
+    c->timed.clear();
+    return PML_OK;
 }
 
 int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names, const uint8_t* chars,

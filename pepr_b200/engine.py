@@ -63,6 +63,10 @@ def lib():
         L.pml_support_tree.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.pml_support_counts.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.pml_comm_unique_id.argtypes = [C.c_char_p]
+        L.pml_profile_begin.argtypes = [C.c_void_p]
+        L.pml_timer_start.argtypes = [C.c_void_p]
+        L.pml_timer_stop.argtypes = [C.c_void_p, c_f64p]
+        L.pml_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pml_bootstrap_weights_host.argtypes = [C.c_void_p, C.c_int64, c_i64p, C.c_int, C.c_void_p]
         L.pml_crunch_patterns.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
         _LIB = L
@@ -100,6 +104,26 @@ class Context:
 
     def sync(self):
         self.check(lib().pml_ctx_sync(self.h), "pml_ctx_sync")
+
+    def timer_start(self):
+        self.check(lib().pml_timer_start(self.h), "pml_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self.check(lib().pml_timer_stop(self.h, C.byref(ms)), "pml_timer_stop")
+        return ms.value
+
+    def profile_begin(self):
+        self.check(lib().pml_profile_begin(self.h), "pml_profile_begin")
+
+    def profile_end(self):
+        """-> dict kind -> (device ms, launches, pattern rows)"""
+        ms = (C.c_double * 6)()
+        n = (C.c_int64 * 6)()
+        rows = (C.c_int64 * 6)()
+        self.check(lib().pml_profile_end(self.h, ms, n, rows), "pml_profile_end")
+        kinds = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "sumtable", "core"]
+        return {k: (ms[i], n[i], rows[i]) for i, k in enumerate(kinds)}
 
     def close(self):
         if self.h:

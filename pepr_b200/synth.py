@@ -11,6 +11,55 @@ import numpy as np
 
 AA = "ARNDCQEGHILKMFPSTWYV"
 
+# WAG exchangeabilities (PAML wag.dat x100, lower triangle) and the fixed 3-decimal frequencies; the generator carries its
+# own copy so that neither the engine nor the oracle is needed to produce benchmark input.
+_WAG = """55.1571 50.9848 63.5346 73.8998 14.7304 542.942 102.704 52.8191 26.5256 3.02949 90.8598 303.55 154.364 61.6783
+9.88179 158.285 43.9157 94.7198 617.416 2.1352 546.947 141.672 58.4665 112.556 86.5584 30.6674 33.0052 56.7717 31.6954
+213.715 395.629 93.0676 24.8972 429.411 57.0025 24.941 19.3335 18.6979 55.4236 3.9437 17.0135 11.3917 12.7395 3.04501
+13.819 39.7915 49.7671 13.1528 8.48047 38.4287 86.9489 15.4263 6.13037 49.9462 317.097 90.6265 535.142 301.201 47.9855
+7.40339 389.49 258.443 37.3558 89.0432 32.3832 25.7555 89.3496 68.3162 19.8221 10.3754 39.0482 154.526 31.5124 17.41
+40.4141 425.746 485.402 93.4276 21.0494 10.2711 9.61621 4.67304 39.802 9.99208 8.11339 4.9931 67.9371 105.947 211.517
+8.8836 119.063 143.855 67.9489 19.5081 42.3984 10.9404 93.3372 68.2355 24.357 69.6198 9.99288 41.5844 55.6896 17.1329
+16.1444 337.079 122.419 397.423 107.176 140.766 102.887 70.4939 134.182 74.0169 31.944 34.4739 96.713 49.3905 54.5931
+161.328 212.111 55.4413 203.006 37.4866 51.2984 85.7928 82.2765 22.5833 47.3307 145.816 32.6622 138.698 151.612 17.1903
+79.5384 437.802 11.3133 116.392 7.19167 12.9767 71.707 21.5737 15.6557 33.6983 26.2569 21.2483 66.5309 13.7505 51.5706
+152.964 13.9405 52.3742 11.0864 24.0735 38.1533 108.6 32.5711 54.3833 22.771 19.6303 10.3604 387.344 42.017 39.8618
+13.3264 42.8437 645.428 21.6046 78.6993 29.1148 248.539 200.601 25.1849 19.6246 15.2335 100.214 30.1281 58.8731 18.7247
+11.8358 782.13 180.034 30.5434 205.845 64.9892 31.4887 23.2739 138.823 36.5369 31.473"""
+WAG_PI = np.array([0.087, 0.044, 0.039, 0.057, 0.019, 0.037, 0.058, 0.083, 0.024, 0.049,
+                   0.086, 0.062, 0.020, 0.038, 0.046, 0.070, 0.061, 0.014, 0.035, 0.071])
+
+
+class WagModel:
+    """numpy-only WAG+Gamma4 used to SIMULATE data (not to score it)"""
+
+    def __init__(self, alpha=1.0, ncat=4):
+        from scipy.special import gammainc
+        from scipy.stats import gamma as G
+        S = np.zeros((20, 20))
+        S[np.tril_indices(20, -1)] = np.array(_WAG.split(), float)
+        S = S + S.T
+        Q = S * WAG_PI[None, :]
+        np.fill_diagonal(Q, 0.0)
+        np.fill_diagonal(Q, -Q.sum(1))
+        Q /= -(WAG_PI * np.diag(Q)).sum()
+        sq = np.sqrt(WAG_PI)
+        A = (sq[:, None] * Q) / sq[None, :]
+        self.lam, U = np.linalg.eigh(0.5 * (A + A.T))
+        self.V, self.Vi = U / sq[:, None], U.T * sq[None, :]
+        self.pi = WAG_PI
+        b = G.ppf(np.arange(1, ncat) / ncat, alpha, scale=1.0 / alpha)
+        c = np.concatenate([[0.0], gammainc(alpha + 1.0, b * alpha), [1.0]])
+        self.rates = np.diff(c) * ncat
+
+    def pmatrix(self, t, rate=1.0):
+        return (self.V * np.exp(self.lam * rate * t)) @ self.Vi
+
+
+def simulate_wag(ntax, nsites, seed, alpha=1.0, missing_frac=0.0):
+    m = WagModel(alpha)
+    return simulate(ntax, nsites, seed, m.pmatrix, m.rates, m.pi, missing_frac=missing_frac)
+
 
 def random_tree(ntax, rng, mean_bl=0.08, min_bl=0.005):
     """returns (newick string with lengths, nested structure) ; taxa are named T0000.."""
