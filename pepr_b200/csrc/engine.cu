@@ -58,7 +58,8 @@ NcclApi g_nccl;
 }  // namespace
 
 struct pml_ctx {
-    int device = 0, rank = 0, nranks = 1;
+    int device = 0, rank = 0, nranks = 1, sms = 148;
+    bool scalar_newview = false;  // PML_NEWVIEW=scalar: debugging aid, selects the one-thread-per-(pattern,category) kernel
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
     std::string err;
@@ -233,7 +234,8 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
             nv.out_scale = t->scale(op.node);
             const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
             const int tk = c->tick(2 - ntip, a->nloc);
-            launch_newview(nv, a->npad, c->stream);
+            if (c->scalar_newview) launch_newview(nv, a->npad, c->stream);
+            else launch_newview_mma(nv, a->npad, c->sms, c->stream);
             c->tock(tk);
             ++t->launches;
             t->site_updates[2 - ntip] += a->nloc;
@@ -529,6 +531,9 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     c->nranks = nranks;
     if (!c->bind() || !c->cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create"))
         return fail(nullptr, PML_ENODEVICE, c->err);
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, gpu_id);
+    configure_mma_kernels();
+    if (const char* e = getenv("PML_NEWVIEW")) c->scalar_newview = std::strcmp(e, "scalar") == 0;
     c->stage_cap = 1 << 20;
     if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
         !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc"))

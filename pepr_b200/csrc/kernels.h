@@ -46,6 +46,11 @@ void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t
 // CLV update for np patterns (np padded rows must exist in every buffer)
 void launch_newview(const NewviewOp& op, int64_t np, cudaStream_t stream);
 
+// the same update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 32
+void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream);
+// raises the dynamic shared-memory limit of the tensor-path kernels on the current device (once per context)
+void configure_mma_kernels();
+
 // lnL at a branch: per-pattern lnL into site_lnl[np]; partial weighted sums -> result[0]
 void launch_evaluate(const DeviceModel* dm, const Side& a, const Side& b, const PBlock* p, const int32_t* weights, int64_t np,
                      double* site_lnl, double* partials, double* result, cudaStream_t stream);
