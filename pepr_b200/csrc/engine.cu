@@ -59,7 +59,6 @@ NcclApi g_nccl;
 
 struct pml_ctx {
     int device = 0, rank = 0, nranks = 1, sms = 148;
-    bool scalar_newview = false;  // PML_NEWVIEW=scalar: debugging aid, selects the one-thread-per-(pattern,category) kernel
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
     std::string err;
@@ -234,32 +233,13 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
             nv.out_scale = t->scale(op.node);
             const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
             const int tk = c->tick(2 - ntip, a->nloc);
-            if (c->scalar_newview) launch_newview(nv, a->npad, c->stream);
-            else launch_newview_mma(nv, a->npad, c->sms, c->stream);
+            launch_newview_mma(nv, a->npad, c->sms, c->stream);
             c->tock(tk);
             ++t->launches;
             t->site_updates[2 - ntip] += a->nloc;
         }
     }
     return c->cuda(cudaGetLastError(), "CLV kernels");
-}
-
-// one extra P block (slot after the batch area) for the branch a likelihood is evaluated on
-PBlock* single_pblock(pml_tree* t, double len) {
-    pml_ctx* c = t->aln->ctx;
-    auto* hl = (double*)c->stage(sizeof(double) + 8);
-    if (!hl) return nullptr;
-    hl[0] = len;
-    ((uint8_t*)(hl + 1))[0] = 0;
-    double* dl = t->d_lengths + 2 * kOpsPerBatch;
-    uint8_t* dt = t->d_wanttip + 2 * kOpsPerBatch;
-    if (!c->cuda(cudaMemcpyAsync(dl, hl, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload") ||
-        !c->cuda(cudaMemcpyAsync(dt, hl + 1, 1, cudaMemcpyHostToDevice, c->stream), "flag upload"))
-        return nullptr;
-    PBlock* pb = t->d_pblocks + 2 * kOpsPerBatch;
-    launch_make_p(t->aln->d_model, dl, dt, pb, 1, c->stream);
-    ++t->launches;
-    return pb;
 }
 
 // brings both ends of branch e up to date; (a, b) is returned with b inner and a the tip end if there is one
@@ -281,22 +261,12 @@ bool fetch_result(pml_ctx* c, const double* d_result, int n, double* out) {
     return true;
 }
 
-int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
-    pml_aln* a = t->aln;
+bool upload_scalar(pml_aln* a, double v) {
     pml_ctx* c = a->ctx;
-    const int32_t* dw = device_weights(a, weights);
-    if (!dw) return PML_ENODEVICE;
-    int x, y;
-    if (!orient_branch(t, e, x, y)) return PML_ENODEVICE;
-    PBlock* pb = single_pblock(t, t->topo.len[e]);
-    if (!pb) return PML_ENODEVICE;
-    const int tk = c->tick(3, a->nloc);
-    launch_evaluate(a->d_model, t->side(x), t->side(y), pb, dw, a->npad, a->d_site_lnl, a->d_partials, a->d_result, c->stream);
-    c->tock(tk);
-    t->launches += 2;
-    if (!c->cuda(cudaGetLastError(), "evaluate kernel")) return PML_ENODEVICE;
-    if (!c->allreduce(a->d_result, 1)) return PML_ECOMM;
-    return fetch_result(c, a->d_result, 1, lnl) ? PML_OK : PML_ENODEVICE;
+    auto* h = (double*)c->stage(sizeof(double));
+    if (!h) return false;
+    h[0] = v;
+    return c->cuda(cudaMemcpyAsync(a->d_scalar, h, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload");
 }
 
 bool ensure_sumtable(pml_aln* a) {
@@ -306,27 +276,51 @@ bool ensure_sumtable(pml_aln* a) {
            c->cuda(cudaMalloc(&a->d_sumscale, sizeof(int32_t) * a->npad), "sumtable scale alloc");
 }
 
-bool prepare_branch(pml_tree* t, int e) {
+// One pass over the two CLVs at the ends of branch e: out = {lnL, dlnL/dt, d2lnL/dt2} at length len, summed over ranks.
+// keep_table stores the eigen-space product table so that further lengths can be tried without re-reading the CLVs;
+// site_lnl fills the per-pattern lnL buffer (root evaluate).
+bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, double out[3]) {
     pml_aln* a = t->aln;
-    if (!ensure_sumtable(a)) return false;
+    pml_ctx* c = a->ctx;
+    if (keep_table && !ensure_sumtable(a)) return false;
     int x, y;
     if (!orient_branch(t, e, x, y)) return false;
-    const int tk = a->ctx->tick(4, a->nloc);
-    launch_sumtable(a->d_model, t->side(x), t->side(y), a->npad, a->d_sumtable, a->d_sumscale, a->ctx->stream);
-    a->ctx->tock(tk);
-    ++t->launches;
-    t->prepared_branch = e;
-    return a->ctx->cuda(cudaGetLastError(), "sumtable kernel");
+    if (!upload_scalar(a, len)) return false;
+    BranchArgs args{};
+    args.a = t->side(x);
+    args.b = t->side(y);
+    args.dm = a->d_model;
+    args.weights = dw;
+    args.d_t = a->d_scalar;
+    args.site_lnl = site_lnl ? a->d_site_lnl : nullptr;
+    args.sumtable = keep_table ? a->d_sumtable : nullptr;
+    args.sum_scale = keep_table ? a->d_sumscale : nullptr;
+    args.partials = a->d_partials;
+    const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
+    const int grid = launch_branch_mma(args, a->npad, c->sms, c->stream);
+    c->tock(tk);
+    launch_reduce(a->d_partials, grid, 3, a->d_result, c->stream);
+    t->launches += 2;
+    t->prepared_branch = keep_table ? e : -1;
+    if (!c->cuda(cudaGetLastError(), "branch kernel")) return false;
+    if (!c->allreduce(a->d_result, 3)) return false;
+    return fetch_result(c, a->d_result, 3, out);
 }
 
-// lnL, dlnL/dt, d2lnL/dt2 of the prepared branch at length len
+int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
+    const int32_t* dw = device_weights(t->aln, weights);
+    if (!dw) return PML_ENODEVICE;
+    double r[3];
+    if (!branch_pass(t, e, dw, t->topo.len[e], false, true, r)) return t->aln->ctx->err.rfind("nccl", 0) == 0 ? PML_ECOMM : PML_ENODEVICE;
+    *lnl = r[0];
+    return PML_OK;
+}
+
+// lnL, dlnL/dt, d2lnL/dt2 of the branch whose product table is resident, at length len
 bool core_at(pml_tree* t, const int32_t* dw, double len, double out[3]) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
-    auto* h = (double*)c->stage(sizeof(double));
-    if (!h) return false;
-    h[0] = len;
-    if (!c->cuda(cudaMemcpyAsync(a->d_scalar, h, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload")) return false;
+    if (!upload_scalar(a, len)) return false;
     const int tk = c->tick(5, a->nloc);
     launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, a->d_scalar, a->d_partials, a->d_result, c->stream);
     c->tock(tk);
@@ -346,7 +340,9 @@ void set_branch(pml_tree* t, int e, double len) {
 // guarded Newton-Raphson on z = exp(-t) in log z, constants and control flow of raxmlHPC topLevelMakenewz:
 // bad curvature -> z = 0.37 z + 0.63; step z *= exp(-d1/d2) when that exponent is < 100; cap z <= 0.25 zprev + 0.75
 bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z_out) {
-    if (!prepare_branch(t, e)) return false;
+    // a single NR step needs the CLVs once and no product table; longer iterations keep the table and re-use it
+    const bool keep = maxiter > 1;
+    bool first = true;
     double z = std::exp(-t->topo.len[e]);
     z = std::min(std::max(z, kZmin), kZmax);
     double zprev = z, zstep = 0.0;
@@ -359,7 +355,10 @@ bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z
         }
         z = std::min(std::max(z, kZmin), kZmax);
         double r[3];
-        if (!core_at(t, dw, -std::log(z), r)) return false;
+        if (first || !keep) {
+            if (!branch_pass(t, e, dw, -std::log(z), keep, false, r)) return false;
+        } else if (!core_at(t, dw, -std::log(z), r)) return false;
+        first = false;
         const double d1 = -r[1], d2 = r[2];  // derivatives in lz = log z = -t
         if (d2 >= 0.0 && z < kZmax) zprev = z = 0.37 * z + 0.63;
         else curvature_ok = true;
@@ -533,7 +532,7 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
         return fail(nullptr, PML_ENODEVICE, c->err);
     cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, gpu_id);
     configure_mma_kernels();
-    if (const char* e = getenv("PML_NEWVIEW")) c->scalar_newview = std::strcmp(e, "scalar") == 0;
+    configure_branch_kernels();
     c->stage_cap = 1 << 20;
     if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
         !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc"))
@@ -849,9 +848,10 @@ int pml_branch_derivs(pml_tree* t, int branch, double len, const int32_t* weight
     if (!c->bind()) return PML_ENODEVICE;
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
-    if (t->prepared_branch != branch && !prepare_branch(t, branch)) return PML_ENODEVICE;
     double r[3];
-    if (!core_at(t, dw, len, r)) return PML_ENODEVICE;
+    if (t->prepared_branch != branch) {
+        if (!branch_pass(t, branch, dw, len, true, false, r)) return PML_ENODEVICE;
+    } else if (!core_at(t, dw, len, r)) return PML_ENODEVICE;
     if (lnl) *lnl = r[0];
     if (d1) *d1 = r[1];
     if (d2) *d2 = r[2];

@@ -43,20 +43,27 @@ struct NewviewOp {
 // P(t) for `nblocks` branches: lengths[b] in expected substitutions per site; tips[b] != 0 also fills PBlock::tip
 void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t* d_want_tip, PBlock* d_blocks, int nblocks, cudaStream_t stream);
 
-// CLV update for np patterns (np padded rows must exist in every buffer)
-void launch_newview(const NewviewOp& op, int64_t np, cudaStream_t stream);
-
-// the same update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 32
+// CLV update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 64 and all buffers hold np rows
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream);
 // raises the dynamic shared-memory limit of the tensor-path kernels on the current device (once per context)
 void configure_mma_kernels();
 
-// lnL at a branch: per-pattern lnL into site_lnl[np]; partial weighted sums -> result[0]
-void launch_evaluate(const DeviceModel* dm, const Side& a, const Side& b, const PBlock* p, const int32_t* weights, int64_t np,
-                     double* site_lnl, double* partials, double* result, cudaStream_t stream);
-
-// eigen-space product table of the two ends of a branch (np x 80) and combined scaling counts
-void launch_sumtable(const DeviceModel* dm, const Side& a, const Side& b, int64_t np, double* sumtable, int32_t* sum_scale, cudaStream_t stream);
+// One pass over the two ends of a branch (b inner, a inner or tip): lnL, dlnL/dt, d2lnL/dt2 at length *d_t as CTA partials
+// (+ per-pattern lnL when site_lnl != nullptr, + the eigen-space product table when sumtable != nullptr).
+struct BranchArgs {
+    Side a, b;
+    const DeviceModel* dm;
+    const int32_t* weights;
+    const double* d_t;
+    double* site_lnl;     // optional
+    double* sumtable;     // optional: np x 80
+    int32_t* sum_scale;   // with sumtable
+    double* partials;     // 3 x grid doubles
+};
+int launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
+void configure_branch_kernels();
+// fixed-order sum of `nblocks` partials for each of `nvals` values
+void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream);
 
 // result[0..2] = lnL, dlnL/dt, d2lnL/dt2 at branch length *d_t (device scalar) from a sumtable
 void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np, const double* d_t,

@@ -1,0 +1,107 @@
+// Shared device helpers of the tensor-path kernels: mbarrier / TMA bulk-copy wrappers, the DMMA m8n8k4 wrapper and the
+// fragment conventions (which state a lane feeds into which k-tile).
+//
+// CLV layout in HBM ("blocked"): patterns are grouped in blocks of 8 rows; one block is 640 contiguous doubles laid out
+// [category c][chunk], where the chunks of a category are  states 0-7 as 8 rows x 8,  states 8-15 as 8 rows x 8,
+// states 16-19 as 8 rows x 4  (160 doubles per category).  With lane = 4*g + t (g = row in block) this makes
+//   - a 16-row tile one contiguous 10,240 B piece: ONE TMA bulk copy per child and stage, no row padding;
+//   - the A-fragment reads (states {2t,2t+1}, {8+2t,9+2t}, {16+t}) two 128-bit and one 64-bit shared-memory loads whose
+//     32 lanes touch consecutive addresses -> conflict free;
+//   - the D-fragment writes (states nt*8+2t+{0,1}) 128-bit stores to consecutive addresses -> fully coalesced.
+// Only the engine's own kernels ever read CLVs, so the layout is private to this directory.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.h"
+
+namespace pml {
+namespace mma {
+
+constexpr int kTileRows = 16;                // patterns per pipeline stage (one stage = one group iteration)
+constexpr int kBlockRows = 8;                // rows of one layout block = rows of one MMA m-tile
+constexpr int kBlockDoubles = kBlockRows * kRow;  // 640
+constexpr int kCatDoubles = kBlockRows * kStates; // 160
+constexpr int kTileDoubles = kTileRows * kRow;    // one child's share of a stage
+constexpr int kTipPad = 82;                  // doubles per padded tip-table row
+constexpr int kGroups = 3;                   // independent groups of 4 warps (one warp per rate category)
+constexpr int kDepth = 3;                    // stages in each group's private ring
+constexpr int kComputeWarps = 4 * kGroups;
+constexpr int kThreadsMma = kComputeWarps * 32;  // 384: no dedicated producer warp, the register budget stays at 168
+constexpr double kTwo256 = 1.157920892373161954235709850086879078532699846656405640394575840079131296399e77;
+constexpr double kMinLik = 8.636168555094444625386351862800399571116000364436281385023703470168591803162e-78;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// TMA engine bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// state index that lane t feeds into k-tile kt: pairs of k-tiles share one 128-bit shared-memory load
+__device__ __forceinline__ int kmap(int kt, int t) { return kt < 4 ? (kt >> 1) * 8 + 2 * t + (kt & 1) : 16 + t; }
+
+// B fragments of P_c^T for one child: frag[nt][kt] = P_c[nt*8 + g][kmap(kt, t)] (0 beyond state 19)
+__device__ __forceinline__ void load_p_fragments(const PBlock* pb, int c, int g, int t, double (&frag)[3][5]) {
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+        const int i = nt * 8 + g;
+#pragma unroll
+        for (int kt = 0; kt < 5; ++kt) frag[nt][kt] = i < kStates ? pb->P[c][i][kmap(kt, t)] : 0.0;
+    }
+}
+
+// A fragments of one 8-row block: the lane's five state values x[row g][c][kmap(kt, t)]
+struct AFrag {
+    double v[5];
+};
+__device__ __forceinline__ AFrag load_a(const double* block, int c, int lane) {
+    const double* x = block + c * kCatDoubles;
+    const double2 a01 = reinterpret_cast<const double2*>(x)[lane];
+    const double2 a23 = reinterpret_cast<const double2*>(x + 64)[lane];
+    AFrag f;
+    f.v[0] = a01.x;
+    f.v[1] = a01.y;
+    f.v[2] = a23.x;
+    f.v[3] = a23.y;
+    f.v[4] = x[128 + lane];
+    return f;
+}
+// D fragments (states nt*8 + 2t + {0,1}; nt = 2 only for t < 2) of one 8-row block back into the blocked layout
+__device__ __forceinline__ void store_d(double* block, int c, int lane, const double (&d)[3][2]) {
+    double* x = block + c * kCatDoubles;
+    reinterpret_cast<double2*>(x)[lane] = make_double2(d[0][0], d[0][1]);
+    reinterpret_cast<double2*>(x + 64)[lane] = make_double2(d[1][0], d[1][1]);
+    if ((lane & 3) < 2) *reinterpret_cast<double2*>(x + 128 + (lane >> 2) * 4 + 2 * (lane & 3)) = make_double2(d[2][0], d[2][1]);
+}
+
+}  // namespace mma
+}  // namespace pml
