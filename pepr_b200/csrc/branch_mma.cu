@@ -125,14 +125,14 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
             code[0] = args.a.codes[row0 + g];
             code[1] = args.a.codes[row0 + 8 + g];
         }
-        int32_t sc[2] = {0, 0};
-        double w[2] = {0.0, 0.0};
+        // per-row integers are only needed after the MMAs: issue the loads now, consume them at the end
+        int32_t sca[2] = {0, 0}, scb[2] = {0, 0}, wi[2] = {0, 0};
         if (c == 0 && t == 0) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                sc[m] = args.b.scale[row0 + m * 8 + g];
-                if (!kTipA) sc[m] += args.a.scale[row0 + m * 8 + g];
-                w[m] = (double)args.weights[row0 + m * 8 + g];
+                scb[m] = __ldg(args.b.scale + row0 + m * 8 + g);
+                if (!kTipA) sca[m] = __ldg(args.a.scale + row0 + m * 8 + g);
+                wi[m] = __ldg(args.weights + row0 + m * 8 + g);
             }
         }
         mbar_wait(gfull + slot, (it / kDepth) & 1);
@@ -214,13 +214,14 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
                     f1 += src[1];
                     f2 += src[2];
                 }
-                const double inv = 1.0 / f, q = f1 * inv;
-                const double l = log(0.25 * f) + sc[m] * kLogMinLik;
+                const double inv = 1.0 / f, q = f1 * inv, w = (double)wi[m];
+                const int32_t sc = sca[m] + scb[m];
+                const double l = log(0.25 * f) + sc * kLogMinLik;
                 if (args.site_lnl) args.site_lnl[row0 + r] = l;
-                if (kStore) args.sum_scale[row0 + r] = sc[m];
-                sum_l = fma(w[m], l, sum_l);
-                sum_d1 = fma(w[m], q, sum_d1);
-                sum_d2 = fma(w[m], f2 * inv - q * q, sum_d2);
+                if (kStore) args.sum_scale[row0 + r] = sc;
+                sum_l = fma(w, l, sum_l);
+                sum_d1 = fma(w, q, sum_d1);
+                sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
             }
         }
     }

@@ -31,6 +31,7 @@ constexpr int kComputeWarps = 4 * kGroups;
 constexpr int kThreadsMma = kComputeWarps * 32;  // 384: no dedicated producer warp, the register budget stays at 168
 constexpr double kTwo256 = 1.157920892373161954235709850086879078532699846656405640394575840079131296399e77;
 constexpr double kMinLik = 8.636168555094444625386351862800399571116000364436281385023703470168591803162e-78;
+constexpr int kMinLikHi = 0x2FF00000;        // high word of 2^-256 (biased exponent 1023 - 256 = 0x2FF, mantissa 0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_tip = reinterpret_cast<double*>(smem_raw + 128);
-    double* s_max = s_tip + Plan::kTipDoubles;
-    double* s_stage = s_max + Plan::kMaxDoubles;
+    int* s_max = reinterpret_cast<int*>(s_tip + Plan::kTipDoubles);
+    double* s_stage = s_tip + Plan::kTipDoubles + Plan::kMaxDoubles;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -111,12 +111,13 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
             code[0] = codes[row0 + g];
             code[1] = codes[row0 + 8 + g];
         }
-        int32_t sc[2] = {0, 0};
+        // the children's scaling counts are only needed after the MMAs: issue the loads now, consume them at the end
+        int32_t scl[2] = {0, 0}, scr[2] = {0, 0};
         if (c == 0 && t == 0) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                if (!kTipL) sc[m] += op.left.scale[row0 + m * 8 + g];
-                if (!kTipR) sc[m] += op.right.scale[row0 + m * 8 + g];
+                if (!kTipL) scl[m] = __ldg(op.left.scale + row0 + m * 8 + g);
+                if (!kTipR) scr[m] = __ldg(op.right.scale + row0 + m * 8 + g);
             }
         }
         mbar_wait(gfull + slot, (it / kDepth) & 1);
@@ -148,18 +149,20 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                     if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
                 }
         // per-row magnitude over this category's 20 states, then over the four categories through shared memory
-        double* mx = s_max + (((it & 1) * kGroups + grp) * kCats) * kTileRows;
+        // magnitudes are compared through the high word of |x| on the integer pipe (2^-256 has a zero low word, so
+        // "|x| < 2^-256" is exactly "hi(|x|) < hi(2^-256)"): the FP64 pipe is left to the MMAs
+        int* mx = s_max + (((it & 1) * kGroups + grp) * kCats) * kTileRows;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            double big = 0.0;
+            int big = 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
                 accL[m][nt][0] *= accR[m][nt][0];
                 accL[m][nt][1] *= accR[m][nt][1];
-                if (nt < 2 || t < 2) big = fmax(big, fmax(fabs(accL[m][nt][0]), fabs(accL[m][nt][1])));
+                if (nt < 2 || t < 2) big = max(big, max(__double2hiint(accL[m][nt][0]) & 0x7fffffff, __double2hiint(accL[m][nt][1]) & 0x7fffffff));
             }
-            big = fmax(big, __shfl_xor_sync(0xffffffffu, big, 1));
-            big = fmax(big, __shfl_xor_sync(0xffffffffu, big, 2));
+            big = max(big, __shfl_xor_sync(0xffffffffu, big, 1));
+            big = max(big, __shfl_xor_sync(0xffffffffu, big, 2));
             if (t == 0) mx[c * kTileRows + m * 8 + g] = big;
         }
         named_barrier(1 + grp, 4 * 32);
@@ -168,8 +171,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             const int r = m * 8 + g;
-            const double big = fmax(fmax(mx[r], mx[kTileRows + r]), fmax(mx[2 * kTileRows + r], mx[3 * kTileRows + r]));
-            const bool rescale = big < kMinLik;
+            const int big = max(max(mx[r], mx[kTileRows + r]), max(mx[2 * kTileRows + r], mx[3 * kTileRows + r]));
+            const bool rescale = big < kMinLikHi;
             if (rescale) {
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt) {
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                 }
             }
             store_d(op.out + (size_t)tile * kTileDoubles + m * kBlockDoubles, c, lane, accL[m]);
-            if (c == 0 && t == 0) op.out_scale[row0 + r] = sc[m] + (rescale ? 1 : 0);
+            if (c == 0 && t == 0) op.out_scale[row0 + r] = scl[m] + scr[m] + (rescale ? 1 : 0);
         }
     }
 }
