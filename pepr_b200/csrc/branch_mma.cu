@@ -30,7 +30,7 @@ struct BranchPlan {
     static constexpr int kStageDoubles = kInner * kTileDoubles;
     static constexpr int kTipDoubles = kTipA ? kCodes * kTipVecPad : 0;
     static constexpr int kRedDoubles = 2 * kGroups * kCats * kTileRows * 3;  // [parity][group][cat][row][f,f1,f2]
-    static constexpr int kFinalDoubles = 16;
+    static constexpr int kFinalDoubles = 3 * kComputeWarps + 4;
     static constexpr size_t kBytes = 128 + sizeof(double) * (size_t)(kTipDoubles + kRedDoubles + kFinalDoubles + kStages * kStageDoubles);
 };
 
@@ -114,26 +114,29 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
                 e2[nt][j] = a * a * e;
             }
     }
-    double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;  // only lanes with c == 0 && t == 0 accumulate
+    double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;  // lanes 0-3 of every warp accumulate
 
+    int next_code[2] = {0, 0};
+    if (kTipA && first < ntiles) {
+        next_code[0] = __ldg(args.a.codes + (int64_t)first * kTileRows + g);
+        next_code[1] = __ldg(args.a.codes + (int64_t)first * kTileRows + 8 + g);
+    }
     int it = 0;
     for (int tile = first; tile < ntiles; tile += stride, ++it) {
         const int slot = it % kDepth;
         const int64_t row0 = (int64_t)tile * kTileRows;
-        int code[2] = {0, 0};
-        if (kTipA) {
-            code[0] = args.a.codes[row0 + g];
-            code[1] = args.a.codes[row0 + 8 + g];
+        int code[2] = {next_code[0], next_code[1]};
+        if (kTipA && tile + stride < ntiles) {  // the codes of the following tile travel while this one is computed
+            next_code[0] = __ldg(args.a.codes + row0 + (int64_t)stride * kTileRows + g);
+            next_code[1] = __ldg(args.a.codes + row0 + (int64_t)stride * kTileRows + 8 + g);
         }
         // per-row integers are only needed after the MMAs: issue the loads now, consume them at the end
-        int32_t sca[2] = {0, 0}, scb[2] = {0, 0}, wi[2] = {0, 0};
-        if (c == 0 && t == 0) {
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                scb[m] = __ldg(args.b.scale + row0 + m * 8 + g);
-                if (!kTipA) sca[m] = __ldg(args.a.scale + row0 + m * 8 + g);
-                wi[m] = __ldg(args.weights + row0 + m * 8 + g);
-            }
+        // the four warps of a group share the per-row finish: warp c closes rows 4c .. 4c+3 with its lanes 0-3
+        int32_t sca = 0, scb = 0, wi = 0;
+        if (lane < 4) {
+            scb = __ldg(args.b.scale + row0 + c * 4 + lane);
+            if (!kTipA) sca = __ldg(args.a.scale + row0 + c * 4 + lane);
+            wi = __ldg(args.weights + row0 + c * 4 + lane);
         }
         mbar_wait(gfull + slot, (it / kDepth) & 1);
         const double* stage = gstage + (size_t)slot * Plan::kStageDoubles;
@@ -202,45 +205,42 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
         }
         named_barrier(1 + grp, 4 * 32);
         if (c == 0 && tile + kDepth * stride < ntiles) refill(tile + kDepth * stride, slot);
-        if (c == 0 && t == 0) {
+        if (lane < 4) {
+            const int r = c * 4 + lane;
+            double f = 0.0, f1 = 0.0, f2 = 0.0;
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const int r = m * 8 + g;
-                double f = 0.0, f1 = 0.0, f2 = 0.0;
-#pragma unroll
-                for (int cc = 0; cc < kCats; ++cc) {
-                    const double* src = red + (cc * kTileRows + r) * 3;
-                    f += src[0];
-                    f1 += src[1];
-                    f2 += src[2];
-                }
-                const double inv = 1.0 / f, q = f1 * inv, w = (double)wi[m];
-                const int32_t sc = sca[m] + scb[m];
-                const double l = log(0.25 * f) + sc * kLogMinLik;
-                if (args.site_lnl) args.site_lnl[row0 + r] = l;
-                if (kStore) args.sum_scale[row0 + r] = sc;
-                sum_l = fma(w, l, sum_l);
-                sum_d1 = fma(w, q, sum_d1);
-                sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
+            for (int cc = 0; cc < kCats; ++cc) {
+                const double* src = red + (cc * kTileRows + r) * 3;
+                f += src[0];
+                f1 += src[1];
+                f2 += src[2];
             }
+            const double inv = 1.0 / f, q = f1 * inv, w = (double)wi;
+            const int32_t sc = sca + scb;
+            const double l = log(0.25 * f) + sc * kLogMinLik;
+            if (args.site_lnl) args.site_lnl[row0 + r] = l;
+            if (kStore) args.sum_scale[row0 + r] = sc;
+            sum_l = fma(w, l, sum_l);
+            sum_d1 = fma(w, q, sum_d1);
+            sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
         }
     }
-    // CTA partials in a fixed order: warp shuffle, then the three category-0 warps through shared memory
+    // CTA partials in a fixed order: lanes 0-3 by shuffle, then the twelve warps through shared memory
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 2; o > 0; o >>= 1) {
         sum_l += __shfl_xor_sync(0xffffffffu, sum_l, o);
         sum_d1 += __shfl_xor_sync(0xffffffffu, sum_d1, o);
         sum_d2 += __shfl_xor_sync(0xffffffffu, sum_d2, o);
     }
-    if (c == 0 && lane == 0) {
-        s_final[grp * 3 + 0] = sum_l;
-        s_final[grp * 3 + 1] = sum_d1;
-        s_final[grp * 3 + 2] = sum_d2;
+    if (lane == 0) {
+        s_final[warp * 3 + 0] = sum_l;
+        s_final[warp * 3 + 1] = sum_d1;
+        s_final[warp * 3 + 2] = sum_d2;
     }
     named_barrier(8, kComputeWarps * 32);
     if (threadIdx.x < 3) {
         double v = 0.0;
-        for (int k = 0; k < kGroups; ++k) v += s_final[k * 3 + threadIdx.x];
+        for (int k = 0; k < kComputeWarps; ++k) v += s_final[k * 3 + threadIdx.x];
         args.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
     }
 }

@@ -454,7 +454,8 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
     }
     double lo = std::min(xa, xc), hi = std::max(xa, xc), x = xb, w = xb, v = xb, fx = fb, fw = fb, fv = fb, d = 0.0, e = 0.0;
     for (int it = 0; ok && it < 100; ++it) {
-        const double mid = 0.5 * (lo + hi), tol1 = tol * std::fabs(x) + 1e-10, tol2 = 2.0 * tol1;
+        // absolute tolerance on log(alpha): a relative one degenerates when alpha is close to 1 (log alpha close to 0)
+        const double mid = 0.5 * (lo + hi), tol1 = tol, tol2 = 2.0 * tol1;
         if (std::fabs(x - mid) <= tol2 - 0.5 * (hi - lo)) break;
         bool golden = true;
         if (std::fabs(e) > tol1) {
@@ -887,7 +888,7 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
         cur = best;
         if (!tree_evaluate(t, weights, dw, 0.0625, &best)) return PML_ENODEVICE;
         if (opt_alpha) {
-            if (!optimise_alpha(t, weights, 1.0e-4, &best)) return PML_ENODEVICE;
+            if (!optimise_alpha(t, weights, 1.0e-3, &best)) return PML_ENODEVICE;
         }
         if (!tree_evaluate(t, weights, dw, 0.1, &best)) return PML_ENODEVICE;
     } while (std::fabs(cur - best) > eps && ++rounds < 200);

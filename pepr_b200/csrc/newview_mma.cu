@@ -100,16 +100,22 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
     if (!kTipL) load_p_fragments(op.pleft, c, g, t, fragL);
     if (!kTipR) load_p_fragments(op.pright, c, g, t, fragR);
 
+    int next_code[2] = {0, 0};
+    if ((kTipL || kTipR) && first < ntiles) {
+        const uint8_t* codes = kTipL ? op.left.codes : op.right.codes;
+        next_code[0] = __ldg(codes + (int64_t)first * kTileRows + g);
+        next_code[1] = __ldg(codes + (int64_t)first * kTileRows + 8 + g);
+    }
     int it = 0;
     for (int tile = first; tile < ntiles; tile += stride, ++it) {
         const int slot = it % kDepth;
         const int64_t row0 = (int64_t)tile * kTileRows;
         // small global reads first so that their latency hides behind the wait for the stage
-        int code[2] = {0, 0};
-        if (kTipL || kTipR) {
+        int code[2] = {next_code[0], next_code[1]};
+        if ((kTipL || kTipR) && tile + stride < ntiles) {  // the codes of the following tile travel while this one is computed
             const uint8_t* codes = kTipL ? op.left.codes : op.right.codes;
-            code[0] = codes[row0 + g];
-            code[1] = codes[row0 + 8 + g];
+            next_code[0] = __ldg(codes + row0 + (int64_t)stride * kTileRows + g);
+            next_code[1] = __ldg(codes + row0 + (int64_t)stride * kTileRows + 8 + g);
         }
         // the children's scaling counts are only needed after the MMAs: issue the loads now, consume them at the end
         int32_t scl[2] = {0, 0}, scr[2] = {0, 0};
@@ -191,63 +197,92 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
 // Whether a (code, code) pair needs the x2^256 rescale is decided once per CTA for all 529 pairs; the streaming loop
 // then has no cross-thread traffic and its stores are fully coalesced (consecutive threads, consecutive 16 B).
 constexpr int kTipTipThreads = 256;
-constexpr int kTipTipRows = 64;
-__global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op, int ntiles) {
+constexpr int kTipTipRows = 128;  // one CTA per 128-row tile; many small CTAs per SM hide the code-load latency
+__global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op) {
     __shared__ __align__(16) double s_l[kCodes * kRow];
     __shared__ __align__(16) double s_r[kCodes * kRow];
+    __shared__ double s_maxl[kCodes], s_maxr[kCodes];
+    __shared__ int s_argl[kCodes];
     __shared__ uint8_t s_flag[kCodes * kCodes];
-    __shared__ uint8_t s_pair[2][kTipTipRows][2];
+    __shared__ uint8_t s_pair[kTipTipRows][2];
+    const int64_t row0 = (int64_t)blockIdx.x * kTipTipRows;
+    // the residue codes of the tile are requested first; the table set-up below hides their latency
+    uint8_t my_l = 0, my_r = 0;
+    if (threadIdx.x < kTipTipRows) {
+        my_l = __ldg(op.left.codes + row0 + threadIdx.x);
+        my_r = __ldg(op.right.codes + row0 + threadIdx.x);
+    }
     for (int i = threadIdx.x; i < kCodes * kRow; i += kTipTipThreads) {
         s_l[i] = (&op.pleft->tip[0][0])[i];
         s_r[i] = (&op.pright->tip[0][0])[i];
     }
     __syncthreads();
-    for (int pair = threadIdx.x; pair < kCodes * kCodes; pair += kTipTipThreads) {
-        const double* a = s_l + (pair / kCodes) * kRow;
-        const double* b = s_r + (pair % kCodes) * kRow;
+    // row maxima of both lookups bound every product: max_l * max_r from above, l[arg] * r[arg] from below
+    if (threadIdx.x < 2 * kCodes) {
+        const bool right = threadIdx.x >= kCodes;
+        const int code = threadIdx.x - (right ? kCodes : 0);
+        const double* row = (right ? s_r : s_l) + code * kRow;
         double big = 0.0;
+        int arg = 0;
         for (int i = 0; i < kRow; ++i) {
-            const int k = (i + threadIdx.x) % kRow;  // rotate so that the lanes of a warp hit different banks
-            big = fmax(big, fabs(a[k] * b[k]));
-        }
-        s_flag[pair] = big < kMinLik ? 1 : 0;
-    }
-    int buf = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-        const int64_t row0 = (int64_t)tile * kTipTipRows;
-        if (threadIdx.x < kTipTipRows) {
-            s_pair[buf][threadIdx.x][0] = op.left.codes[row0 + threadIdx.x];
-            s_pair[buf][threadIdx.x][1] = op.right.codes[row0 + threadIdx.x];
-        }
-        __syncthreads();
-        double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
-#pragma unroll 2
-        for (int q = threadIdx.x; q < kTipTipRows * (kRow / 2); q += kTipTipThreads) {
-            // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
-            const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
-            const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
-            int g, st;
-            if (u < 64) {
-                g = (u & 31) >> 2;
-                st = (u >> 5) * 8 + (u & 3) * 2;
-            } else {
-                g = (u - 64) >> 1;
-                st = 16 + ((u - 64) & 1) * 2;
+            const int k = (i + threadIdx.x) % kRow;
+            if (fabs(row[k]) > big) {
+                big = fabs(row[k]);
+                arg = k;
             }
-            const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
-            const int cl = s_pair[buf][r][0], cr = s_pair[buf][r][1];
-            const double2 a = reinterpret_cast<const double2*>(s_l + cl * kRow)[k];
-            const double2 b = reinterpret_cast<const double2*>(s_r + cr * kRow)[k];
-            double2 v = make_double2(a.x * b.x, a.y * b.y);
-            if (s_flag[cl * kCodes + cr]) {
-                v.x *= kTwo256;
-                v.y *= kTwo256;
-            }
-            out[q] = v;
         }
-        if (threadIdx.x < kTipTipRows)
-            op.out_scale[row0 + threadIdx.x] = s_flag[s_pair[buf][threadIdx.x][0] * kCodes + s_pair[buf][threadIdx.x][1]];
+        if (right) s_maxr[code] = big;
+        else {
+            s_maxl[code] = big;
+            s_argl[code] = arg;
+        }
     }
+    __syncthreads();
+    for (int pair = threadIdx.x; pair < kCodes * kCodes; pair += kTipTipThreads) {
+        const int cl = pair / kCodes, cr = pair % kCodes;
+        const double* a = s_l + cl * kRow;
+        const double* b = s_r + cr * kRow;
+        uint8_t flag;
+        if (s_maxl[cl] * s_maxr[cr] < kMinLik) flag = 1;                               // every product is below 2^-256
+        else if (fabs(a[s_argl[cl]] * b[s_argl[cl]]) >= kMinLik) flag = 0;            // one product is certainly not
+        else {                                                                         // undecided: test all 80
+            double big = 0.0;
+            for (int i = 0; i < kRow; ++i) big = fmax(big, fabs(a[i] * b[i]));
+            flag = big < kMinLik ? 1 : 0;
+        }
+        s_flag[pair] = flag;
+    }
+    if (threadIdx.x < kTipTipRows) {
+        s_pair[threadIdx.x][0] = my_l;
+        s_pair[threadIdx.x][1] = my_r;
+    }
+    __syncthreads();
+    double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
+#pragma unroll 4
+    for (int q = threadIdx.x; q < kTipTipRows * (kRow / 2); q += kTipTipThreads) {
+        // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
+        const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
+        const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
+        int g, st;
+        if (u < 64) {
+            g = (u & 31) >> 2;
+            st = (u >> 5) * 8 + (u & 3) * 2;
+        } else {
+            g = (u - 64) >> 1;
+            st = 16 + ((u - 64) & 1) * 2;
+        }
+        const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
+        const int cl = s_pair[r][0], cr = s_pair[r][1];
+        const double2 a = reinterpret_cast<const double2*>(s_l + cl * kRow)[k];
+        const double2 b = reinterpret_cast<const double2*>(s_r + cr * kRow)[k];
+        double2 v = make_double2(a.x * b.x, a.y * b.y);
+        if (s_flag[cl * kCodes + cr]) {
+            v.x *= kTwo256;
+            v.y *= kTwo256;
+        }
+        out[q] = v;
+    }
+    if (threadIdx.x < kTipTipRows) op.out_scale[row0 + threadIdx.x] = s_flag[my_l * kCodes + my_r];
 }
 
 template <bool kTipL, bool kTipR>
@@ -266,13 +301,11 @@ void configure_mma_kernels() {
     cudaFuncSetAttribute(k_newview_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<false, false>::kBytes);
 }
 
-// np must be a multiple of 64 (the engine pads pattern rows to 128)
+// np must be a multiple of 128 (the engine pads pattern rows to 128)
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
     const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr;
     if (tl && tr) {
-        const int ntiles = (int)(np / kTipTipRows);
-        const int grid = ntiles < 3 * sms ? ntiles : 3 * sms;
-        k_newview_tiptip<<<grid, kTipTipThreads, 0, stream>>>(op, ntiles);
+        k_newview_tiptip<<<(int)(np / kTipTipRows), kTipTipThreads, 0, stream>>>(op);
     } else if (tl) launch_one<true, false>(op, np, sms, stream);
     else if (tr) launch_one<false, true>(op, np, sms, stream);
     else launch_one<false, false>(op, np, sms, stream);
