@@ -146,7 +146,7 @@ def reference_arm(args):
         for i in range(total):
             r = run_raxml(names, sseqs, topo, cores, tmp, "r%d" % i)
             if r is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/raxmlHPC-PTHREADS missing or failed"}))
+                emit({"impl": "reference", "unavailable": "oracle/_ref/raxmlHPC-PTHREADS missing or failed"})
                 return 0
             last = r
             if i >= args.warmup:
@@ -159,7 +159,7 @@ def reference_arm(args):
     value = per_pat * last["patterns"] / t
     desc = "first %d of %d columns of the 100-taxon workload, raxmlHPC-PTHREADS -T %d -f e; effective site-updates = %s" % (
         sample, SITES_PER_GPU, cores, how)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -167,11 +167,20 @@ def reference_arm(args):
                    "sample_sites": sample, "patterns": last["patterns"], "effective": True},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "lnl": last["lnl"]}))
+        "lnl": last["lnl"]})
     return 0
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def emit(obj):
+    """the ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's version banner) was sent to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,7 +379,7 @@ def main():
                 a.close()
             else:
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
-        print(json.dumps(out))
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -13,6 +13,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/peprml.h"
@@ -86,6 +87,49 @@ struct pml_ctx {
         return (int)timed.size() - 1;
     }
     void tock(int idx) { if (idx >= 0) cudaEventRecord(timed[idx].t1, stream); }
+
+    // Device blocks released by pml_aln_free / pml_tree_free stay cached in the context: PEPR calls the runner once per tree
+    // (hundreds of times per refinement round), and a fresh cudaMalloc of a multi-GB CLV arena costs ~100 ms each time.
+    std::vector<std::pair<size_t, void*>> cached_blocks;
+    template <typename T>
+    cudaError_t dev_alloc(T** out, size_t bytes) {
+        bytes = (bytes + 511) & ~size_t(511);
+        size_t best = cached_blocks.size();
+        for (size_t i = 0; i < cached_blocks.size(); ++i)
+            if (cached_blocks[i].first >= bytes && cached_blocks[i].first <= bytes + bytes / 4 + 4096 &&
+                (best == cached_blocks.size() || cached_blocks[i].first < cached_blocks[best].first))
+                best = i;
+        if (best != cached_blocks.size()) {
+            *out = (T*)cached_blocks[best].second;
+            sizes[(void*)*out] = cached_blocks[best].first;
+            cached_blocks.erase(cached_blocks.begin() + best);
+            return cudaSuccess;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess && !cached_blocks.empty()) {  // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            for (auto& b : cached_blocks) cudaFree(b.second);
+            cached_blocks.clear();
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e == cudaSuccess) {
+            *out = (T*)p;
+            sizes[p] = bytes;
+        }
+        return e;
+    }
+    void dev_free(void* p) {
+        if (!p) return;
+        auto it = sizes.find(p);
+        if (it == sizes.end()) {
+            cudaFree(p);
+            return;
+        }
+        cached_blocks.push_back({it->second, p});
+        sizes.erase(it);
+    }
+    std::unordered_map<void*, size_t> sizes;
 
     bool cuda(cudaError_t e, const char* what) {
         if (e == cudaSuccess) return true;
@@ -272,8 +316,8 @@ bool upload_scalar(pml_aln* a, double v) {
 bool ensure_sumtable(pml_aln* a) {
     pml_ctx* c = a->ctx;
     if (a->d_sumtable) return true;
-    return c->cuda(cudaMalloc(&a->d_sumtable, sizeof(double) * a->npad * kRow), "sumtable alloc") &&
-           c->cuda(cudaMalloc(&a->d_sumscale, sizeof(int32_t) * a->npad), "sumtable scale alloc");
+    return c->cuda(c->dev_alloc(&a->d_sumtable, sizeof(double) * a->npad * kRow), "sumtable alloc") &&
+           c->cuda(c->dev_alloc(&a->d_sumscale, sizeof(int32_t) * a->npad), "sumtable scale alloc");
 }
 
 // One pass over the two CLVs at the ends of branch e: out = {lnL, dlnL/dt, d2lnL/dt2} at length len, summed over ranks.
@@ -452,7 +496,11 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
         if (xc == xb) break;
         fc = f(xc);
     }
-    double lo = std::min(xa, xc), hi = std::max(xa, xc), x = xb, w = xb, v = xb, fx = fb, fw = fb, fv = fb, d = 0.0, e = 0.0;
+    // Brent's memory starts from the bracket itself (best point, then the better and the worse end), so the very first
+    // step is already a parabola through three evaluated points instead of a golden-section probe
+    double lo = std::min(xa, xc), hi = std::max(xa, xc), x = xb, fx = fb;
+    double w = fa <= fc ? xa : xc, fw = std::min(fa, fc), v = fa <= fc ? xc : xa, fv = std::max(fa, fc);
+    double d = 0.5 * (hi - lo), e = hi - lo;
     for (int it = 0; ok && it < 100; ++it) {
         // absolute tolerance on log(alpha): a relative one degenerates when alpha is close to 1 (log alpha close to 0)
         const double mid = 0.5 * (lo + hi), tol1 = tol, tol2 = 2.0 * tol1;
@@ -559,6 +607,7 @@ void pml_ctx_destroy(pml_ctx* c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    for (auto& b : c->cached_blocks) cudaFree(b.second);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
@@ -640,14 +689,14 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
         std::memcpy(hc.data() + (size_t)t * a->npad, a->pat.codes.data() + (size_t)t * np + a->p0, a->nloc);
     std::vector<int32_t> hw(a->npad, 0);
     std::copy(a->pat.weight.begin() + a->p0, a->pat.weight.begin() + a->p0 + a->nloc, hw.begin());
-    bool ok = c->cuda(cudaMalloc(&a->d_codes, hc.size()), "codes alloc") &&
-              c->cuda(cudaMalloc(&a->d_weights, sizeof(int32_t) * a->npad), "weights alloc") &&
-              c->cuda(cudaMalloc(&a->d_wcustom, sizeof(int32_t) * a->npad), "weights alloc") &&
-              c->cuda(cudaMalloc(&a->d_model, sizeof(DeviceModel)), "model alloc") &&
-              c->cuda(cudaMalloc(&a->d_site_lnl, sizeof(double) * a->npad), "site lnl alloc") &&
-              c->cuda(cudaMalloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
-              c->cuda(cudaMalloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
-              c->cuda(cudaMalloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
+    bool ok = c->cuda(c->dev_alloc(&a->d_codes, hc.size()), "codes alloc") &&
+              c->cuda(c->dev_alloc(&a->d_weights, sizeof(int32_t) * a->npad), "weights alloc") &&
+              c->cuda(c->dev_alloc(&a->d_wcustom, sizeof(int32_t) * a->npad), "weights alloc") &&
+              c->cuda(c->dev_alloc(&a->d_model, sizeof(DeviceModel)), "model alloc") &&
+              c->cuda(c->dev_alloc(&a->d_site_lnl, sizeof(double) * a->npad), "site lnl alloc") &&
+              c->cuda(c->dev_alloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
+              c->cuda(c->dev_alloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
+              c->cuda(c->dev_alloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
               c->cuda(cudaMemcpy(a->d_codes, hc.data(), hc.size(), cudaMemcpyHostToDevice), "codes upload") &&
               c->cuda(cudaMemcpy(a->d_weights, hw.data(), sizeof(int32_t) * a->npad, cudaMemcpyHostToDevice), "weights upload") &&
               c->cuda(cudaMemset(a->d_wcustom, 0, sizeof(int32_t) * a->npad), "weights clear");
@@ -682,16 +731,16 @@ void pml_aln_free(pml_aln* a) {
     if (!a) return;
     a->ctx->bind();
     cudaStreamSynchronize(a->ctx->stream);
-    cudaFree(a->d_codes);
-    cudaFree(a->d_weights);
-    cudaFree(a->d_wcustom);
-    cudaFree(a->d_model);
-    cudaFree(a->d_site_lnl);
-    cudaFree(a->d_partials);
-    cudaFree(a->d_result);
-    cudaFree(a->d_scalar);
-    cudaFree(a->d_sumtable);
-    cudaFree(a->d_sumscale);
+    a->ctx->dev_free(a->d_codes);
+    a->ctx->dev_free(a->d_weights);
+    a->ctx->dev_free(a->d_wcustom);
+    a->ctx->dev_free(a->d_model);
+    a->ctx->dev_free(a->d_site_lnl);
+    a->ctx->dev_free(a->d_partials);
+    a->ctx->dev_free(a->d_result);
+    a->ctx->dev_free(a->d_scalar);
+    a->ctx->dev_free(a->d_sumtable);
+    a->ctx->dev_free(a->d_sumscale);
     delete a;
 }
 
@@ -763,11 +812,11 @@ int pml_tree_load(pml_aln* a, const char* newick, pml_tree** out) {
     t->views.reset(t->topo);
     const size_t inner = (size_t)a->pat.ntax - 2;
     t->pblock_cap = 2 * kOpsPerBatch + 1;
-    bool ok = c->cuda(cudaMalloc(&t->d_clv, sizeof(double) * inner * a->npad * kRow), "CLV arena alloc") &&
-              c->cuda(cudaMalloc(&t->d_scale, sizeof(int32_t) * inner * a->npad), "scaler alloc") &&
-              c->cuda(cudaMalloc(&t->d_pblocks, sizeof(PBlock) * t->pblock_cap), "P block alloc") &&
-              c->cuda(cudaMalloc(&t->d_lengths, sizeof(double) * t->pblock_cap), "lengths alloc") &&
-              c->cuda(cudaMalloc(&t->d_wanttip, t->pblock_cap), "flags alloc");
+    bool ok = c->cuda(c->dev_alloc(&t->d_clv, sizeof(double) * inner * a->npad * kRow), "CLV arena alloc") &&
+              c->cuda(c->dev_alloc(&t->d_scale, sizeof(int32_t) * inner * a->npad), "scaler alloc") &&
+              c->cuda(c->dev_alloc(&t->d_pblocks, sizeof(PBlock) * t->pblock_cap), "P block alloc") &&
+              c->cuda(c->dev_alloc(&t->d_lengths, sizeof(double) * t->pblock_cap), "lengths alloc") &&
+              c->cuda(c->dev_alloc(&t->d_wanttip, t->pblock_cap), "flags alloc");
     if (!ok) {
         pml_tree_free(t.release());
         return PML_ENOMEM;
@@ -781,11 +830,11 @@ void pml_tree_free(pml_tree* t) {
     if (!t) return;
     t->aln->ctx->bind();
     cudaStreamSynchronize(t->aln->ctx->stream);
-    cudaFree(t->d_clv);
-    cudaFree(t->d_scale);
-    cudaFree(t->d_pblocks);
-    cudaFree(t->d_lengths);
-    cudaFree(t->d_wanttip);
+    t->aln->ctx->dev_free(t->d_clv);
+    t->aln->ctx->dev_free(t->d_scale);
+    t->aln->ctx->dev_free(t->d_pblocks);
+    t->aln->ctx->dev_free(t->d_lengths);
+    t->aln->ctx->dev_free(t->d_wanttip);
     delete t;
 }
 
@@ -932,8 +981,8 @@ int pml_evaluate_replicates(pml_tree* t, const int32_t* W, int nrep, double* lnl
     int32_t* dW = nullptr;
     double* dl = nullptr;
     const int64_t np = a->pat.npat;
-    bool ok = c->cuda(cudaMalloc(&dW, sizeof(int32_t) * (size_t)nrep * a->npad), "replicate weights alloc") &&
-              c->cuda(cudaMalloc(&dl, sizeof(double) * nrep), "replicate lnL alloc") &&
+    bool ok = c->cuda(c->dev_alloc(&dW, sizeof(int32_t) * (size_t)nrep * a->npad), "replicate weights alloc") &&
+              c->cuda(c->dev_alloc(&dl, sizeof(double) * nrep), "replicate lnL alloc") &&
               c->cuda(cudaMemsetAsync(dW, 0, sizeof(int32_t) * (size_t)nrep * a->npad, c->stream), "replicate weights clear") &&
               c->cuda(cudaMemcpy2DAsync(dW, sizeof(int32_t) * a->npad, W + a->p0, sizeof(int32_t) * np, sizeof(int32_t) * a->nloc,
                                         nrep, cudaMemcpyHostToDevice, c->stream),
@@ -945,8 +994,8 @@ int pml_evaluate_replicates(pml_tree* t, const int32_t* W, int nrep, double* lnl
              c->cuda(cudaMemcpyAsync(lnl, dl, sizeof(double) * nrep, cudaMemcpyDeviceToHost, c->stream), "replicate lnL download") &&
              c->sync();
     }
-    cudaFree(dW);
-    cudaFree(dl);
+    c->dev_free(dW);
+    c->dev_free(dl);
     return ok ? PML_OK : PML_ENODEVICE;
 }
 

@@ -1,0 +1,216 @@
+"""Host-side mirror of PEPR's tool-runner interface for the maximum-likelihood path, in-process over the C ABI.
+
+It keeps the method names, argument meaning and error behaviour of
+  edu.vt.vbi.ci.pepr.tree.RAxMLRunner           (src/edu/vt/vbi/ci/pepr/tree/RAxMLRunner.java)
+  edu.vt.vbi.ci.pepr.tree.FastTreeRunner        (.../FastTreeRunner.java:142-199, getRaxmlBranchLengths)
+  edu.vt.vbi.ci.pepr.tree.TreeSupportDecorator  (.../TreeSupportDecorator.java:86-163)
+so that the parity tests read like calls PEPR itself makes.  The Java twin (`B200MLRunner`) binds the
+same C entry points through JNI / Panama; no JDK exists in this image, so this Python class is the executable mirror.
+
+Error convention of the reference: a failed tool run is logged, the result file is then missing and the getter returns
+""/null (ExecUtilities.java:29-35, RAxMLRunner.java:307-315).  Here the failure is kept in `last_error`, logged, and the
+getters return "" / None in the same way; `strict=True` raises instead.
+"""
+import logging
+
+import numpy as np
+
+from . import engine as _e
+
+logger = logging.getLogger("PEPR")
+
+ML_ALGORITHM, PARSIMONY_ALGORITHM, PARSIMONY_WITH_BL_ALGORITHM, PER_SITE_LL_ALGORITHM = range(4)
+
+
+class SequenceAlignment:
+    """the slice of edu.vt.vbi.ci.pepr.alignment.SequenceAlignment the runners use: taxon names + one string per taxon"""
+
+    def __init__(self, names, seqs, name="alignment"):
+        if len(names) != len(seqs) or len({len(s) for s in seqs}) != 1:
+            raise ValueError("alignment needs one equal-length sequence per taxon")
+        self.names, self.seqs, self.name = list(names), list(seqs), name
+
+    def getNTax(self):
+        return len(self.names)
+
+    def getLength(self):
+        return len(self.seqs[0])
+
+    def getAlignmentAsExtendedPhylipUsingTaxonNames(self):
+        """SequenceAlignment.java:489-522"""
+        w = max(len(n) for n in self.names) + 1
+        return "%d %d\n" % (len(self.names), len(self.seqs[0])) + "".join(n.ljust(w) + s + "\n" for n, s in zip(self.names, self.seqs))
+
+
+class B200MLRunner:
+    """drop-in for RAxMLRunner on the likelihood path: `-f e`, `-f g`, `-f b`, bootstrap weight vectors.
+
+    `threads` (RAxMLRunner's `-T`) selects nothing here: pattern parallelism is the GPU's.  Tree SEARCH (`-f d`, `-f a`;
+    RAxMLRunner.run with the ML algorithm and no start tree) belongs to SURVEY.md section 8(f) "next" and is reported as an
+    error, never approximated."""
+
+    def __init__(self, threads=1, gpu=0, ctx=None, strict=False):
+        self.threads, self.strict = threads, strict
+        self._own_ctx = ctx is None
+        self.ctx = ctx if ctx is not None else _e.Context(gpu)
+        self.matrix = "PROTGAMMAWAG"            # the pipeline always sets it (PhylogenomicPipeline2.java:248-250)
+        self.alignment = None
+        self.bootstrap_reps = 0
+        self.algorithm = ML_ALGORITHM
+        self.per_site_ll_trees = None
+        self.start_tree = None
+        self.random_seed = 12345
+        self.eps = 0.1
+        self.last_error = None
+        self._best_tree = ""
+        self._per_site_lines = None
+        self._lnl = None
+        self._alpha = None
+        self.tree_options = ""                  # what PEPRTracker.setTreeOptions would receive
+
+    # ---- configuration (RAxMLRunner setters) ------------------------------------------------------------------
+    def setAlignment(self, alignment):
+        self.alignment = alignment
+
+    def setMatrix(self, m):
+        self.matrix = m
+
+    def setBootstrapReps(self, n):
+        self.bootstrap_reps = int(n)
+
+    def setThreadCount(self, n):
+        self.threads = int(n)
+
+    def setParsimonyWithBL(self, flag=True):
+        if flag:
+            self.algorithm = PARSIMONY_WITH_BL_ALGORITHM
+
+    def setPerSiteLogLikelihoods(self, flag=True):
+        if flag:
+            self.algorithm = PER_SITE_LL_ALGORITHM
+
+    def setPerSiteLLTrees(self, trees):
+        self.per_site_ll_trees = list(trees)
+
+    def setStartTree(self, newick):
+        """the `-t` tree of `-f e` (FastTreeRunner.getRaxmlBranchLengths / the second run of parsimony-with-BL)"""
+        self.start_tree = newick
+
+    # ---- execution ------------------------------------------------------------------------------------------------
+    def _fail(self, msg):
+        self.last_error = msg
+        logger.error(msg)
+        if self.strict:
+            raise _e.EngineError(msg)
+
+    def _load(self):
+        a = self.alignment
+        return _e.Alignment(self.ctx, a.names, a.seqs, alpha=1.0, model=self.matrix)
+
+    def _optimise(self, aln, newick):
+        tree = _e.Tree(aln, newick)
+        for e in range(tree.num_branches):      # raxmlHPC ignores the lengths of the -t tree and starts at z = 0.9
+            tree.set_branch(e, -np.log(0.9))
+        aln.set_model(1.0, self.matrix)
+        lnl, alpha = tree.optimize(True, self.eps)
+        return tree, lnl, alpha
+
+    def run(self):
+        self.last_error, self._best_tree, self._per_site_lines = None, "", None
+        if self.alignment is None:
+            return self._fail("no alignment set")
+        try:
+            if self.algorithm == PER_SITE_LL_ALGORITHM:
+                self._run_per_site_ll()
+            elif self.start_tree is not None:
+                self._run_branch_lengths()
+            else:
+                self._fail("ML tree search (-f d / -f a) is not provided by the B200 engine yet (SURVEY.md 8f row 1); "
+                           "give a start tree (setStartTree) for `-f e`")
+        except _e.EngineError as ex:
+            self._fail(str(ex))
+
+    def _run_branch_lengths(self):
+        """`-f e -m <matrix> -s aln -t tree` (RAxMLRunner.java:245-262, FastTreeRunner.java:145-184)"""
+        self.tree_options = "peprml -f e -m %s" % self.matrix
+        aln = self._load()
+        try:
+            tree, self._lnl, self._alpha = self._optimise(aln, self.start_tree)
+            self._best_tree = tree.newick()
+            tree.close()
+        finally:
+            aln.close()
+
+    def _run_per_site_ll(self):
+        """`-f g -z trees` (RAxMLRunner.java:162-213): per tree, optimise then print per-site lnL in column order"""
+        self.tree_options = "peprml -f g -m %s" % self.matrix
+        trees = self.per_site_ll_trees or []
+        aln = self._load()
+        lines = ["  %d  %d" % (len(trees), self.alignment.getLength())]
+        try:
+            for i, nw in enumerate(trees):
+                tree, self._lnl, self._alpha = self._optimise(aln, nw)
+                _, ps = tree.evaluate(per_site=True)
+                lines.append("tr%d\t" % (i + 1) + "".join("%.6f " % v for v in ps))
+                self._best_tree = tree.newick()
+                tree.close()
+        finally:
+            aln.close()
+        self._per_site_lines = lines
+
+    # ---- results (RAxMLRunner getters) ------------------------------------------------------------------------------
+    def getBestTree(self):
+        return self._best_tree
+
+    def getParsimonyWithBLTree(self):
+        return self._best_tree
+
+    def getPerSiteLLResultFile(self):
+        return self._per_site_lines
+
+    def getLikelihood(self):
+        return self._lnl
+
+    def getAlpha(self):
+        return self._alpha
+
+    def getSupportDecoratedTree(self, main_tree, support_trees):
+        """RAxMLRunner.getSupportDecoratedTree (RAxMLRunner.java:453-516): `-f b`, integer percent labels"""
+        try:
+            return _e.support_tree(main_tree, list(support_trees), as_percent=True)
+        except _e.EngineError as ex:
+            self._fail(str(ex))
+            return None
+
+    def getBootstrapWeights(self, seed=None, reps=None):
+        """replicate site-weight vectors of `-x seed -N reps` / `-b seed` (computeNextReplicate), pattern order"""
+        aln = self._load()
+        try:
+            w, _ = aln.bootstrap_weights(self.random_seed if seed is None else seed, self.bootstrap_reps if reps is None else reps)
+        finally:
+            aln.close()
+        return w
+
+    def close(self):
+        if self._own_ctx and self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
+
+
+class TreeSupportDecorator:
+    """TreeSupportDecorator.addSupportValues (TreeSupportDecorator.java:86-163): raw counts as node labels"""
+
+    @staticmethod
+    def addSupportValues(main, supports):
+        return _e.support_tree(main, list(supports), as_percent=False)
+
+
+def getTreeScore(runner, tree):
+    """PhylogenomicPipeline2.getTreeScore (PhylogenomicPipeline2.java:1482-1500): run `-f g` on one tree and sum line 2"""
+    runner.setPerSiteLogLikelihoods(True)
+    runner.setPerSiteLLTrees([tree])
+    runner.run()
+    lines = runner.getPerSiteLLResultFile()
+    if not lines:
+        return float("nan")
+    return sum(float(x) for x in lines[1].split("\t")[1].split())

@@ -1,0 +1,123 @@
+"""The reference-facing layers on the GPU: the RAxMLRunner mirror (in-process) and the raxmlHPC-compatible executable
+(process + files, the protocol PEPR's ExecUtilities uses)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import pepr_b200 as pb
+from pepr_b200 import runner as R
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "pepr_b200", "bin", "peprml")
+
+
+def test_runner_branch_lengths_like_f_e(gpu_ctx, golden):
+    g = golden("small")
+    r = R.B200MLRunner(threads=4, ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r.setMatrix("PROTGAMMAWAG")
+    r.setStartTree(g.meta["tree_in"])
+    r.run()
+    assert r.last_error is None
+    assert abs(r.getLikelihood() - g.meta["fe"]["lnl"]) < 0.1          # raxmlHPC's own stopping tolerance
+    assert abs(r.getAlpha() - g.meta["fe"]["alpha"]) / g.meta["fe"]["alpha"] < 0.05
+    t = r.getBestTree()
+    assert t.endswith("):0.0;") and all(n in t for n in g.names)
+
+
+def test_runner_per_site_ll_and_tree_score(gpu_ctx, golden):
+    g = golden("small")
+    r = R.B200MLRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    score = R.getTreeScore(r, g.meta["tree_in"])
+    lines = r.getPerSiteLLResultFile()
+    assert lines[0].split() == ["1", "300"]
+    vals = np.array([float(x) for x in lines[1].split("\t")[1].split()])
+    assert len(vals) == 300
+    # raxmlHPC -f g optimises first too; its per-site values are the golden ones up to the optimisers' 0.1 lnL agreement
+    assert abs(score - sum(g.meta["fg"]["per_site"])) < 0.1
+    assert np.abs(vals - np.array(g.meta["fg"]["per_site"])).max() < 0.05
+
+
+def test_runner_reports_errors_the_reference_way(gpu_ctx, golden):
+    g = golden("small")
+    r = R.B200MLRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r.run()                                     # no start tree: tree search is not part of this round
+    assert r.getBestTree() == "" and "tree search" in r.last_error
+    r.setStartTree("((TaxA,TaxB),(TaxC,Oops),((TaxE,TaxF),(TaxG,TaxH)));")
+    r.run()
+    assert r.getBestTree() == "" and "Oops" in r.last_error
+    with pytest.raises(pb.EngineError):
+        R.B200MLRunner(ctx=gpu_ctx, strict=True).run()
+
+
+def test_runner_bootstrap_weights_and_supports(gpu_ctx, golden):
+    g = golden("small")
+    r = R.B200MLRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r.setBootstrapReps(3)
+    assert r.getBootstrapWeights(seed=g.meta["fj"]["seed"]).tolist() == g.meta["fj"]["replicate_weights"]
+    from tests.test_oracle_golden import _labels
+    got = r.getSupportDecoratedTree(g.meta["fe"]["tree"], g.meta["fb"]["support_trees"])
+    assert _labels(got) == _labels(g.meta["fb"]["bipartitions"])
+
+
+def _run_cli(args, cwd):
+    return subprocess.run([CLI] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def test_cli_f_e_writes_raxml_files(tmp_path, golden):
+    g = golden("small")
+    from pepr_b200 import synth
+    synth.write_phylip(str(tmp_path / "t.phy"), g.names, g.seqs)
+    (tmp_path / "t.nwk").write_text(g.meta["tree_in"] + "\n")
+    r = _run_cli(["-f", "e", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "run1", "-t", "t.nwk", "-T", "8"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    info = (tmp_path / "RAxML_info.run1").read_text()
+    lnl = float(re.search(r"Final GAMMA\s+likelihood: (\S+)", info).group(1))
+    alpha = float(re.search(r"alpha: (\S+)", info).group(1))
+    assert abs(lnl - g.meta["fe"]["lnl"]) < 0.1
+    assert abs(alpha - g.meta["fe"]["alpha"]) / g.meta["fe"]["alpha"] < 0.05
+    assert "Alignment has %d distinct alignment patterns" % g.meta["fe"]["patterns"] in info
+    tree = (tmp_path / "RAxML_result.run1").read_text().strip()
+    assert tree.endswith(":0.0;")
+    # like raxmlHPC, a second run under the same name is refused
+    assert _run_cli(["-f", "e", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "run1", "-t", "t.nwk"], tmp_path).returncode != 0
+
+
+def test_cli_f_g_and_f_j(tmp_path, golden):
+    g = golden("small")
+    from pepr_b200 import synth
+    from oracle import oracle as orc
+    synth.write_phylip(str(tmp_path / "t.phy"), g.names, g.seqs)
+    (tmp_path / "t.nwk").write_text(g.meta["tree_in"] + "\n")
+    r = _run_cli(["-f", "g", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "g1", "-z", "t.nwk"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    lines = (tmp_path / "RAxML_perSiteLLs.g1").read_text().split("\n")
+    assert lines[0].split() == ["1", "300"]
+    vals = [float(x) for x in lines[1].split("\t")[1].split()]
+    assert abs(sum(vals) - sum(g.meta["fg"]["per_site"])) < 0.1
+    r = _run_cli(["-f", "j", "-b", "12345", "-#", "3", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "j1"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    for k in range(3):
+        _, bs = orc.read_phylip(str(tmp_path / ("t.phy.BS%d" % k)))
+        bc = orc.encode(bs)
+        cols = {}
+        for j in range(bc.shape[1]):
+            key = bytes(bc[:, j])
+            cols[key] = cols.get(key, 0) + 1
+        w = [cols.get(bytes(g.pat[:, p]), 0) for p in range(g.pat.shape[1])]
+        assert w == g.meta["fj"]["replicate_weights"][k]         # bit exact with raxmlHPC -f j
+
+
+def test_cli_rejects_tree_search_loudly(tmp_path, golden):
+    g = golden("small")
+    from pepr_b200 import synth
+    synth.write_phylip(str(tmp_path / "t.phy"), g.names, g.seqs)
+    r = _run_cli(["-f", "d", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "d1"], tmp_path)
+    assert r.returncode == 2 and "not implemented" in r.stderr
