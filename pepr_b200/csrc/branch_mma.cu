@@ -5,6 +5,10 @@
 // (evaluateGTRGAMMAPROT) including per-pattern lnL.  The product table is only written out when the caller wants to
 // iterate Newton-Raphson on it (kStore).
 //
+// The streaming kernel only leaves three sums (f, f', f'') per pattern; the short k_branch_finish turns them into
+// per-pattern lnL and the weighted totals (log, divisions and integer weights stay off the FP64 pipe the MMAs need) and
+// performs the fixed-order reduction, so the pair replaces sumtable + core + reduce of the first engine generation.
+//
 // Same pipeline as newview_mma.cu: three groups of four warps (one per rate category), each with a private ring of
 // shared-memory stages filled by TMA bulk copies, DMMA m8n8k4 with the fixed 20x20 matrices as B fragments in registers.
 #include <cuda_runtime.h>
@@ -30,7 +34,7 @@ struct BranchPlan {
     static constexpr int kStageDoubles = kInner * kTileDoubles;
     static constexpr int kTipDoubles = kTipA ? kCodes * kTipVecPad : 0;
     static constexpr int kRedDoubles = 2 * kGroups * kCats * kTileRows * 3;  // [parity][group][cat][row][f,f1,f2]
-    static constexpr int kFinalDoubles = 3 * kComputeWarps + 4;
+    static constexpr int kFinalDoubles = 0;
     static constexpr size_t kBytes = 128 + sizeof(double) * (size_t)(kTipDoubles + kRedDoubles + kFinalDoubles + kStages * kStageDoubles);
 };
 
@@ -114,7 +118,6 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
                 e2[nt][j] = a * a * e;
             }
     }
-    double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;  // lanes 0-3 of every warp accumulate
 
     int next_code[2] = {0, 0};
     if (kTipA && first < ntiles) {
@@ -131,13 +134,6 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
             next_code[1] = __ldg(args.a.codes + row0 + (int64_t)stride * kTileRows + 8 + g);
         }
         // per-row integers are only needed after the MMAs: issue the loads now, consume them at the end
-        // the four warps of a group share the per-row finish: warp c closes rows 4c .. 4c+3 with its lanes 0-3
-        int32_t sca = 0, scb = 0, wi = 0;
-        if (lane < 4) {
-            scb = __ldg(args.b.scale + row0 + c * 4 + lane);
-            if (!kTipA) sca = __ldg(args.a.scale + row0 + c * 4 + lane);
-            wi = __ldg(args.weights + row0 + c * 4 + lane);
-        }
         mbar_wait(gfull + slot, (it / kDepth) & 1);
         const double* stage = gstage + (size_t)slot * Plan::kStageDoubles;
         AFrag fa[2], fb[2];
@@ -205,52 +201,81 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
         }
         named_barrier(1 + grp, 4 * 32);
         if (c == 0 && tile + kDepth * stride < ntiles) refill(tile + kDepth * stride, slot);
-        if (lane < 4) {
-            const int r = c * 4 + lane;
-            double f = 0.0, f1 = 0.0, f2 = 0.0;
-#pragma unroll
-            for (int cc = 0; cc < kCats; ++cc) {
-                const double* src = red + (cc * kTileRows + r) * 3;
-                f += src[0];
-                f1 += src[1];
-                f2 += src[2];
-            }
-            const double inv = 1.0 / f, q = f1 * inv, w = (double)wi;
-            const int32_t sc = sca + scb;
-            const double l = log(0.25 * f) + sc * kLogMinLik;
-            if (args.site_lnl) args.site_lnl[row0 + r] = l;
-            if (kStore) args.sum_scale[row0 + r] = sc;
-            sum_l = fma(w, l, sum_l);
-            sum_d1 = fma(w, q, sum_d1);
-            sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
+        // the four warps of a group share the row sums: warp c adds the categories of rows 4c .. 4c+3 (3 values each)
+        if (lane < 12) {
+            const int r = c * 4 + lane / 3, v = lane % 3;
+            const double sum = (red[(0 * kTileRows + r) * 3 + v] + red[(1 * kTileRows + r) * 3 + v]) +
+                               (red[(2 * kTileRows + r) * 3 + v] + red[(3 * kTileRows + r) * 3 + v]);
+            args.rowsum[(row0 + r) * 3 + v] = sum;
         }
-    }
-    // CTA partials in a fixed order: lanes 0-3 by shuffle, then the twelve warps through shared memory
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
-        sum_l += __shfl_xor_sync(0xffffffffu, sum_l, o);
-        sum_d1 += __shfl_xor_sync(0xffffffffu, sum_d1, o);
-        sum_d2 += __shfl_xor_sync(0xffffffffu, sum_d2, o);
-    }
-    if (lane == 0) {
-        s_final[warp * 3 + 0] = sum_l;
-        s_final[warp * 3 + 1] = sum_d1;
-        s_final[warp * 3 + 2] = sum_d2;
-    }
-    named_barrier(8, kComputeWarps * 32);
-    if (threadIdx.x < 3) {
-        double v = 0.0;
-        for (int k = 0; k < kComputeWarps; ++k) v += s_final[k * 3 + threadIdx.x];
-        args.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
     }
 }
 
+// per pattern: lnL = log(f/4) + scale * ln 2^-256, and the weighted sums of lnL, f'/f, f''/f - (f'/f)^2.
+// Stage 1 per block, stage 2 by the block that takes the last ticket, both in a fixed order (bit-reproducible result).
+constexpr int kFinishThreads = 256;
+__global__ void __launch_bounds__(kFinishThreads) k_branch_finish(BranchArgs args, int64_t np, unsigned int* ticket, double* result) {
+    __shared__ double s_part[3][kFinishThreads / 32];
+    __shared__ bool s_last;
+    const int64_t p = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
+    double l = 0.0, d1 = 0.0, d2 = 0.0;
+    if (p < np) {
+        const double f = args.rowsum[p * 3], f1 = args.rowsum[p * 3 + 1], f2 = args.rowsum[p * 3 + 2];
+        int32_t sc = args.b.scale[p];
+        if (args.a.scale) sc += args.a.scale[p];
+        const double w = (double)args.weights[p], inv = 1.0 / f, q = f1 * inv;
+        const double lnl = log(0.25 * f) + sc * kLogMinLik;
+        if (args.site_lnl) args.site_lnl[p] = lnl;
+        if (args.sum_scale) args.sum_scale[p] = sc;
+        l = w * lnl;
+        d1 = w * q;
+        d2 = w * (f2 * inv - q * q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l += __shfl_xor_sync(0xffffffffu, l, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_part[0][threadIdx.x >> 5] = l;
+        s_part[1][threadIdx.x >> 5] = d1;
+        s_part[2][threadIdx.x >> 5] = d2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int k = 0; k < kFinishThreads / 32; ++k) v += s_part[threadIdx.x][k];
+        args.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the last block adds the block partials: strided by thread, then a shared-memory tree -- the same order every run
+    __shared__ double s_tree[kFinishThreads];
+    for (int v = 0; v < 3; ++v) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += kFinishThreads) acc += args.partials[(int64_t)v * gridDim.x + i];
+        s_tree[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = kFinishThreads / 2; w > 0; w >>= 1) {
+            if (threadIdx.x < w) s_tree[threadIdx.x] += s_tree[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) result[v] = s_tree[0];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 template <bool kTipA, bool kStore>
-int launch_one(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
+void launch_one(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
     k_branch_mma<kTipA, kStore><<<grid, kThreadsMma, BranchPlan<kTipA>::kBytes, stream>>>(args, ntiles);
-    return grid;
 }
 
 }  // namespace
@@ -262,11 +287,13 @@ void configure_branch_kernels() {
     cudaFuncSetAttribute(k_branch_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<false>::kBytes);
 }
 
-// returns the number of CTA partials written per value (the grid size); np must be a multiple of 16
-int launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
+// streaming pass + finish; result[0..2] = lnL, dlnL/dt, d2lnL/dt2 of this rank's patterns.  np must be a multiple of 16.
+void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, unsigned int* ticket, double* result, cudaStream_t stream) {
     const bool tip = args.a.clv == nullptr, store = args.sumtable != nullptr;
-    if (tip) return store ? launch_one<true, true>(args, np, sms, stream) : launch_one<true, false>(args, np, sms, stream);
-    return store ? launch_one<false, true>(args, np, sms, stream) : launch_one<false, false>(args, np, sms, stream);
+    if (tip) store ? launch_one<true, true>(args, np, sms, stream) : launch_one<true, false>(args, np, sms, stream);
+    else store ? launch_one<false, true>(args, np, sms, stream) : launch_one<false, false>(args, np, sms, stream);
+    const int blocks = (int)((np + kFinishThreads - 1) / kFinishThreads);
+    k_branch_finish<<<blocks, kFinishThreads, 0, stream>>>(args, np, ticket, result);
 }
 
 }  // namespace pml

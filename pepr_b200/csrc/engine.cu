@@ -178,6 +178,8 @@ struct pml_aln {
     double* d_partials = nullptr;
     double* d_result = nullptr;  // 16 doubles
     double* d_scalar = nullptr;  // branch length handed to the NR core
+    double* d_rowsum = nullptr;  // npad x 3: per-pattern f, f', f'' of the branch kernel
+    unsigned int* d_ticket = nullptr;
     double* d_sumtable = nullptr;
     int32_t* d_sumscale = nullptr;
     int ntrees = 0;
@@ -339,11 +341,11 @@ bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_ta
     args.site_lnl = site_lnl ? a->d_site_lnl : nullptr;
     args.sumtable = keep_table ? a->d_sumtable : nullptr;
     args.sum_scale = keep_table ? a->d_sumscale : nullptr;
+    args.rowsum = a->d_rowsum;
     args.partials = a->d_partials;
     const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
-    const int grid = launch_branch_mma(args, a->npad, c->sms, c->stream);
+    launch_branch_mma(args, a->npad, c->sms, a->d_ticket, a->d_result, c->stream);
     c->tock(tk);
-    launch_reduce(a->d_partials, grid, 3, a->d_result, c->stream);
     t->launches += 2;
     t->prepared_branch = keep_table ? e : -1;
     if (!c->cuda(cudaGetLastError(), "branch kernel")) return false;
@@ -697,6 +699,9 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
               c->cuda(c->dev_alloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
               c->cuda(c->dev_alloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
               c->cuda(c->dev_alloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
+              c->cuda(c->dev_alloc(&a->d_rowsum, sizeof(double) * 3 * a->npad), "row sum alloc") &&
+              c->cuda(c->dev_alloc(&a->d_ticket, 64), "ticket alloc") &&
+              c->cuda(cudaMemset(a->d_ticket, 0, 64), "ticket clear") &&
               c->cuda(cudaMemcpy(a->d_codes, hc.data(), hc.size(), cudaMemcpyHostToDevice), "codes upload") &&
               c->cuda(cudaMemcpy(a->d_weights, hw.data(), sizeof(int32_t) * a->npad, cudaMemcpyHostToDevice), "weights upload") &&
               c->cuda(cudaMemset(a->d_wcustom, 0, sizeof(int32_t) * a->npad), "weights clear");
@@ -739,6 +744,8 @@ void pml_aln_free(pml_aln* a) {
     a->ctx->dev_free(a->d_partials);
     a->ctx->dev_free(a->d_result);
     a->ctx->dev_free(a->d_scalar);
+    a->ctx->dev_free(a->d_rowsum);
+    a->ctx->dev_free(a->d_ticket);
     a->ctx->dev_free(a->d_sumtable);
     a->ctx->dev_free(a->d_sumscale);
     delete a;

@@ -29,18 +29,23 @@ __global__ void __launch_bounds__(256) k_make_p(const DeviceModel* __restrict__ 
                                                 const uint8_t* __restrict__ want_tip, PBlock* __restrict__ blocks) {
     __shared__ double s_exp[kCats][kStates];
     __shared__ double s_P[kCats][kStates][kStates];
+    __shared__ double s_V[kStates][kStates + 1], s_Vinv[kStates][kStates];
     const int b = blockIdx.x;
     const double t = lengths[b];
     if (threadIdx.x < kRow) {
         const int c = threadIdx.x / kStates, k = threadIdx.x % kStates;
         s_exp[c][k] = exp(dm->lambda[k] * dm->rates[c] * t);
     }
+    for (int idx = threadIdx.x; idx < kStates * kStates; idx += blockDim.x) {
+        s_V[idx / kStates][idx % kStates] = (&dm->V[0][0])[idx];
+        (&s_Vinv[0][0])[idx] = (&dm->Vinv[0][0])[idx];
+    }
     __syncthreads();
     for (int idx = threadIdx.x; idx < kCats * kStates * kStates; idx += blockDim.x) {
         const int c = idx / (kStates * kStates), i = (idx / kStates) % kStates, j = idx % kStates;
         double acc = 0.0;
 #pragma unroll
-        for (int k = 0; k < kStates; ++k) acc = fma(dm->V[i][k] * s_exp[c][k], dm->Vinv[k][j], acc);
+        for (int k = 0; k < kStates; ++k) acc = fma(s_V[i][k] * s_exp[c][k], s_Vinv[k][j], acc);
         s_P[c][i][j] = acc;
         blocks[b].P[c][i][j] = acc;
     }

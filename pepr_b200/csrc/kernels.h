@@ -58,9 +58,10 @@ struct BranchArgs {
     double* site_lnl;     // optional
     double* sumtable;     // optional: np x 80
     int32_t* sum_scale;   // with sumtable
-    double* partials;     // 3 x grid doubles
+    double* rowsum;       // np x 3 scratch: f, f', f'' per pattern
+    double* partials;     // 3 x ceil(np/256) doubles
 };
-int launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
+void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, unsigned int* ticket, double* result, cudaStream_t stream);
 void configure_branch_kernels();
 // fixed-order sum of `nblocks` partials for each of `nvals` values
 void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream);
