@@ -5,9 +5,10 @@
 // (evaluateGTRGAMMAPROT) including per-pattern lnL.  The product table is only written out when the caller wants to
 // iterate Newton-Raphson on it (kStore).
 //
-// The streaming kernel only leaves three sums (f, f', f'') per pattern; the short k_branch_finish turns them into
-// per-pattern lnL and the weighted totals (log, divisions and integer weights stay off the FP64 pipe the MMAs need) and
-// performs the fixed-order reduction, so the pair replaces sumtable + core + reduce of the first engine generation.
+// The streaming loop only leaves three sums (f, f', f'') per pattern; after its last tile every CTA turns the sums of its
+// own tiles into per-pattern lnL and weighted totals with all 384 threads (logs, divisions and integer weights stay out of
+// the loop whose FP64 pipe the MMAs need), and the CTA that draws the last ticket adds the CTA partials in a fixed order:
+// one launch replaces sumtable + core + reduce of the first engine generation and its result is bit-reproducible.
 //
 // Same pipeline as newview_mma.cu: three groups of four warps (one per rate category), each with a private ring of
 // shared-memory stages filled by TMA bulk copies, DMMA m8n8k4 with the fixed 20x20 matrices as B fragments in registers.
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
     // exp(lambda_k r_c t) and its first two t-derivatives at the D-fragment positions k = nt*8 + 2t + {0,1}
     double e0[3][2], e1[3][2], e2[3][2];
     {
-        const double tt = args.d_t[0], rate = dm->rates[c];
+        const double tt = args.t, rate = dm->rates[c];
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
@@ -209,66 +210,67 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
             args.rowsum[(row0 + r) * 3 + v] = sum;
         }
     }
-}
 
-// per pattern: lnL = log(f/4) + scale * ln 2^-256, and the weighted sums of lnL, f'/f, f''/f - (f'/f)^2.
-// Stage 1 per block, stage 2 by the block that takes the last ticket, both in a fixed order (bit-reproducible result).
-constexpr int kFinishThreads = 256;
-__global__ void __launch_bounds__(kFinishThreads) k_branch_finish(BranchArgs args, int64_t np, unsigned int* ticket, double* result) {
-    __shared__ double s_part[3][kFinishThreads / 32];
-    __shared__ bool s_last;
-    const int64_t p = (int64_t)blockIdx.x * kFinishThreads + threadIdx.x;
-    double l = 0.0, d1 = 0.0, d2 = 0.0;
-    if (p < np) {
+    // ---- finish: the rows of this CTA's own tiles, all threads -------------------------------------------------
+    __syncthreads();
+    double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int idx = threadIdx.x; idx < my_tiles * kTileRows; idx += kThreadsMma) {
+        const int64_t p = ((int64_t)blockIdx.x + (int64_t)(idx / kTileRows) * gridDim.x) * kTileRows + idx % kTileRows;
         const double f = args.rowsum[p * 3], f1 = args.rowsum[p * 3 + 1], f2 = args.rowsum[p * 3 + 2];
-        int32_t sc = args.b.scale[p];
-        if (args.a.scale) sc += args.a.scale[p];
-        const double w = (double)args.weights[p], inv = 1.0 / f, q = f1 * inv;
+        int32_t sc = __ldg(args.b.scale + p);
+        if (!kTipA) sc += __ldg(args.a.scale + p);
+        const double w = (double)__ldg(args.weights + p), inv = 1.0 / f, q = f1 * inv;
         const double lnl = log(0.25 * f) + sc * kLogMinLik;
         if (args.site_lnl) args.site_lnl[p] = lnl;
-        if (args.sum_scale) args.sum_scale[p] = sc;
-        l = w * lnl;
-        d1 = w * q;
-        d2 = w * (f2 * inv - q * q);
+        if (kStore) args.sum_scale[p] = sc;
+        sum_l = fma(w, lnl, sum_l);
+        sum_d1 = fma(w, q, sum_d1);
+        sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        l += __shfl_xor_sync(0xffffffffu, l, o);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        sum_l += __shfl_xor_sync(0xffffffffu, sum_l, o);
+        sum_d1 += __shfl_xor_sync(0xffffffffu, sum_d1, o);
+        sum_d2 += __shfl_xor_sync(0xffffffffu, sum_d2, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        s_part[0][threadIdx.x >> 5] = l;
-        s_part[1][threadIdx.x >> 5] = d1;
-        s_part[2][threadIdx.x >> 5] = d2;
+    double* s_fin = s_red;           // the exchange buffer of the loop is free now
+    __shared__ bool s_last;
+    if (lane == 0) {
+        s_fin[warp * 3 + 0] = sum_l;
+        s_fin[warp * 3 + 1] = sum_d1;
+        s_fin[warp * 3 + 2] = sum_d2;
     }
     __syncthreads();
     if (threadIdx.x < 3) {
         double v = 0.0;
-        for (int k = 0; k < kFinishThreads / 32; ++k) v += s_part[threadIdx.x][k];
+        for (int k = 0; k < kComputeWarps; ++k) v += s_fin[k * 3 + threadIdx.x];
         args.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+        __threadfence();
     }
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // the last block adds the block partials: strided by thread, then a shared-memory tree -- the same order every run
-    __shared__ double s_tree[kFinishThreads];
-    for (int v = 0; v < 3; ++v) {
+    if (warp < 3) {  // warp v adds value v over the CTAs: lane-strided, then a shuffle tree -- the same order every run
         double acc = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += kFinishThreads) acc += args.partials[(int64_t)v * gridDim.x + i];
-        s_tree[threadIdx.x] = acc;
-        __syncthreads();
-        for (int w = kFinishThreads / 2; w > 0; w >>= 1) {
-            if (threadIdx.x < w) s_tree[threadIdx.x] += s_tree[threadIdx.x + w];
-            __syncthreads();
+        for (int i = lane; i < (int)gridDim.x; i += 32) acc += args.partials[(int64_t)warp * gridDim.x + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            args.result[warp] = acc;
+            if (args.host_result) args.host_result[warp] = acc;
         }
-        if (threadIdx.x == 0) result[v] = s_tree[0];
-        __syncthreads();
     }
-    if (threadIdx.x == 0) *ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *args.ticket = 0;
+        if (args.host_result) {
+            __threadfence_system();
+            args.host_result[3] = args.sequence;
+        }
+    }
 }
 
 template <bool kTipA, bool kStore>
@@ -287,13 +289,11 @@ void configure_branch_kernels() {
     cudaFuncSetAttribute(k_branch_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<false>::kBytes);
 }
 
-// streaming pass + finish; result[0..2] = lnL, dlnL/dt, d2lnL/dt2 of this rank's patterns.  np must be a multiple of 16.
-void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, unsigned int* ticket, double* result, cudaStream_t stream) {
+// args.result[0..2] = lnL, dlnL/dt, d2lnL/dt2 of this rank's patterns.  np must be a multiple of 16.
+void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const bool tip = args.a.clv == nullptr, store = args.sumtable != nullptr;
     if (tip) store ? launch_one<true, true>(args, np, sms, stream) : launch_one<true, false>(args, np, sms, stream);
     else store ? launch_one<false, true>(args, np, sms, stream) : launch_one<false, false>(args, np, sms, stream);
-    const int blocks = (int)((np + kFinishThreads - 1) / kFinishThreads);
-    k_branch_finish<<<blocks, kFinishThreads, 0, stream>>>(args, np, ticket, result);
 }
 
 }  // namespace pml

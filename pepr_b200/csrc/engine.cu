@@ -67,6 +67,11 @@ struct pml_ctx {
     uint8_t* h_stage = nullptr;
     size_t stage_cap = 0, stage_used = 0;
     double* h_result = nullptr;
+    // zero-copy result slot: the branch kernel writes {lnL, d1, d2, sequence} here and the host polls the sequence, which
+    // saves a D2H copy and a stream synchronisation per Newton-Raphson step (single-rank contexts only)
+    volatile double* h_mapped = nullptr;
+    double* d_mapped = nullptr;
+    double sequence = 0.0;
     // optional per-launch device timing (pml_profile_begin/end)
     struct Timed { int kind; int64_t rows; cudaEvent_t t0, t1; };
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
@@ -247,12 +252,47 @@ const int32_t* device_weights(pml_aln* a, const int32_t* weights) {
     return a->d_wcustom;
 }
 
+// one CLV kernel per traversal entry; entry i of the batch uses P blocks 2i and 2i+1
+void launch_entries(pml_tree* t, const std::vector<ViewOp>& ops, size_t base, int n) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    for (int i = 0; i < n; ++i) {
+        const ViewOp& op = ops[base + i];
+        NewviewOp nv{};
+        nv.left = t->side(op.child[0]);
+        nv.right = t->side(op.child[1]);
+        nv.pleft = t->d_pblocks + 2 * i;
+        nv.pright = t->d_pblocks + 2 * i + 1;
+        nv.out = t->clv(op.node);
+        nv.out_scale = t->scale(op.node);
+        const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+        const int tk = c->tick(2 - ntip, a->nloc);
+        launch_newview_mma(nv, a->npad, c->sms, c->stream);
+        c->tock(tk);
+        ++t->launches;
+        t->site_updates[2 - ntip] += a->nloc;
+    }
+}
+
 // executes a traversal descriptor: P blocks for every entry in one launch, then one CLV kernel per entry
 bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     for (size_t base = 0; base < ops.size(); base += kOpsPerBatch) {
         const int n = (int)std::min<size_t>(kOpsPerBatch, ops.size() - base);
+        if (2 * n <= kMakePInline) {
+            // the usual case while smoothing (1-3 entries): branch lengths ride in the kernel arguments
+            MakePInline batch{};
+            for (int i = 0; i < n; ++i)
+                for (int k = 0; k < 2; ++k) {
+                    batch.length[2 * i + k] = t->topo.len[ops[base + i].cedge[k]];
+                    batch.want_tip[2 * i + k] = t->topo.is_tip(ops[base + i].child[k]) ? 1 : 0;
+                }
+            launch_make_p_inline(a->d_model, batch, t->d_pblocks, 2 * n, c->stream);
+            ++t->launches;
+            launch_entries(t, ops, base, n);
+            continue;
+        }
         auto* hl = (double*)c->stage(sizeof(double) * 2 * n + 2 * n);
         if (!hl) return false;
         auto* ht = (uint8_t*)(hl + 2 * n);
@@ -268,22 +308,7 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
             return false;
         launch_make_p(a->d_model, t->d_lengths, t->d_wanttip, t->d_pblocks, 2 * n, c->stream);
         ++t->launches;
-        for (int i = 0; i < n; ++i) {
-            const ViewOp& op = ops[base + i];
-            NewviewOp nv{};
-            nv.left = t->side(op.child[0]);
-            nv.right = t->side(op.child[1]);
-            nv.pleft = t->d_pblocks + 2 * i;
-            nv.pright = t->d_pblocks + 2 * i + 1;
-            nv.out = t->clv(op.node);
-            nv.out_scale = t->scale(op.node);
-            const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-            const int tk = c->tick(2 - ntip, a->nloc);
-            launch_newview_mma(nv, a->npad, c->sms, c->stream);
-            c->tock(tk);
-            ++t->launches;
-            t->site_updates[2 - ntip] += a->nloc;
-        }
+        launch_entries(t, ops, base, n);
     }
     return c->cuda(cudaGetLastError(), "CLV kernels");
 }
@@ -307,14 +332,6 @@ bool fetch_result(pml_ctx* c, const double* d_result, int n, double* out) {
     return true;
 }
 
-bool upload_scalar(pml_aln* a, double v) {
-    pml_ctx* c = a->ctx;
-    auto* h = (double*)c->stage(sizeof(double));
-    if (!h) return false;
-    h[0] = v;
-    return c->cuda(cudaMemcpyAsync(a->d_scalar, h, sizeof(double), cudaMemcpyHostToDevice, c->stream), "length upload");
-}
-
 bool ensure_sumtable(pml_aln* a) {
     pml_ctx* c = a->ctx;
     if (a->d_sumtable) return true;
@@ -331,24 +348,47 @@ bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_ta
     if (keep_table && !ensure_sumtable(a)) return false;
     int x, y;
     if (!orient_branch(t, e, x, y)) return false;
-    if (!upload_scalar(a, len)) return false;
     BranchArgs args{};
     args.a = t->side(x);
     args.b = t->side(y);
     args.dm = a->d_model;
     args.weights = dw;
-    args.d_t = a->d_scalar;
+    args.t = len;
     args.site_lnl = site_lnl ? a->d_site_lnl : nullptr;
     args.sumtable = keep_table ? a->d_sumtable : nullptr;
     args.sum_scale = keep_table ? a->d_sumscale : nullptr;
     args.rowsum = a->d_rowsum;
     args.partials = a->d_partials;
+    args.ticket = a->d_ticket;
+    args.result = a->d_result;
+    const bool zero_copy = c->nranks == 1;
+    if (zero_copy) {
+        args.host_result = c->d_mapped;
+        args.sequence = (c->sequence += 1.0);
+    }
     const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
-    launch_branch_mma(args, a->npad, c->sms, a->d_ticket, a->d_result, c->stream);
+    launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
-    t->launches += 2;
+    t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
     if (!c->cuda(cudaGetLastError(), "branch kernel")) return false;
+    if (zero_copy) {
+        // everything queued before the kernel has completed once its result is visible, so the staging area is free again
+        long spins = 0;
+        while (c->h_mapped[3] != args.sequence) {
+            if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(c->stream) != cudaErrorNotReady) {
+                if (c->h_mapped[3] == args.sequence) break;
+                c->cuda(cudaStreamSynchronize(c->stream), "branch kernel");
+                if (c->err.empty()) c->err = "branch kernel finished without publishing its result";
+                return false;
+            }
+        }
+        out[0] = c->h_mapped[0];
+        out[1] = c->h_mapped[1];
+        out[2] = c->h_mapped[2];
+        c->stage_used = 0;
+        return true;
+    }
     if (!c->allreduce(a->d_result, 3)) return false;
     return fetch_result(c, a->d_result, 3, out);
 }
@@ -366,9 +406,8 @@ int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
 bool core_at(pml_tree* t, const int32_t* dw, double len, double out[3]) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
-    if (!upload_scalar(a, len)) return false;
     const int tk = c->tick(5, a->nloc);
-    launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, a->d_scalar, a->d_partials, a->d_result, c->stream);
+    launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, len, a->d_partials, a->d_result, c->stream);
     c->tock(tk);
     t->launches += 2;
     if (!c->cuda(cudaGetLastError(), "core kernel")) return false;
@@ -586,8 +625,11 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     configure_branch_kernels();
     c->stage_cap = 1 << 20;
     if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
-        !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc"))
+        !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc") ||
+        !c->cuda(cudaHostAlloc((void**)&c->h_mapped, 64, cudaHostAllocMapped), "mapped alloc") ||
+        !c->cuda(cudaHostGetDevicePointer((void**)&c->d_mapped, (void*)c->h_mapped, 0), "mapped pointer"))
         return fail(nullptr, PML_ENOMEM, c->err);
+    c->h_mapped[3] = 0.0;
     if (nranks > 1) {
         if (!unique_id) return fail(nullptr, PML_EINVAL, "unique_id required when nranks > 1");
         std::string err;
@@ -612,6 +654,7 @@ void pml_ctx_destroy(pml_ctx* c) {
     for (auto& b : c->cached_blocks) cudaFree(b.second);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->h_mapped) cudaFreeHost((void*)c->h_mapped);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
     for (auto e : c->spare_events) cudaEventDestroy(e);
     delete c;

@@ -25,13 +25,22 @@ __device__ __forceinline__ void load_row20(const double* __restrict__ src, doubl
 }
 
 // ------------------------------------------------------------------------------------------------ P(t) ----
+__device__ __forceinline__ void make_p_block(const DeviceModel* __restrict__ dm, double t, bool want_tip, PBlock* __restrict__ blocks);
+
 __global__ void __launch_bounds__(256) k_make_p(const DeviceModel* __restrict__ dm, const double* __restrict__ lengths,
                                                 const uint8_t* __restrict__ want_tip, PBlock* __restrict__ blocks) {
+    make_p_block(dm, lengths[blockIdx.x], want_tip[blockIdx.x] != 0, blocks);
+}
+
+__global__ void __launch_bounds__(256) k_make_p_inline(const DeviceModel* __restrict__ dm, const MakePInline batch, PBlock* __restrict__ blocks) {
+    make_p_block(dm, batch.length[blockIdx.x], batch.want_tip[blockIdx.x] != 0, blocks);
+}
+
+__device__ __forceinline__ void make_p_block(const DeviceModel* __restrict__ dm, const double t, const bool want_tip, PBlock* __restrict__ blocks) {
     __shared__ double s_exp[kCats][kStates];
     __shared__ double s_P[kCats][kStates][kStates];
     __shared__ double s_V[kStates][kStates + 1], s_Vinv[kStates][kStates];
     const int b = blockIdx.x;
-    const double t = lengths[b];
     if (threadIdx.x < kRow) {
         const int c = threadIdx.x / kStates, k = threadIdx.x % kStates;
         s_exp[c][k] = exp(dm->lambda[k] * dm->rates[c] * t);
@@ -49,7 +58,7 @@ __global__ void __launch_bounds__(256) k_make_p(const DeviceModel* __restrict__ 
         s_P[c][i][j] = acc;
         blocks[b].P[c][i][j] = acc;
     }
-    if (!want_tip[b]) return;
+    if (!want_tip) return;
     __syncthreads();
     for (int idx = threadIdx.x; idx < kCodes * kRow; idx += blockDim.x) {
         const int code = idx / kRow, c = (idx % kRow) / kStates, i = idx % kStates;
@@ -94,12 +103,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------------ NR core --
 __global__ void __launch_bounds__(kThreads) k_core(const DeviceModel* __restrict__ dm, const double* __restrict__ sumtable,
                                                    const int32_t* __restrict__ sum_scale, const int32_t* __restrict__ weights,
-                                                   int64_t np, const double* __restrict__ d_t, double* __restrict__ partials) {
+                                                   int64_t np, const double t, double* __restrict__ partials) {
     __shared__ double s_e[3][kCats][kStates];
     __shared__ double s_f[3][kCats][kPatternsPerBlock];
     if (threadIdx.x < kRow) {
         const int c = threadIdx.x / kStates, k = threadIdx.x % kStates;
-        const double a = dm->lambda[k] * dm->rates[c], e = exp(a * d_t[0]);
+        const double a = dm->lambda[k] * dm->rates[c], e = exp(a * t);
         s_e[0][c][k] = e;
         s_e[1][c][k] = a * e;
         s_e[2][c][k] = a * a * e;
@@ -169,10 +178,14 @@ void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t
     if (nblocks > 0) k_make_p<<<nblocks, 256, 0, stream>>>(dm, d_lengths, d_want_tip, d_blocks);
 }
 
+void launch_make_p_inline(const DeviceModel* dm, const MakePInline& batch, PBlock* d_blocks, int nblocks, cudaStream_t stream) {
+    if (nblocks > 0) k_make_p_inline<<<nblocks, 256, 0, stream>>>(dm, batch, d_blocks);
+}
+
 void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np,
-                 const double* d_t, double* partials, double* result, cudaStream_t stream) {
+                 double t, double* partials, double* result, cudaStream_t stream) {
     const int grid = blocks_for(np);
-    k_core<<<grid, kThreads, 0, stream>>>(dm, sumtable, sum_scale, weights, np, d_t, partials);
+    k_core<<<grid, kThreads, 0, stream>>>(dm, sumtable, sum_scale, weights, np, t, partials);
     k_reduce<<<1, 1024, 0, stream>>>(partials, grid, 3, result);
 }
 

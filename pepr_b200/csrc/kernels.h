@@ -41,6 +41,13 @@ struct NewviewOp {
 };
 
 // P(t) for `nblocks` branches: lengths[b] in expected substitutions per site; tips[b] != 0 also fills PBlock::tip
+// small batches travel as kernel arguments (no staging copy): up to kMakePInline branches
+constexpr int kMakePInline = 32;
+struct MakePInline {
+    double length[kMakePInline];
+    uint8_t want_tip[kMakePInline];
+};
+void launch_make_p_inline(const DeviceModel* dm, const MakePInline& batch, PBlock* d_blocks, int nblocks, cudaStream_t stream);
 void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t* d_want_tip, PBlock* d_blocks, int nblocks, cudaStream_t stream);
 
 // CLV update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 64 and all buffers hold np rows
@@ -54,20 +61,24 @@ struct BranchArgs {
     Side a, b;
     const DeviceModel* dm;
     const int32_t* weights;
-    const double* d_t;
+    double t;             // branch length the sums are evaluated at
     double* site_lnl;     // optional
     double* sumtable;     // optional: np x 80
     int32_t* sum_scale;   // with sumtable
     double* rowsum;       // np x 3 scratch: f, f', f'' per pattern
-    double* partials;     // 3 x ceil(np/256) doubles
+    double* partials;     // 3 x grid doubles
+    unsigned int* ticket; // zero-initialised; the CTA drawing the last ticket adds the partials and resets it
+    double* result;       // 3 doubles in device memory (input of the NCCL allreduce when ranks > 1)
+    volatile double* host_result;  // optional: 4 doubles in mapped pinned memory; [3] receives `sequence` after [0..2]
+    double sequence;
 };
-void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, unsigned int* ticket, double* result, cudaStream_t stream);
+void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
 void configure_branch_kernels();
 // fixed-order sum of `nblocks` partials for each of `nvals` values
 void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream);
 
 // result[0..2] = lnL, dlnL/dt, d2lnL/dt2 at branch length *d_t (device scalar) from a sumtable
-void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np, const double* d_t,
+void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np, double t,
                  double* partials, double* result, cudaStream_t stream);
 
 // lnl[r] = sum_p W[r][p] * site_lnl[p]

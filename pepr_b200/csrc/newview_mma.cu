@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
         next_code[0] = __ldg(codes + (int64_t)first * kTileRows + g);
         next_code[1] = __ldg(codes + (int64_t)first * kTileRows + 8 + g);
     }
+    int32_t next_sc[4] = {0, 0, 0, 0};
+    if (c == 0 && t == 0 && first < ntiles) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            if (!kTipL) next_sc[m] = __ldg(op.left.scale + (int64_t)first * kTileRows + m * 8 + g);
+            if (!kTipR) next_sc[2 + m] = __ldg(op.right.scale + (int64_t)first * kTileRows + m * 8 + g);
+        }
+    }
     int it = 0;
     for (int tile = first; tile < ntiles; tile += stride, ++it) {
         const int slot = it % kDepth;
@@ -117,13 +125,15 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
             next_code[0] = __ldg(codes + row0 + (int64_t)stride * kTileRows + g);
             next_code[1] = __ldg(codes + row0 + (int64_t)stride * kTileRows + 8 + g);
         }
-        // the children's scaling counts are only needed after the MMAs: issue the loads now, consume them at the end
-        int32_t scl[2] = {0, 0}, scr[2] = {0, 0};
-        if (c == 0 && t == 0) {
+        // the children's scaling counts travel one iteration ahead (like the tip codes): their DRAM latency never stalls
+        // the category-0 warp, which would otherwise hold up the other three at the group barrier
+        const int32_t scl[2] = {next_sc[0], next_sc[1]}, scr[2] = {next_sc[2], next_sc[3]};
+        if (c == 0 && t == 0 && tile + stride < ntiles) {
+            const int64_t nrow = row0 + (int64_t)stride * kTileRows;
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                if (!kTipL) scl[m] = __ldg(op.left.scale + row0 + m * 8 + g);
-                if (!kTipR) scr[m] = __ldg(op.right.scale + row0 + m * 8 + g);
+                if (!kTipL) next_sc[m] = __ldg(op.left.scale + nrow + m * 8 + g);
+                if (!kTipR) next_sc[2 + m] = __ldg(op.right.scale + nrow + m * 8 + g);
             }
         }
         mbar_wait(gfull + slot, (it / kDepth) & 1);
@@ -218,23 +228,32 @@ __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op)
     }
     __syncthreads();
     // row maxima of both lookups bound every product: max_l * max_r from above, l[arg] * r[arg] from below
-    if (threadIdx.x < 2 * kCodes) {
-        const bool right = threadIdx.x >= kCodes;
-        const int code = threadIdx.x - (right ? kCodes : 0);
+    for (int rowid = threadIdx.x >> 5; rowid < 2 * kCodes; rowid += kTipTipThreads / 32) {  // one warp per lookup row
+        const bool right = rowid >= kCodes;
+        const int code = rowid - (right ? kCodes : 0), lane = threadIdx.x & 31;
         const double* row = (right ? s_r : s_l) + code * kRow;
-        double big = 0.0;
+        double big = -1.0;
         int arg = 0;
-        for (int i = 0; i < kRow; ++i) {
-            const int k = (i + threadIdx.x) % kRow;
+        for (int k = lane; k < kRow; k += 32)
             if (fabs(row[k]) > big) {
                 big = fabs(row[k]);
                 arg = k;
             }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, big, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > big || (ob == big && oa < arg)) {
+                big = ob;
+                arg = oa;
+            }
         }
-        if (right) s_maxr[code] = big;
-        else {
-            s_maxl[code] = big;
-            s_argl[code] = arg;
+        if (lane == 0) {
+            if (right) s_maxr[code] = big;
+            else {
+                s_maxl[code] = big;
+                s_argl[code] = arg;
+            }
         }
     }
     __syncthreads();
