@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU, help="sites per GPU (default: the named workload)")
     ap.add_argument("--ref-sites", type=int, default=0, help="cap of the CPU sample (columns)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bootstrap-reps", type=int, default=0,
+                    help="also time this many bootstrap-replicate trees (second half of BASELINE.json's metric); off by default")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -288,6 +290,21 @@ def main():
         dist.all_reduce(pass_all, op=dist.ReduceOp.MAX)
     pass_value = (NTAX - 2) * npat / (pass_all.item() * 1e-3)
 
+    # ---- optional: bootstrap-replicate trees (replicate weights -> parsimony start tree -> lazy SPR -> branch lengths) ------
+    boot = None
+    if args.bootstrap_reps > 0:
+        W, _ = aln.bootstrap_weights(12345, args.bootstrap_reps)
+        barrier()
+        t0 = time.perf_counter()
+        for r in range(args.bootstrap_reps):
+            bt = pb.Tree(aln, parsimony_seed=12346 + r)
+            bt.optimize(False, 5.0, weights=W[r])
+            bl, bm = bt.search(radius=5, max_rounds=1, eps=0.1, weights=W[r])
+            bt.close()
+        barrier()
+        boot = {"bootstrap_tree_wall_s": (time.perf_counter() - t0) / args.bootstrap_reps, "replicates": args.bootstrap_reps,
+                "what": "replicate site weights (raxmlHPC stream, seed 12345) -> parsimony start tree -> one lazy-SPR round (radius 5) -> branch lengths"}
+
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------------
     tree.close()
     aln.close()
@@ -356,6 +373,8 @@ def main():
             "wall_s_timed_region": wall,
             "site_updates_per_pattern": (su1 - su0) / args.steps / max(npat_local, 1),
         }
+        if boot:
+            out["bootstrap"] = boot
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = args.ref_sites or min(sites, max(500, int(20.0 * 30.0 * cores)))

@@ -126,6 +126,29 @@ int pml_optimize(pml_tree *, int opt_alpha, double eps, const int32_t *weights, 
 /* one smoothing sweep (one guarded NR step on every branch); returns 1 in *converged when no branch moved */
 int pml_smooth_branches(pml_tree *, int sweeps, const int32_t *weights, int *converged);
 
+/* ---- tree search: parsimony start tree + lazy subtree-pruning-regrafting hill climbing --------------------------
+ * Takes over what `-f d` does inside raxmlHPC (makeParsimonyTree, treeOptimizeRapid/rearrangeBIG/testInsertBIG) for
+ * RAxMLRunner.run (RAxMLRunner.java:79-152).  The search is a heuristic: it is compared with the reference by the lnL of
+ * the tree it finds, not move by move.
+ * pml_tree_start_parsimony: randomised stepwise addition under Fitch parsimony (taxon order from the randum stream).
+ * pml_score_spr_candidates: prune inner node `node` together with the subtree behind its neighbour `keep`, insert it
+ *   into every branch within `radius` steps (halved branch, unchanged subtree branch: raxmlHPC's lazy insertion) and
+ *   return the lnL of each candidate; the tree is left unchanged.  targets/lnl: caller arrays of capacity *ncand in,
+ *   number filled out.
+ * pml_search: repeat { for every (node, subtree): best lazy candidate -> apply, re-optimise the branches around the
+ *   insertion, keep if lnL improves } until a whole round gains < eps or max_rounds is reached. */
+int pml_tree_start_parsimony(pml_aln *, int64_t seed, pml_tree **out);
+/* host-only (no GPU): the same start tree as newick text + its parsimony score */
+int64_t pml_parsimony_tree(int ntax, int64_t nsites, const char *const *names, const uint8_t *chars, int64_t seed, char *buf,
+                           size_t cap, int64_t *score);
+/* applies one pruning-regrafting move for good: `node` and the subtree behind its neighbour `keep` go into branch `target`
+ * (one of the branches pml_score_spr_candidates lists); branch ids of unaffected branches are preserved */
+int pml_tree_spr(pml_tree *, int node, int keep, int target);
+int pml_tree_neighbors(const pml_tree *, int node, int nbr[3]);
+int pml_score_spr_candidates(pml_tree *, int node, int keep, int radius, const int32_t *weights, int *targets, double *lnl,
+                             int *ncand);
+int pml_search(pml_tree *, int radius, int max_rounds, double eps, const int32_t *weights, double *lnl, int *accepted_moves);
+
 /* ---- bootstrap replicates as integer site-weight vectors (computeNextReplicate + randum) -------------------
  * Replaces `-x seed -N reps` / `-b seed` weight generation (RAxMLRunner.java:112-124).  out: nrep x npatterns int32,
  * bit-identical to raxmlHPC for the same seed; *seed is advanced so that consecutive calls continue the stream. */

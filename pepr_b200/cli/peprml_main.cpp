@@ -5,9 +5,10 @@
 // pointing `-DraxmlHPC-PTHREADS=<this file>` (or installing it under that name) swaps the engine in with zero Java change.
 // It speaks the file protocol of SURVEY.md section 8b: reads relaxed phylip / newick from the CWD, writes RAxML_info.<n>,
 // RAxML_result.<n>, RAxML_log.<n>, RAxML_perSiteLLs.<n>, RAxML_bipartitions.<n>, RAxML_bipartitionsBranchLabels.<n>,
-// <aln>.BS<k>.  Flags honoured: -f e|g|n|b|j, -m PROTGAMMAWAG, -s, -n, -t, -z, -a, -b, -#/-N, -e, -T (accepted: the
-// pattern-parallel workers of -T are the GPU's SMs here), -w.  `-f d` / `-f a` (tree search) are not part of this round and
-// fail loudly with exit code 2.
+// RAxML_bestTree.<n>, RAxML_parsimonyTree.<n>, RAxML_bootstrap.<n>, <aln>.BS<k>.  Flags honoured: -f d|a|e|g|n|b|j,
+// -m PROTGAMMAWAG, -s, -n, -t, -z, -a, -b, -x, -p, -#/-N, -e, -y, -T (accepted: the pattern-parallel workers of -T are the
+// GPU's SMs here), -w.  `-f d` = parsimony start tree + lazy-SPR hill climbing + model optimisation; `-f a -x seed -N k` =
+// k bootstrap replicates (raxmlHPC's weight stream, a quick search each) + ML search + supports drawn on the ML tree.
 #include <sys/stat.h>
 
 #include <chrono>
@@ -26,7 +27,8 @@ namespace {
 
 struct Args {
     std::string f = "d", model, aln, name, tree, trees, weights, workdir;
-    long long bseed = 0;
+    long long bseed = 0, pseed = 12345;
+    bool parsimony_only = false;
     int reps = 1, threads = 1;
     double eps = 0.1;
 };
@@ -103,14 +105,16 @@ int main(int argc, char** argv) {
         else if (k == "-z") a.trees = val();
         else if (k == "-a") a.weights = val();
         else if (k == "-w") a.workdir = val();
-        else if (k == "-b" || k == "-x" || k == "-p") a.bseed = std::atoll(val().c_str());
+        else if (k == "-b" || k == "-x") a.bseed = std::atoll(val().c_str());
+        else if (k == "-p") a.pseed = std::atoll(val().c_str());
+        else if (k == "-y") a.parsimony_only = true;
         else if (k == "-#" || k == "-N") a.reps = std::atoi(val().c_str());
         else if (k == "-T") a.threads = std::atoi(val().c_str());
         else if (k == "-e") a.eps = std::atof(val().c_str());
         else if (k == "-v") {
             std::printf("%s (raxmlHPC-compatible front end)\n", pml_version());
             return 0;
-        } else if (k == "-y" || k == "-Y" || k == "-k" || k == "-d" || k == "-D" || k == "-F" || k == "-j" || k == "-M") {
+        } else if (k == "-Y" || k == "-k" || k == "-d" || k == "-D" || k == "-F" || k == "-j" || k == "-M") {
             // accepted, no effect on the modes implemented here
         } else die("unknown option " + k);
     }
@@ -119,8 +123,6 @@ int main(int argc, char** argv) {
     const std::string dir = a.workdir.empty() ? std::string() : a.workdir + "/";
     const std::string info_path = dir + "RAxML_info." + a.name;
     if (exists(info_path)) die("RAxML output files with the run ID <" + a.name + "> already exist", 1);  // raxmlHPC refuses too
-    if (a.f == "d" || a.f == "a" || a.f == "o")
-        die("-f " + a.f + " (ML tree search) is not implemented by the B200 engine in this round; supported: -f e, g, n, b, j", 2);
 
     const auto t_start = std::chrono::steady_clock::now();
     std::ofstream info(info_path);
@@ -204,6 +206,73 @@ int main(int argc, char** argv) {
                 out << "\n";
             }
         }
+        return 0;
+    }
+
+    if (a.f == "d" || a.f == "a" || a.f == "o") {
+        // ---- ML tree search (RAxMLRunner.run: `-f d`, or `-f a -x seed -N reps` when bootstrapReps > 0) ----------------
+        auto search_tree = [&](const int32_t* w, int64_t pseed, int rounds, bool final_opt, double* lnl_out, double* alpha_out) {
+            pml_tree* t = nullptr;
+            check(ctx, pml_model_set(aln, a.model.c_str(), 1.0), "model");
+            check(ctx, pml_tree_start_parsimony(aln, pseed, &t), "parsimony start tree");
+            double lnl = 0.0, alpha = 1.0;
+            check(ctx, pml_optimize(t, 1, 5.0, w, &lnl, &alpha), "initial optimisation");
+            int moves = 0;
+            check(ctx, pml_search(t, 5, rounds, a.eps, w, &lnl, &moves), "tree search");
+            if (final_opt) check(ctx, pml_optimize(t, 1, a.eps, w, &lnl, &alpha), "final optimisation");
+            if (lnl_out) *lnl_out = lnl;
+            if (alpha_out) *alpha_out = alpha;
+            return t;
+        };
+        if (a.parsimony_only) {  // `-y`: stop after the parsimony start tree (RAxMLRunner.runRaxmlParsimonyWithBranchLengths, 1st run)
+            pml_tree* t = nullptr;
+            check(ctx, pml_tree_start_parsimony(aln, a.pseed, &t), "parsimony start tree");
+            std::string s = tree_string(t);
+            std::ofstream(dir + "RAxML_parsimonyTree." + a.name) << s << "\n";
+            return 0;
+        }
+        std::vector<std::string> boots;
+        if (a.f == "a") {
+            std::vector<int32_t> W((size_t)npat * a.reps);
+            int64_t seed = a.bseed;
+            check(ctx, pml_bootstrap_weights(aln, &seed, a.reps, W.data()), "bootstrap weights");
+            std::ofstream bs(dir + "RAxML_bootstrap." + a.name);
+            for (int r = 0; r < a.reps; ++r) {
+                pml_tree* t = search_tree(W.data() + (size_t)r * npat, a.pseed + 1 + r, 1, false, nullptr, nullptr);
+                boots.push_back(tree_string(t));
+                bs << boots.back() << "\n";
+                pml_tree_free(t);
+            }
+        }
+        double lnl = 0.0, alpha = 1.0;
+        pml_tree* t = search_tree(nullptr, a.pseed, 10, true, &lnl, &alpha);
+        const std::string best = tree_string(t);
+        std::ofstream(dir + "RAxML_result." + a.name) << best << "\n";
+        std::ofstream(dir + "RAxML_bestTree." + a.name) << best << "\n";
+        char buf[64];
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        std::snprintf(buf, sizeof buf, "%.6f", lnl);
+        std::ofstream(dir + "RAxML_log." + a.name) << secs << " " << buf << "\n";
+        info << "Final GAMMA-based Score of best tree " << buf << "\n";
+        info << "Final GAMMA  likelihood: " << buf << "\n";
+        std::snprintf(buf, sizeof buf, "%.6f", alpha);
+        info << "alpha: " << buf << "\n";
+        std::snprintf(buf, sizeof buf, "%.6f", tree_length(t));
+        info << "Tree-Length: " << buf << "\n";
+        info << "Overall execution time: " << secs << " secs\n";
+        if (a.f == "a") {
+            std::vector<const char*> ptr;
+            for (auto& s : boots) ptr.push_back(s.c_str());
+            const int64_t n = pml_support_tree(best.c_str(), ptr.data(), (int)ptr.size(), 1, nullptr, 0);
+            if (n < 0) die(std::string("supports: ") + pml_last_error(nullptr), 3);
+            std::string out((size_t)n, '\0');
+            pml_support_tree(best.c_str(), ptr.data(), (int)ptr.size(), 1, out.data(), (size_t)n);
+            out.resize(std::strlen(out.c_str()));
+            std::ofstream(dir + "RAxML_bipartitions." + a.name) << out << "\n";
+        }
+        pml_tree_free(t);
+        pml_aln_free(aln);
+        pml_ctx_destroy(ctx);
         return 0;
     }
 

@@ -581,6 +581,74 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
     return true;
 }
 
+// lnL of the tree at branch e without touching parameters (weights already on the device)
+bool lnl_at(pml_tree* t, int e, const int32_t* dw, double& lnl) {
+    double r[3];
+    if (!branch_pass(t, e, dw, t->topo.len[e], false, false, r)) return false;
+    lnl = r[0];
+    return true;
+}
+
+// a few guarded NR steps on one branch
+bool polish_branch(pml_tree* t, int e, const int32_t* dw, int iters) {
+    double z;
+    if (!newton_branch(t, e, dw, iters, z)) return false;
+    set_branch(t, e, -std::log(z));
+    return true;
+}
+
+struct SearchStats {
+    int64_t candidates = 0;
+    int accepted = 0;
+};
+
+// one pass over every (node, subtree) pair: lazy scores for all targets, thorough check of the best one
+bool spr_round(pml_tree* t, const int32_t* dw, int radius, double& best, SearchStats& st) {
+    Topology& T = t->topo;
+    const int root_branch = T.edge[0][0];
+    for (int p = T.ntax; p < T.nnodes(); ++p) {
+        for (int k = 0; k < 3; ++k) {
+            const int s = T.nbr[p][k];
+            const std::vector<int> targets = spr_targets(T, p, s, radius);
+            if (targets.empty()) continue;
+            int best_target = -1;
+            double best_lazy = -1e300;
+            for (int tgt : targets) {
+                SprMove mv;
+                if (!spr_apply(T, t->views, p, s, tgt, mv)) continue;
+                t->prepared_branch = -1;
+                double l;
+                const bool ok = lnl_at(t, mv.e_s, dw, l);
+                spr_undo(T, t->views, mv);
+                if (!ok) return false;
+                ++st.candidates;
+                if (l > best_lazy) {
+                    best_lazy = l;
+                    best_target = tgt;
+                }
+            }
+            // the lazy score leaves three branches unoptimised, so a candidate slightly below the current tree may still win
+            if (best_target < 0 || best_lazy < best - 2.0) continue;
+            SprMove mv;
+            if (!spr_apply(T, t->views, p, s, best_target, mv)) continue;
+            t->prepared_branch = -1;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int e : {mv.e_t, mv.e_r, mv.e_s, mv.e_q})
+                    if (!polish_branch(t, e, dw, 3)) return false;
+            double cand;
+            if (!lnl_at(t, root_branch, dw, cand)) return false;
+            if (cand > best + 1e-3) {
+                best = cand;
+                ++st.accepted;
+                break;  // p's surroundings changed: go on with the next node
+            }
+            spr_undo(T, t->views, mv);
+            t->prepared_branch = -1;
+        }
+    }
+    return true;
+}
+
 int fail(pml_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     else g_create_error = msg;
@@ -993,6 +1061,105 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
     } while (std::fabs(cur - best) > eps && ++rounds < 200);
     if (lnl) *lnl = best;
     if (alpha) *alpha = a->alpha;
+    return PML_OK;
+}
+
+int pml_tree_start_parsimony(pml_aln* a, int64_t seed, pml_tree** out) {
+    if (!a || !out) return PML_EINVAL;
+    pml_ctx* c = a->ctx;
+    *out = nullptr;
+    Topology topo;
+    parsimony_start_tree(a->pat, seed, kDefaultLen, topo, nullptr);
+    if (topo.ntax != a->pat.ntax) return fail(c, PML_EINVAL, "parsimony start tree failed");
+    const std::string text = write_newick_result(topo, a->pat.names);
+    return pml_tree_load(a, text.substr(0, text.size() - 5).append(";").c_str(), out);
+}
+
+int64_t pml_parsimony_tree(int ntax, int64_t nsites, const char* const* names, const uint8_t* chars, int64_t seed, char* buf,
+                           size_t cap, int64_t* score) {
+    if (ntax < 3 || nsites < 1 || !names || !chars) return PML_EINVAL;
+    Patterns pat;
+    crunch_patterns(ntax, nsites, chars, nullptr, pat);
+    for (int i = 0; i < ntax; ++i) pat.names.emplace_back(names[i]);
+    Topology topo;
+    parsimony_start_tree(pat, seed, kDefaultLen, topo, score);
+    if (topo.ntax != ntax) return fail(nullptr, PML_EINVAL, "parsimony start tree failed");
+    const std::string s = write_newick_result(topo, pat.names);
+    if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size() + 1;
+}
+
+int pml_tree_spr(pml_tree* t, int node, int keep, int target) {
+    if (!t) return PML_EINVAL;
+    Topology& T = t->topo;
+    if (node < T.ntax || node >= T.nnodes() || T.slot_of(node, keep) < 0 || target < 0 || target >= T.nedges())
+        return fail(t->aln->ctx, PML_EINVAL, "bad pruning-regrafting move");
+    const std::vector<int> ok = spr_targets(T, node, keep, T.nnodes());
+    if (std::find(ok.begin(), ok.end(), target) == ok.end())
+        return fail(t->aln->ctx, PML_EINVAL, "target branch lies inside the moved subtree or next to the pruning point");
+    SprMove mv;
+    if (!spr_apply(T, t->views, node, keep, target, mv)) return fail(t->aln->ctx, PML_EINVAL, "move rejected");
+    t->prepared_branch = -1;
+    return PML_OK;
+}
+
+int pml_tree_neighbors(const pml_tree* t, int node, int nbr[3]) {
+    if (!t || !nbr || node < 0 || node >= t->topo.nnodes()) return PML_EINVAL;
+    for (int k = 0; k < 3; ++k) nbr[k] = t->topo.nbr[node][k];
+    return PML_OK;
+}
+
+int pml_score_spr_candidates(pml_tree* t, int node, int keep, int radius, const int32_t* weights, int* targets, double* lnl,
+                             int* ncand) {
+    if (!t || !ncand || !targets || !lnl || radius < 1) return PML_EINVAL;
+    Topology& T = t->topo;
+    if (node < T.ntax || node >= T.nnodes() || T.slot_of(node, keep) < 0) return fail(t->aln->ctx, PML_EINVAL, "bad (node, keep) pair");
+    pml_ctx* c = t->aln->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    const int32_t* dw = device_weights(t->aln, weights);
+    if (!dw) return PML_ENODEVICE;
+    const std::vector<int> cand = spr_targets(T, node, keep, radius);
+    int n = 0;
+    for (int tgt : cand) {
+        if (n >= *ncand) break;
+        SprMove mv;
+        if (!spr_apply(T, t->views, node, keep, tgt, mv)) continue;
+        t->prepared_branch = -1;
+        double l;
+        const bool ok = lnl_at(t, mv.e_s, dw, l);
+        spr_undo(T, t->views, mv);
+        t->prepared_branch = -1;
+        if (!ok) return PML_ENODEVICE;
+        targets[n] = tgt;
+        lnl[n] = l;
+        ++n;
+    }
+    *ncand = n;
+    return PML_OK;
+}
+
+int pml_search(pml_tree* t, int radius, int max_rounds, double eps, const int32_t* weights, double* lnl, int* accepted_moves) {
+    if (!t || radius < 1 || max_rounds < 1) return PML_EINVAL;
+    pml_ctx* c = t->aln->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    if (!(eps > 0.0)) eps = 0.1;
+    const int32_t* dw = device_weights(t->aln, weights);
+    if (!dw) return PML_ENODEVICE;
+    double best;
+    if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return PML_ENODEVICE;
+    SearchStats st;
+    for (int round = 0; round < max_rounds; ++round) {
+        const double before = best;
+        if (!spr_round(t, dw, radius, best, st)) return PML_ENODEVICE;
+        // settle all branch lengths on the new topology before the next round
+        bool smoothed = false;
+        for (int sweep = 0; sweep < 2 && !smoothed; ++sweep)
+            if (!smooth_sweep(t, dw, smoothed)) return PML_ENODEVICE;
+        if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return PML_ENODEVICE;
+        if (best - before < eps) break;
+    }
+    if (lnl) *lnl = best;
+    if (accepted_moves) *accepted_moves = st.accepted;
     return PML_OK;
 }
 

@@ -541,3 +541,263 @@ std::string support_tree(const std::string& main_newick, const std::vector<std::
 }
 
 }  // namespace pml
+
+// =========================================================================================== SPR ============
+namespace pml {
+
+namespace {
+void set_link(Topology& T, int v, int old_nb, int new_nb, int e) {
+    const int s = T.slot_of(v, old_nb);
+    T.nbr[v][s] = new_nb;
+    T.edge[v][s] = e;
+}
+}  // namespace
+
+bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv) {
+    if (T.is_tip(p)) return false;
+    mv = SprMove();
+    mv.p = p;
+    mv.s = s;
+    for (int k = 0; k < 3; ++k) {
+        const int nb = T.nbr[p][k];
+        if (nb == s) mv.e_s = T.edge[p][k];
+        else if (mv.q < 0) {
+            mv.q = nb;
+            mv.e_q = T.edge[p][k];
+            mv.slot_q = k;
+        } else {
+            mv.r = nb;
+            mv.e_r = T.edge[p][k];
+            mv.slot_r = k;
+        }
+    }
+    if (mv.e_s < 0 || mv.r < 0 || target == mv.e_q || target == mv.e_r || target == mv.e_s) return false;
+    mv.e_t = target;
+    mv.a = T.ea[target];
+    mv.b = T.eb[target];
+    mv.len_q = T.len[mv.e_q];
+    mv.len_r = T.len[mv.e_r];
+    mv.len_t = T.len[target];
+    // prune: q -- r through branch e_q
+    set_link(T, mv.q, p, mv.r, mv.e_q);
+    set_link(T, mv.r, p, mv.q, mv.e_q);
+    T.ea[mv.e_q] = mv.q;
+    T.eb[mv.e_q] = mv.r;
+    T.len[mv.e_q] = mv.len_q + mv.len_r;
+    // regraft: a -- p through e_t, p -- b through e_r
+    set_link(T, mv.a, mv.b, p, mv.e_t);
+    set_link(T, mv.b, mv.a, p, mv.e_r);
+    T.nbr[p][mv.slot_q] = mv.a;
+    T.edge[p][mv.slot_q] = mv.e_t;
+    T.nbr[p][mv.slot_r] = mv.b;
+    T.edge[p][mv.slot_r] = mv.e_r;
+    T.ea[mv.e_t] = mv.a;
+    T.eb[mv.e_t] = p;
+    T.ea[mv.e_r] = p;
+    T.eb[mv.e_r] = mv.b;
+    T.len[mv.e_t] = T.len[mv.e_r] = 0.5 * mv.len_t;
+    V.orient[p - T.ntax] = -1;
+    V.branch_changed(T, mv.e_q);
+    V.branch_changed(T, mv.e_t);
+    V.branch_changed(T, mv.e_r);
+    return true;
+}
+
+void spr_undo(Topology& T, ViewState& V, const SprMove& mv) {
+    const int p = mv.p;
+    // detach from a, b
+    set_link(T, mv.a, p, mv.b, mv.e_t);
+    set_link(T, mv.b, p, mv.a, mv.e_t);
+    T.ea[mv.e_t] = mv.a;
+    T.eb[mv.e_t] = mv.b;
+    T.len[mv.e_t] = mv.len_t;
+    // back between q and r
+    set_link(T, mv.q, mv.r, p, mv.e_q);
+    set_link(T, mv.r, mv.q, p, mv.e_r);
+    T.nbr[p][mv.slot_q] = mv.q;
+    T.edge[p][mv.slot_q] = mv.e_q;
+    T.nbr[p][mv.slot_r] = mv.r;
+    T.edge[p][mv.slot_r] = mv.e_r;
+    T.ea[mv.e_q] = p;
+    T.eb[mv.e_q] = mv.q;
+    T.ea[mv.e_r] = p;
+    T.eb[mv.e_r] = mv.r;
+    T.len[mv.e_q] = mv.len_q;
+    T.len[mv.e_r] = mv.len_r;
+    V.orient[p - T.ntax] = -1;
+    V.branch_changed(T, mv.e_q);
+    V.branch_changed(T, mv.e_t);
+    V.branch_changed(T, mv.e_r);
+}
+
+std::vector<int> spr_targets(const Topology& T, int p, int s, int radius) {
+    std::vector<int> out;
+    if (T.is_tip(p)) return out;
+    int q = -1, r = -1;
+    for (int k = 0; k < 3; ++k) {
+        const int nb = T.nbr[p][k];
+        if (nb == s) continue;
+        (q < 0 ? q : r) = nb;
+    }
+    // walk away from p through q and through r; depth counts branches beyond the two next to p
+    struct Item { int node, from, depth; };
+    std::vector<Item> stack{{q, p, 0}, {r, p, 0}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (T.is_tip(it.node) || it.depth >= radius) continue;
+        for (int k = 0; k < 3; ++k) {
+            const int nb = T.nbr[it.node][k];
+            if (nb == it.from) continue;
+            out.push_back(T.edge[it.node][k]);
+            stack.push_back({nb, it.node, it.depth + 1});
+        }
+    }
+    return out;
+}
+
+// =========================================================================================== parsimony ======
+namespace {
+
+inline uint32_t code_mask(int code) {
+    if (code < 20) return 1u << code;
+    if (code == 20) return (1u << 2) | (1u << 3);
+    if (code == 21) return (1u << 5) | (1u << 6);
+    return 0xFFFFFu;
+}
+
+struct GrowTree {
+    // rooted at the first taxon: node 0 = root tip; every other node has a parent; inner nodes have two children
+    std::vector<int> parent, left, right, taxon;
+    int add_node(int tx) {
+        parent.push_back(-1);
+        left.push_back(-1);
+        right.push_back(-1);
+        taxon.push_back(tx);
+        return (int)parent.size() - 1;
+    }
+};
+
+}  // namespace
+
+void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score_out) {
+    const int n = pat.ntax;
+    const int64_t P = pat.npat;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    for (int i = n - 1; i > 0; --i) {  // Fisher-Yates on the randum stream
+        const int j = (int)((double)(i + 1) * randum(&seed));
+        std::swap(order[i], order[j < 0 ? 0 : (j > i ? i : j)]);
+    }
+    std::vector<std::vector<uint32_t>> tipmask(n, std::vector<uint32_t>((size_t)P));
+    for (int t = 0; t < n; ++t)
+        for (int64_t s = 0; s < P; ++s) tipmask[t][s] = code_mask(pat.codes[(size_t)t * P + s]);
+
+    GrowTree g;
+    const int root = g.add_node(order[0]);  // the root tip hangs above the single top node
+    int top = g.add_node(-1);
+    {
+        const int a = g.add_node(order[1]), b = g.add_node(order[2]);
+        g.left[top] = a;
+        g.right[top] = b;
+        g.parent[a] = g.parent[b] = top;
+        g.parent[top] = root;
+        g.left[root] = top;
+    }
+    std::vector<std::vector<uint32_t>> down, up;  // per node: Fitch set of the subtree below / of everything above
+    int64_t total_score = 0;
+    for (int k = 3; k <= n; ++k) {
+        const int N = (int)g.parent.size();
+        down.assign(N, {});
+        up.assign(N, {});
+        // post-order
+        std::vector<int> post, stack{g.left[root]};
+        while (!stack.empty()) {
+            const int v = stack.back();
+            stack.pop_back();
+            post.push_back(v);
+            if (g.left[v] >= 0) {
+                stack.push_back(g.left[v]);
+                stack.push_back(g.right[v]);
+            }
+        }
+        int64_t score = 0;
+        for (int i = (int)post.size() - 1; i >= 0; --i) {
+            const int v = post[i];
+            if (g.left[v] < 0) {
+                down[v] = tipmask[g.taxon[v]];
+                continue;
+            }
+            const auto &A = down[g.left[v]], &B = down[g.right[v]];
+            down[v].resize((size_t)P);
+            for (int64_t s = 0; s < P; ++s) {
+                const uint32_t x = A[s] & B[s];
+                if (x) down[v][s] = x;
+                else {
+                    down[v][s] = A[s] | B[s];
+                    score += pat.weight[s];
+                }
+            }
+        }
+        {
+            const auto &A = down[g.left[root]], &B = tipmask[g.taxon[root]];
+            for (int64_t s = 0; s < P; ++s)
+                if (!(A[s] & B[s])) score += pat.weight[s];
+        }
+        total_score = score;
+        if (k == n) break;
+        // pre-order: set above each node
+        up[g.left[root]] = tipmask[g.taxon[root]];
+        for (int v : post) {
+            if (g.left[v] < 0) continue;
+            for (int side = 0; side < 2; ++side) {
+                const int c = side ? g.right[v] : g.left[v], sib = side ? g.left[v] : g.right[v];
+                up[c].resize((size_t)P);
+                const auto &U = up[v], &S = down[sib];
+                for (int64_t s = 0; s < P; ++s) {
+                    const uint32_t x = U[s] & S[s];
+                    up[c][s] = x ? x : (U[s] | S[s]);
+                }
+            }
+        }
+        // cheapest branch (above node v) for the next taxon
+        const std::vector<uint32_t>& X = tipmask[order[k]];
+        int best_v = -1;
+        int64_t best_cost = 0;
+        for (int v : post) {
+            const auto &U = up[v], &D = down[v];
+            int64_t cost = 0;
+            for (int64_t s = 0; s < P; ++s) {
+                uint32_t e = U[s] & D[s];
+                if (!e) e = U[s] | D[s];
+                if (!(e & X[s])) cost += pat.weight[s];
+            }
+            if (best_v < 0 || cost < best_cost) {
+                best_v = v;
+                best_cost = cost;
+            }
+        }
+        // insert a new inner node above best_v
+        const int w = g.add_node(-1), x = g.add_node(order[k]);
+        const int par = g.parent[best_v];
+        g.parent[w] = par;
+        if (g.left[par] == best_v) g.left[par] = w; else g.right[par] = w;
+        g.left[w] = best_v;
+        g.right[w] = x;
+        g.parent[best_v] = g.parent[x] = w;
+    }
+    if (score_out) *score_out = total_score;
+    // to newick (root tip joined to the top node as a trifurcation), then through the ordinary parser
+    std::function<std::string(int)> nw = [&](int v) -> std::string {
+        if (g.left[v] < 0) return pat.names[g.taxon[v]];
+        return "(" + nw(g.left[v]) + "," + nw(g.right[v]) + ")";
+    };
+    const int t0 = g.left[root];
+    std::string text;
+    if (g.left[t0] >= 0) text = "(" + pat.names[g.taxon[root]] + "," + nw(g.left[t0]) + "," + nw(g.right[t0]) + ");";
+    else text = "(" + pat.names[g.taxon[root]] + "," + nw(t0) + ");";
+    std::string err;
+    parse_newick(text, pat.names, default_len, out, err);
+}
+
+}  // namespace pml

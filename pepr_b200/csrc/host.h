@@ -72,3 +72,28 @@ std::string support_tree(const std::string& main_newick, const std::vector<std::
                          std::vector<int32_t>* counts, std::string& err);
 
 }  // namespace pml
+
+namespace pml {
+
+// ---- topology editing (subtree pruning and regrafting) ------------------------------------------------------
+// Moves inner node p together with the subtree behind its neighbour s: the other two neighbours q and r of p are joined
+// by one branch (length = sum), and p is inserted into `target` (each half gets half of its length).  Views whose subtree
+// changed are marked stale.  `undo` restores node links, branch ids and lengths exactly.
+struct SprMove {
+    int p = -1, s = -1, q = -1, r = -1, a = -1, b = -1;
+    int e_s = -1, e_q = -1, e_r = -1, e_t = -1;
+    int slot_q = -1, slot_r = -1;  // p's own link slots (q and r may coincide with a or b, so p is never searched by value)
+    double len_q = 0, len_r = 0, len_t = 0;
+};
+bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv);
+void spr_undo(Topology& T, ViewState& V, const SprMove& mv);
+// branches of the tree that remains after pruning (p, s), at 1..radius steps from the pruning point, excluding the subtree
+// behind s and the two branches next to p (re-inserting there gives the same topology)
+std::vector<int> spr_targets(const Topology& T, int p, int s, int radius);
+
+// ---- parsimony starting tree ---------------------------------------------------------------------------------
+// randomised stepwise addition under Fitch parsimony on the weighted patterns (raxmlHPC makeParsimonyTree's role);
+// taxa are added in a random order drawn from randum(seed); all branch lengths are set to default_len
+void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score);
+
+}  // namespace pml

@@ -209,8 +209,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
 constexpr int kTipTipThreads = 256;
 constexpr int kTipTipRows = 128;  // one CTA per 128-row tile; many small CTAs per SM hide the code-load latency
 __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op) {
-    __shared__ __align__(16) double s_l[kCodes * kRow];
-    __shared__ __align__(16) double s_r[kCodes * kRow];
+    __shared__ __align__(16) double s_l[kCodes * kTipPad];  // rows padded: the 8 rows a warp gathers from hit different banks
+    __shared__ __align__(16) double s_r[kCodes * kTipPad];
     __shared__ double s_maxl[kCodes], s_maxr[kCodes];
     __shared__ int s_argl[kCodes];
     __shared__ uint8_t s_flag[kCodes * kCodes];
@@ -223,15 +223,15 @@ __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op)
         my_r = __ldg(op.right.codes + row0 + threadIdx.x);
     }
     for (int i = threadIdx.x; i < kCodes * kRow; i += kTipTipThreads) {
-        s_l[i] = (&op.pleft->tip[0][0])[i];
-        s_r[i] = (&op.pright->tip[0][0])[i];
+        s_l[(i / kRow) * kTipPad + i % kRow] = (&op.pleft->tip[0][0])[i];
+        s_r[(i / kRow) * kTipPad + i % kRow] = (&op.pright->tip[0][0])[i];
     }
     __syncthreads();
     // row maxima of both lookups bound every product: max_l * max_r from above, l[arg] * r[arg] from below
     for (int rowid = threadIdx.x >> 5; rowid < 2 * kCodes; rowid += kTipTipThreads / 32) {  // one warp per lookup row
         const bool right = rowid >= kCodes;
         const int code = rowid - (right ? kCodes : 0), lane = threadIdx.x & 31;
-        const double* row = (right ? s_r : s_l) + code * kRow;
+        const double* row = (right ? s_r : s_l) + code * kTipPad;
         double big = -1.0;
         int arg = 0;
         for (int k = lane; k < kRow; k += 32)
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op)
     __syncthreads();
     for (int pair = threadIdx.x; pair < kCodes * kCodes; pair += kTipTipThreads) {
         const int cl = pair / kCodes, cr = pair % kCodes;
-        const double* a = s_l + cl * kRow;
-        const double* b = s_r + cr * kRow;
+        const double* a = s_l + cl * kTipPad;
+        const double* b = s_r + cr * kTipPad;
         uint8_t flag;
         if (s_maxl[cl] * s_maxr[cr] < kMinLik) flag = 1;                               // every product is below 2^-256
         else if (fabs(a[s_argl[cl]] * b[s_argl[cl]]) >= kMinLik) flag = 0;            // one product is certainly not
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op)
         }
         const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
         const int cl = s_pair[r][0], cr = s_pair[r][1];
-        const double2 a = reinterpret_cast<const double2*>(s_l + cl * kRow)[k];
-        const double2 b = reinterpret_cast<const double2*>(s_r + cr * kRow)[k];
+        const double2 a = reinterpret_cast<const double2*>(s_l + cl * kTipPad)[k];
+        const double2 b = reinterpret_cast<const double2*>(s_r + cr * kTipPad)[k];
         double2 v = make_double2(a.x * b.x, a.y * b.y);
         if (s_flag[cl * kCodes + cr]) {
             v.x *= kTwo256;

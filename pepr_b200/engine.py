@@ -63,6 +63,13 @@ def lib():
         L.pml_support_tree.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.pml_support_counts.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.pml_comm_unique_id.argtypes = [C.c_char_p]
+        L.pml_parsimony_tree.restype = C.c_int64
+        L.pml_parsimony_tree.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_int64, C.c_char_p, C.c_size_t, c_i64p]
+        L.pml_tree_spr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.pml_tree_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.pml_tree_start_parsimony.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.pml_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, c_f64p, C.POINTER(C.c_int)]
+        L.pml_score_spr_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.pml_profile_begin.argtypes = [C.c_void_p]
         L.pml_timer_start.argtypes = [C.c_void_p]
         L.pml_timer_stop.argtypes = [C.c_void_p, c_f64p]
@@ -185,10 +192,15 @@ class Alignment:
 
 
 class Tree:
-    def __init__(self, aln, newick):
+    def __init__(self, aln, newick=None, parsimony_seed=None):
+        """newick: a given topology; parsimony_seed: randomised stepwise-addition parsimony start tree"""
         self.aln, self.ctx = aln, aln.ctx
         h = C.c_void_p()
-        self.ctx.check(lib().pml_tree_load(aln.h, newick.encode(), C.byref(h)), "pml_tree_load")
+        if newick is not None:
+            self.ctx.check(lib().pml_tree_load(aln.h, newick.encode(), C.byref(h)), "pml_tree_load")
+        else:
+            self.ctx.check(lib().pml_tree_start_parsimony(aln.h, C.c_int64(12345 if parsimony_seed is None else parsimony_seed),
+                                                           C.byref(h)), "pml_tree_start_parsimony")
         self.h = h
 
     @property
@@ -237,6 +249,30 @@ class Tree:
         lnl, alpha = C.c_double(), C.c_double()
         self.ctx.check(lib().pml_optimize(self.h, int(opt_alpha), eps, _ptr(w), C.byref(lnl), C.byref(alpha)), "pml_optimize")
         return lnl.value, alpha.value
+
+    def search(self, radius=5, max_rounds=10, eps=0.1, weights=None):
+        """lazy-SPR hill climbing on this tree (topology changes in place); returns (lnL, accepted moves)"""
+        w = _weights(weights)
+        lnl, moves = C.c_double(), C.c_int()
+        self.ctx.check(lib().pml_search(self.h, radius, max_rounds, eps, _ptr(w), C.byref(lnl), C.byref(moves)), "pml_search")
+        return lnl.value, moves.value
+
+    def score_spr_candidates(self, node, keep, radius=3, weights=None, cap=4096):
+        w = _weights(weights)
+        targets = np.zeros(cap, np.int32)
+        lnl = np.zeros(cap)
+        n = C.c_int(cap)
+        self.ctx.check(lib().pml_score_spr_candidates(self.h, node, keep, radius, _ptr(w), _ptr(targets), _ptr(lnl), C.byref(n)),
+                       "pml_score_spr_candidates")
+        return targets[: n.value].copy(), lnl[: n.value].copy()
+
+    def spr(self, node, keep, target):
+        self.ctx.check(lib().pml_tree_spr(self.h, node, keep, target), "pml_tree_spr")
+
+    def neighbors(self, node):
+        nb = (C.c_int * 3)()
+        self.ctx.check(lib().pml_tree_neighbors(self.h, node, nb), "pml_tree_neighbors")
+        return list(nb)
 
     def evaluate_replicates(self, W):
         W = np.ascontiguousarray(W, np.int32)
@@ -305,6 +341,20 @@ def crunch_patterns(seqs, site_weights=None):
 def pattern_range(npatterns, rank, nranks):
     """this rank's contiguous block of patterns: [p0, p1) -- the same split pml_aln_load applies"""
     return npatterns * rank // nranks, npatterns * (rank + 1) // nranks
+
+
+def parsimony_tree(names, seqs, seed=12345):
+    """host-only: randomised stepwise-addition parsimony tree (newick) and its score"""
+    chars = seqs if isinstance(seqs, np.ndarray) else np.stack([np.frombuffer(s.encode(), np.uint8) for s in seqs])
+    chars = np.ascontiguousarray(chars, np.uint8)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    score = C.c_int64()
+    n = lib().pml_parsimony_tree(chars.shape[0], C.c_int64(chars.shape[1]), arr, _ptr(chars), C.c_int64(seed), None, 0, C.byref(score))
+    if n < 0:
+        raise EngineError("pml_parsimony_tree: " + lib().pml_last_error(None).decode())
+    buf = C.create_string_buffer(n)
+    lib().pml_parsimony_tree(chars.shape[0], C.c_int64(chars.shape[1]), arr, _ptr(chars), C.c_int64(seed), buf, n, C.byref(score))
+    return buf.value.decode(), score.value
 
 
 def support_tree(main_newick, trees, as_percent=False):

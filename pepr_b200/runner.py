@@ -43,11 +43,11 @@ class SequenceAlignment:
 
 
 class B200MLRunner:
-    """drop-in for RAxMLRunner on the likelihood path: `-f e`, `-f g`, `-f b`, bootstrap weight vectors.
+    """drop-in for RAxMLRunner on the likelihood path: `-f d`, `-f a`, `-f e`, `-f g`, `-f b`, bootstrap weight vectors.
 
-    `threads` (RAxMLRunner's `-T`) selects nothing here: pattern parallelism is the GPU's.  Tree SEARCH (`-f d`, `-f a`;
-    RAxMLRunner.run with the ML algorithm and no start tree) belongs to SURVEY.md section 8(f) "next" and is reported as an
-    error, never approximated."""
+    `threads` (RAxMLRunner's `-T`) selects nothing here: pattern parallelism is the GPU's.  run() without a start tree
+    performs the ML tree search (parsimony start tree + lazy SPR + model optimisation), with bootstrapReps > 0 preceded by
+    that many replicate searches whose splits are drawn on the ML tree as integer percentages."""
 
     def __init__(self, threads=1, gpu=0, ctx=None, strict=False):
         self.threads, self.strict = threads, strict
@@ -125,8 +125,7 @@ class B200MLRunner:
             elif self.start_tree is not None:
                 self._run_branch_lengths()
             else:
-                self._fail("ML tree search (-f d / -f a) is not provided by the B200 engine yet (SURVEY.md 8f row 1); "
-                           "give a start tree (setStartTree) for `-f e`")
+                self._run_search()
         except _e.EngineError as ex:
             self._fail(str(ex))
 
@@ -140,6 +139,40 @@ class B200MLRunner:
             tree.close()
         finally:
             aln.close()
+
+    def _search_one(self, aln, weights, seed, rounds, final):
+        tree = _e.Tree(aln, parsimony_seed=seed)
+        aln.set_model(1.0, self.matrix)
+        tree.optimize(True, 5.0, weights=weights)
+        lnl, _ = tree.search(radius=5, max_rounds=rounds, eps=self.eps, weights=weights)
+        alpha = aln.alpha
+        if final:
+            lnl, alpha = tree.optimize(True, self.eps, weights=weights)
+        return tree, lnl, alpha
+
+    def _run_search(self):
+        """`-f d` (bootstrapReps == 0) or `-f a -x seed -N reps` (RAxMLRunner.java:112-132)"""
+        self.tree_options = "peprml -f %s -m %s" % ("a" if self.bootstrap_reps else "d", self.matrix)
+        aln = self._load()
+        try:
+            boots = []
+            if self.bootstrap_reps:
+                W, _ = aln.bootstrap_weights(self.random_seed, self.bootstrap_reps)
+                for r in range(self.bootstrap_reps):
+                    t, _, _ = self._search_one(aln, W[r], self.random_seed + 1 + r, 1, False)
+                    boots.append(t.newick())
+                    t.close()
+            tree, self._lnl, self._alpha = self._search_one(aln, None, self.random_seed, 10, True)
+            self._best_tree = tree.newick()
+            tree.close()
+            self._best_with_supports = _e.support_tree(self._best_tree, boots, as_percent=True) if boots else ""
+            self.bootstrap_trees = boots
+        finally:
+            aln.close()
+
+    def getBestTreeWithSupports(self):
+        """RAxML_bipartitions.<run> of `-f a` (RAxMLRunner.java:302-318)"""
+        return getattr(self, "_best_with_supports", "")
 
     def _run_per_site_ll(self):
         """`-f g -z trees` (RAxMLRunner.java:162-213): per tree, optimise then print per-site lnL in column order"""

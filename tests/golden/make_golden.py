@@ -41,7 +41,10 @@ def info(cwd, n):
     m = re.search(r"Final GAMMA\s+likelihood: (\S+)", txt)
     if m:
         out["lnl"] = float(m.group(1))
-    m = re.search(r"alpha: (\S+)", txt)
+    m = re.search(r"Final GAMMA-based Score of best tree (\S+)", txt)
+    if m:
+        out["lnl"] = float(m.group(1))
+    m = re.search(r"alpha: (\S+)", txt) or re.search(r"alpha\[0\]: (\S+)", txt)
     if m:
         out["alpha"] = float(m.group(1))
     m = re.search(r"Tree-Length: (\S+)", txt)
@@ -186,6 +189,29 @@ def case_wide(d):
 
 
 CASES = {"small": case_small, "dup": case_dup, "deep": case_deep, "wide": case_wide}
+
+
+
+def case_search(d):
+    """24 taxa x 1200 sites WAG+G4 simulated: raxmlHPC -f d (PEPR's default full-tree call, RAxMLRunner.java:112-132) and
+    -f a -x 12345 -N 10 (rapid bootstrap + ML search, the bootstrapReps > 0 branch)"""
+    names, seqs, nwk = _sim(24, 1200, 11)
+    tmp = tempfile.mkdtemp()
+    synth.write_phylip(os.path.join(tmp, "t.phy"), names, seqs)
+    run([RAX, "-f", "d", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "fd", "-p", "12345"], tmp)
+    g = {"names": names, "true_tree": nwk, "fd": info(tmp, "fd")}
+    g["fd"]["tree"] = open(os.path.join(tmp, "RAxML_result.fd")).read().strip()
+    run([RAX, "-f", "a", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "fa", "-x", "12345", "-N", "10", "-p", "12345"], tmp)
+    g["fa"] = info(tmp, "fa")
+    g["fa"]["bipartitions"] = open(os.path.join(tmp, "RAxML_bipartitions.fa")).read().strip()
+    with open(os.path.join(tmp, "t.phy"), "rb") as f, gzip.GzipFile(os.path.join(d, "search.phy.gz"), "wb", mtime=0) as o:
+        o.write(f.read())
+    json.dump(g, open(os.path.join(d, "search.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+
+
+CASES["search"] = case_search
+
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)

@@ -47,11 +47,12 @@ def test_runner_reports_errors_the_reference_way(gpu_ctx, golden):
     g = golden("small")
     r = R.B200MLRunner(ctx=gpu_ctx)
     r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
-    r.run()                                     # no start tree: tree search is not part of this round
-    assert r.getBestTree() == "" and "tree search" in r.last_error
     r.setStartTree("((TaxA,TaxB),(TaxC,Oops),((TaxE,TaxF),(TaxG,TaxH)));")
     r.run()
     assert r.getBestTree() == "" and "Oops" in r.last_error
+    r.setMatrix("GTRGAMMA")                     # PEPR only ever asks for PROTGAMMAWAG; anything else is an error, not a guess
+    r.run()
+    assert r.getBestTree() == "" and "PROTGAMMAWAG" in r.last_error
     with pytest.raises(pb.EngineError):
         R.B200MLRunner(ctx=gpu_ctx, strict=True).run()
 
@@ -115,9 +116,35 @@ def test_cli_f_g_and_f_j(tmp_path, golden):
         assert w == g.meta["fj"]["replicate_weights"][k]         # bit exact with raxmlHPC -f j
 
 
-def test_cli_rejects_tree_search_loudly(tmp_path, golden):
+def test_cli_rejects_unknown_model_loudly(tmp_path, golden):
     g = golden("small")
     from pepr_b200 import synth
     synth.write_phylip(str(tmp_path / "t.phy"), g.names, g.seqs)
-    r = _run_cli(["-f", "d", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "d1"], tmp_path)
-    assert r.returncode == 2 and "not implemented" in r.stderr
+    (tmp_path / "t.nwk").write_text(g.meta["tree_in"] + "\n")
+    r = _run_cli(["-f", "e", "-m", "GTRGAMMA", "-s", "t.phy", "-n", "m1", "-t", "t.nwk"], tmp_path)
+    assert r.returncode != 0 and "PROTGAMMAWAG" in r.stderr
+
+
+def test_cli_f_d_and_f_a_tree_search(tmp_path, golden):
+    """PEPR's default full-tree call (`-f d`) and the rapid-bootstrap call (`-f a -x seed -N reps`) through the executable"""
+    import gzip
+    from tests.test_gpu_search import _splits, _strip
+    g = golden("search")
+    from pepr_b200 import synth
+    synth.write_phylip(str(tmp_path / "t.phy"), g.names, g.seqs)
+    r = _run_cli(["-f", "d", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "d1", "-T", "4"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    info = (tmp_path / "RAxML_info.d1").read_text()
+    lnl = float(re.search(r"Final GAMMA-based Score of best tree (\S+)", info).group(1))
+    assert lnl >= g.meta["fd"]["lnl"] - 0.5
+    tree = (tmp_path / "RAxML_result.d1").read_text().strip()
+    assert _splits(_strip(tree)) == _splits(g.meta["fd"]["tree"])
+    assert (tmp_path / "RAxML_bestTree.d1").exists()
+    r = _run_cli(["-f", "a", "-x", "12345", "-N", "5", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "a1"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert len((tmp_path / "RAxML_bootstrap.a1").read_text().strip().split("\n")) == 5
+    bip = (tmp_path / "RAxML_bipartitions.a1").read_text().strip()
+    labels = [int(x) for x in re.findall(r"\)(\d+)", bip)]
+    assert len(labels) == len(g.names) - 3 and min(labels) >= 0 and max(labels) <= 100
+    r = _run_cli(["-f", "d", "-y", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "p1"], tmp_path)     # parsimony tree only
+    assert r.returncode == 0 and (tmp_path / "RAxML_parsimonyTree.p1").exists()

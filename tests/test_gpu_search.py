@@ -1,0 +1,105 @@
+"""Tree search on the GPU engine: lazy-SPR candidate scoring against the oracle, and whole searches against what
+raxmlHPC `-f d` / `-f a` found on the same alignment (tests/golden/search.json).  Heuristic searches are compared by the
+likelihood and the splits of the tree they end on, not move by move."""
+import re
+
+import numpy as np
+import pytest
+
+import pepr_b200 as pb
+from oracle import oracle as orc
+from pepr_b200 import runner as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _splits(newick):
+    sets = []
+    taxa = sorted(orc._leafsets(orc._parse_topology(newick), sets))
+    return {orc._canon(x, taxa) for x in sets if 1 < len(x) < len(taxa) - 1}
+
+
+def _strip(nw):
+    return nw.replace("):0.0;", ");")
+
+
+def test_lazy_spr_scores_match_oracle(gpu_ctx, golden):
+    g = golden("small")
+    fe = g.meta["fe"]
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=fe["alpha"])
+    tree = pb.Tree(aln, fe["tree"])
+    base = tree.evaluate()
+    m = orc.Model()
+    checked = 0
+    for node in range(aln.ntax, 2 * aln.ntax - 2):
+        for keep in tree.neighbors(node):
+            targets, lnl = tree.score_spr_candidates(node, keep, radius=3)
+            assert abs(tree.evaluate() - base) <= 1e-9 * abs(base)          # scoring leaves the tree as it was
+            for tgt, l in list(zip(targets, lnl))[:2]:
+                moved = pb.Tree(aln, fe["tree"])                            # same parser -> same node / branch ids
+                moved.spr(node, keep, int(tgt))
+                want = orc.evaluate(m, orc.Tree(_strip(moved.newick()), g.names), g.pat, g.w, fe["alpha"])
+                assert abs(l - want) <= 1e-9 * abs(want)
+                assert abs(moved.evaluate() - want) <= 1e-9 * abs(want)
+                moved.close()
+                checked += 1
+    assert checked >= 20
+    tree.close(); aln.close()
+
+
+def test_search_finds_reference_tree(gpu_ctx, golden):
+    g = golden("search")
+    fd = g.meta["fd"]
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=1.0)
+    tree = pb.Tree(aln, parsimony_seed=12345)
+    tree.optimize(True, 5.0)
+    lnl, moves = tree.search(radius=5, max_rounds=10, eps=0.1)
+    lnl, alpha = tree.optimize(True, 0.1)
+    # raxmlHPC -f d stops at dlnL <= 0.1 too; both searches are hill climbers from (different) parsimony trees
+    assert lnl >= fd["lnl"] - 0.5, (lnl, fd["lnl"], moves)
+    assert _splits(_strip(tree.newick())) == _splits(fd["tree"])
+    # and the engine's lnL for that tree is what the oracle computes for it
+    chk = orc.evaluate(orc.Model(), orc.Tree(_strip(tree.newick()), g.names), g.pat, g.w, alpha)
+    assert abs(chk - lnl) <= 1e-9 * abs(lnl)
+    tree.close(); aln.close()
+
+
+def test_search_repairs_a_damaged_tree(gpu_ctx, golden):
+    """start from the reference tree with a few random SPR moves applied: the search must climb back"""
+    g = golden("search")
+    fd = g.meta["fd"]
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=fd["alpha"])
+    tree = pb.Tree(aln, fd["tree"])
+    good = tree.evaluate()
+    rng = np.random.default_rng(4)
+    done = 0
+    while done < 4:
+        node = int(rng.integers(aln.ntax, 2 * aln.ntax - 2))
+        keep = tree.neighbors(node)[int(rng.integers(0, 3))]
+        targets, _ = tree.score_spr_candidates(node, keep, radius=4)
+        if len(targets):
+            tree.spr(node, keep, int(targets[int(rng.integers(0, len(targets)))]))
+            done += 1
+    bad = tree.evaluate()
+    assert bad < good - 10
+    lnl, moves = tree.search(radius=6, max_rounds=10, eps=0.1)
+    assert moves >= 1 and lnl > good - 1.0
+    assert _splits(_strip(tree.newick())) == _splits(fd["tree"])
+    tree.close(); aln.close()
+
+
+def test_runner_f_d_and_f_a(gpu_ctx, golden):
+    g = golden("search")
+    r = R.B200MLRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r.setBootstrapReps(6)
+    r.run()                                                                  # `-f a -x 12345 -N 6`
+    assert r.last_error is None
+    assert r.getLikelihood() >= g.meta["fd"]["lnl"] - 0.5
+    assert _splits(_strip(r.getBestTree())) == _splits(g.meta["fd"]["tree"])
+    sup = r.getBestTreeWithSupports()
+    labels = [int(x) for x in re.findall(r"\)(\d+)", sup)]
+    assert len(labels) == len(g.names) - 3 and all(0 <= v <= 100 for v in labels)
+    # the data carry strong signal: raxmlHPC's own rapid bootstrap gives (nearly) full support, so must the replicates here
+    ref = [int(x) for x in re.findall(r"\)(\d+)", g.meta["fa"]["bipartitions"])]
+    assert np.mean(labels) >= np.mean(ref) - 15

@@ -115,3 +115,18 @@ def test_support_tie_break_uses_lowest_taxon_index():
     main = "((A:1.0,B:1.0):1.0,C:1.0,D:1.0);"
     sup = ["((C,D),A,B);", "((A,B),C,D);", "((A,C),B,D);"]
     assert pb.support_counts(main, sup).tolist() == [2]
+
+
+def test_parsimony_start_tree_is_a_valid_good_tree(golden):
+    from oracle import oracle as orc
+    g = golden("wide")
+    nw, score = pb.parsimony_tree(g.names, g.seqs, 12345)
+    assert score > 0 and all(n in nw for n in g.names)
+    t = orc.Tree(nw.replace("):0.0;", ");"), g.names)         # parses as a binary tree over exactly the taxa
+    assert t.nedge == 2 * len(g.names) - 3
+    found = orc.support_counts(g.meta["fe"]["tree"], [nw.replace("):0.0;", ");")])
+    assert sum(found.values()) >= 0.9 * len(found)                # stepwise addition recovers most true splits
+    nw2, score2 = pb.parsimony_tree(g.names, g.seqs, 12345)
+    assert nw2 == nw and score2 == score                           # seeded, reproducible
+    nw3, _ = pb.parsimony_tree(g.names, g.seqs, 777)
+    assert nw3 != nw                                               # the addition order comes from the seed
