@@ -125,8 +125,16 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
         next_code[0] = __ldg(args.a.codes + (int64_t)first * kTileRows + g);
         next_code[1] = __ldg(args.a.codes + (int64_t)first * kTileRows + 8 + g);
     }
-    int it = 0;
-    for (int tile = first; tile < ntiles; tile += stride, ++it) {
+    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int rounds = (cta_tiles + kGroups - 1) / kGroups;
+    mma_turn_init(grp);
+    for (int it = 0; it < rounds; ++it) {
+        const int tile = first + it * stride;
+        if (tile >= ntiles) {  // no tile left for this group: keep the MMA token moving
+            mma_turn_begin(grp);
+            mma_turn_end(grp);
+            continue;
+        }
         const int slot = it % kDepth;
         const int64_t row0 = (int64_t)tile * kTileRows;
         int code[2] = {next_code[0], next_code[1]};
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
                     accA[m][nt][0] = accA[m][nt][1] = 0.0;
                 }
             }
+        mma_turn_begin(grp);  // see mma_common.cuh: the groups take turns on the FP64 tensor pipe
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -167,6 +176,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
                     if (!kTipA) dmma(accA[m][nt][0], accA[m][nt][1], fa[m].v[kt], fragA[nt][kt]);
                     dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
                 }
+        mma_turn_end(grp);
         double* red = s_red + (((it & 1) * kGroups + grp) * kCats) * kTileRows * 3;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {

@@ -66,6 +66,20 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// MMA turn-taking between the groups of a CTA.  The FP64 tensor pipe is one unit per SM (4 clk per DMMA.8x8x4) and ONE group
+// -- four warps, one per SM sub-partition, each issuing a DMMA every 16 clk -- already saturates it.  Left to the
+// round-robin warp scheduler, all twelve warps crawl through their MMA bursts together and then do their epilogues
+// together, leaving the pipe idle (measured: 56 % busy).  With the token below the bursts of the three groups follow each
+// other and every group's loads, scaling test and stores run under another group's MMAs (the "ping-pong" schedule of
+// warp-specialised GEMMs).  Barrier kTurnBarrier + g is shared by group g (sync) and group g-1 (arrive).
+constexpr int kTurnBarrier = 4;
+__device__ __forceinline__ void mma_turn_begin(int grp) { named_barrier(kTurnBarrier + grp, 2 * 4 * 32); }
+__device__ __forceinline__ void mma_turn_end(int grp) { named_barrier_arrive(kTurnBarrier + (grp + 1) % kGroups, 2 * 4 * 32); }
+__device__ __forceinline__ void mma_turn_init(int grp) {
+    if (grp == kGroups - 1) named_barrier_arrive(kTurnBarrier, 2 * 4 * 32);  // group 0 may start
+}
 
 // state index that lane t feeds into k-tile kt: pairs of k-tiles share one 128-bit shared-memory load
 __device__ __forceinline__ int kmap(int kt, int t) { return kt < 4 ? (kt >> 1) * 8 + 2 * t + (kt & 1) : 16 + t; }

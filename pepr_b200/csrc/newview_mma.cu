@@ -114,8 +114,18 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
             if (!kTipR) next_sc[2 + m] = __ldg(op.right.scale + (int64_t)first * kTileRows + m * 8 + g);
         }
     }
-    int it = 0;
-    for (int tile = first; tile < ntiles; tile += stride, ++it) {
+    // every group runs the same number of rounds so that the MMA token keeps circulating; a group without a tile in the
+    // last round just passes it on
+    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int rounds = (cta_tiles + kGroups - 1) / kGroups;
+    mma_turn_init(grp);
+    for (int it = 0; it < rounds; ++it) {
+        const int tile = first + it * stride;
+        if (tile >= ntiles) {
+            mma_turn_begin(grp);
+            mma_turn_end(grp);
+            continue;
+        }
         const int slot = it % kDepth;
         const int64_t row0 = (int64_t)tile * kTileRows;
         // small global reads first so that their latency hides behind the wait for the stage
@@ -154,7 +164,8 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                 if (!kTipL) accL[m][nt][0] = accL[m][nt][1] = 0.0;
                 if (!kTipR) accR[m][nt][0] = accR[m][nt][1] = 0.0;
             }
-        // up to 12 independent accumulator chains are interleaved between two dependent MMAs
+        // this group's turn on the FP64 tensor pipe; up to 12 independent accumulator chains lie between two dependent MMAs
+        mma_turn_begin(grp);
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -164,6 +175,7 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                     if (!kTipL) dmma(accL[m][nt][0], accL[m][nt][1], aL[m].v[kt], fragL[nt][kt]);
                     if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
                 }
+        mma_turn_end(grp);
         // per-row magnitude over this category's 20 states, then over the four categories through shared memory
         // magnitudes are compared through the high word of |x| on the integer pipe (2^-256 has a zero low word, so
         // "|x| < 2^-256" is exactly "hi(|x|) < hi(2^-256)"): the FP64 pipe is left to the MMAs
