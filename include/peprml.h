@@ -110,6 +110,11 @@ int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_la
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 
+/* profiling aid: while enabled, the CLV kernel accumulates per warp of its first CTA the clock cycles spent in each
+ * pipeline phase (12 warps x 8 counters: wait data, fragments + wait turn, MMAs, products, wait slot, store, tiles, -) */
+int pml_trace_enable(pml_ctx *, int on);
+int pml_trace_read(pml_ctx *, int64_t out[96]);
+
 /* stopwatch on the context's stream: start records an event, stop records another, synchronises and returns the
  * device milliseconds in between (host control flow between the two is included, as it should be for a step time) */
 int pml_timer_start(pml_ctx *);

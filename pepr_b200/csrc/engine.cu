@@ -75,6 +75,7 @@ struct pml_ctx {
     // optional per-launch device timing (pml_profile_begin/end)
     struct Timed { int kind; int64_t rows; cudaEvent_t t0, t1; };
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    long long* d_trace = nullptr;  // pml_trace_enable
     bool profiling = false;
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> spare_events;
@@ -265,6 +266,7 @@ void launch_entries(pml_tree* t, const std::vector<ViewOp>& ops, size_t base, in
         nv.pright = t->d_pblocks + 2 * i + 1;
         nv.out = t->clv(op.node);
         nv.out_scale = t->scale(op.node);
+        nv.trace = c->d_trace;
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
         const int tk = c->tick(2 - ntip, a->nloc);
         launch_newview_mma(nv, a->npad, c->sms, c->stream);
@@ -733,6 +735,24 @@ const char* pml_last_error(const pml_ctx* c) { return c ? c->err.c_str() : g_cre
 int pml_ctx_sync(pml_ctx* c) {
     if (!c) return PML_EINVAL;
     return c->bind() && c->sync() ? PML_OK : PML_ENODEVICE;
+}
+
+int pml_trace_enable(pml_ctx* c, int on) {
+    if (!c || !c->bind() || !c->sync()) return PML_EINVAL;
+    if (on && !c->d_trace) {
+        if (!c->cuda(cudaMalloc(&c->d_trace, 96 * sizeof(long long)), "trace alloc")) return PML_ENOMEM;
+    }
+    if (c->d_trace) cudaMemset(c->d_trace, 0, 96 * sizeof(long long));
+    if (!on && c->d_trace) {
+        cudaFree(c->d_trace);
+        c->d_trace = nullptr;
+    }
+    return PML_OK;
+}
+
+int pml_trace_read(pml_ctx* c, int64_t out[96]) {
+    if (!c || !out || !c->d_trace || !c->bind() || !c->sync()) return PML_EINVAL;
+    return c->cuda(cudaMemcpy(out, c->d_trace, 96 * sizeof(long long), cudaMemcpyDeviceToHost), "trace read") ? PML_OK : PML_ENODEVICE;
 }
 
 int pml_timer_start(pml_ctx* c) {

@@ -38,6 +38,7 @@ struct NewviewOp {
     const PBlock* pright;
     double* out;
     int32_t* out_scale;
+    long long* trace;  // optional (profiling aid): per warp of CTA 0, cycles spent in each phase of the pipeline
 };
 
 // P(t) for `nblocks` branches: lengths[b] in expected substitutions per site; tips[b] != 0 also fills PBlock::tip

@@ -6,10 +6,7 @@
 // share one pipe (profiles/r01_fp64_pipe_peaks.log).  An inner-inner site-update needs 6,480 flop per 1,920 B, i.e.
 // 22 TFLOP/s at the measured 6.5 TB/s -- only the tensor path leaves issue slots and register bandwidth for the rest.
 //
-// Work split inside a persistent CTA (384 threads = 3 groups x 4 warps):
-//   warp w: rate category c = w & 3, group w >> 2; group k takes every third 16-pattern tile of the CTA and owns a private
-//   ring of kDepth stages which its category-0 warp refills (one bulk row copy per lane) right after the group barrier,
-//   so the three groups drift out of phase and one group's epilogue (scaling test, stores) overlaps the others' MMAs
+// Persistent CTAs of 12 warps, warp-specialised (MMA / epilogue / producer, see below);
 //   per 8 rows and child: D[8 x 24] = X[8 x 20] * P_c^T[20 x 24(20 used)] as 3 n-tiles x 5 k-tiles of m8n8k4
 // CLVs live in HBM in the blocked layout described in mma_common.cuh, so a stage is filled by one bulk copy per child.
 #include <cuda_runtime.h>
@@ -41,113 +38,209 @@ __device__ __forceinline__ void lookup_rows(const double* table, int code, int c
     }
 }
 
+// ---- warp-specialised pipeline ---------------------------------------------------------------------------------
+//   warps 0-7   MMA warps: two groups of four (one warp per rate category).  A group takes every second 16-pattern tile
+//               of the CTA: wait for its stage, pull the A fragments, take the MMA turn (the two groups alternate on the
+//               FP64 tensor pipe, see mma_common.cuh), multiply the two children, leave the products (blocked layout)
+//               and the per-category row magnitudes in a shared-memory slot.  They never touch global memory.
+//   warps 8-9   epilogue warps (alternate tiles): combine the four category magnitudes of every row, apply the rare
+//               x2^256 rescale in place, hand the 10 KB tile to the TMA engine (cp.async.bulk shared -> global) and
+//               write the scaling counts.
+//   warp 10     producer: refills the stages with one bulk copy per inner child as soon as a stage has been consumed.
+// Everything an MMA warp does besides its 60 DMMAs is ~70 instructions, so the pipe stays busy; stores cost no LSU work.
+constexpr int kMmaGroups = 2;
+constexpr int kMmaWarps = 4 * kMmaGroups;
+constexpr int kEpiWarps = 2;
+constexpr int kProducerWarp = kMmaWarps + kEpiWarps;
+constexpr int kThreadsNewview = 384;   // warp 11 idles: 12 warps keep the register budget at 168
+constexpr int kProdSlots = 4;
+
 template <bool kTipL, bool kTipR>
 struct SmemPlan {
     static constexpr int kInner = (kTipL ? 0 : 1) + (kTipR ? 0 : 1);
-    static constexpr int kStages = kGroups * kDepth;
-    static constexpr int kStageDoubles = kInner * kTileDoubles;
-    static constexpr int kTipDoubles = ((kTipL ? 1 : 0) + (kTipR ? 1 : 0)) * kCodes * kTipPad;
-    static constexpr int kMaxDoubles = 2 * kGroups * kCats * kTileRows;  // [parity][group][cat][16 rows]
-    static constexpr size_t kBytes = 128 /* barriers */ + sizeof(double) * (size_t)(kTipDoubles + kMaxDoubles + kStages * kStageDoubles);
+    // a stage = the CLV tiles of the inner children + 192 B of per-row side data that travels with them:
+    // [0,64) / [64,128) scaling counts of the inner children, [128,144) residue codes of the tip child
+    static constexpr int kAuxDoubles = 24;
+    static constexpr int kStageDoubles = kInner * kTileDoubles + kAuxDoubles;
+    static constexpr int kTipDoubles = kCodes * kTipPad;             // exactly one child is a tip in the mixed case
+    static constexpr int kMaxInts = kProdSlots * kCats * kTileRows;  // [slot][cat][row]
+    static constexpr size_t kBarBytes = 256;
+    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(kInner == 2 ? 0 : kTipDoubles) + sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
+                                     sizeof(double) * (size_t)(kProdSlots * kTileDoubles + kMmaGroups * kDepth * kStageDoubles);
 };
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // at least one child is an inner node (the tip-tip case has its own kernel below)
 template <bool kTipL, bool kTipR>
-__global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, int ntiles) {
+__global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op, int ntiles) {
     using Plan = SmemPlan<kTipL, kTipR>;
-    constexpr int ST = Plan::kStages;
+    constexpr bool kMixed = kTipL || kTipR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    double* s_tip = reinterpret_cast<double*>(smem_raw + 128);
-    int* s_max = reinterpret_cast<int*>(s_tip + Plan::kTipDoubles);
-    double* s_stage = s_tip + Plan::kTipDoubles + Plan::kMaxDoubles;
+    uint64_t* in_full = reinterpret_cast<uint64_t*>(smem_raw);    // [group][kDepth]
+    uint64_t* in_empty = in_full + kMmaGroups * kDepth;            // [group][kDepth]
+    uint64_t* prod_full = in_empty + kMmaGroups * kDepth;          // [kProdSlots]
+    uint64_t* prod_empty = prod_full + kProdSlots;                 // [kProdSlots]
+    double* s_tip = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);
+    int* s_max = reinterpret_cast<int*>(s_tip + (kMixed ? Plan::kTipDoubles : 0));
+    int* s_sc = s_max + Plan::kMaxInts;                            // [kProdSlots][16] summed scaling counts of the children
+    double* s_prod = reinterpret_cast<double*>(s_sc + kProdSlots * kTileRows);
+    double* s_stage = s_prod + kProdSlots * kTileDoubles;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_entry = op.trace ? clock64() : 0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) mbar_init(full + s, 1);
+        for (int i = 0; i < kMmaGroups * kDepth; ++i) {
+            mbar_init(in_full + i, 1);
+            mbar_init(in_empty + i, 4);
+        }
+        for (int i = 0; i < kProdSlots; ++i) {
+            mbar_init(prod_full + i, 4);
+            mbar_init(prod_empty + i, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (kTipL || kTipR) {
+    if (kMixed) {
         const double* src = kTipL ? &op.pleft->tip[0][0] : &op.pright->tip[0][0];
-        for (int i = threadIdx.x; i < kCodes * kRow; i += kThreadsMma) s_tip[(i / kRow) * kTipPad + i % kRow] = src[i];
+        for (int i = threadIdx.x; i < kCodes * kRow; i += kThreadsNewview) s_tip[(i / kRow) * kTipPad + i % kRow] = src[i];
     }
     __syncthreads();
 
-    const int c = warp & 3, grp = warp >> 2, g = lane >> 2, t = lane & 3;
-    uint64_t* gfull = full + grp * kDepth;
-    double* gstage = s_stage + (size_t)grp * kDepth * Plan::kStageDoubles;
-    const int stride = kGroups * gridDim.x;  // tile distance between two iterations of this group
-    // refill of one ring slot: a 16-row tile is contiguous in the blocked layout -> one bulk copy per inner child
-    auto refill = [&](int tile, int slot) {
+    // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
+    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == kProducerWarp) {
+        // ---------------------------------------------------------------------------------------------- producer
         if (lane == 0) {
             constexpr uint32_t bytes = kTileDoubles * sizeof(double);
-            mbar_expect_tx(gfull + slot, Plan::kInner * bytes);
-            const size_t goff = (size_t)tile * kTileDoubles;
-            double* dst = gstage + (size_t)slot * Plan::kStageDoubles;
-            if (!kTipL) {
-                bulk_g2s(dst, op.left.clv + goff, bytes, gfull + slot);
-                dst += kTileDoubles;
+            for (int n = 0; n < cta_tiles; ++n) {
+                const int grp = n % kMmaGroups, j = n / kMmaGroups, slot = j % kDepth;
+                uint64_t* full = in_full + grp * kDepth + slot;
+                mbar_wait(in_empty + grp * kDepth + slot, ((j / kDepth) & 1) ^ 1);
+                constexpr uint32_t sc_bytes = kTileRows * sizeof(int32_t);
+                mbar_expect_tx(full, Plan::kInner * (bytes + sc_bytes) + (kMixed ? kTileRows : 0));
+                const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
+                const size_t goff = tile * kTileDoubles;
+                double* dst = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
+                unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
+                if (!kTipL) {
+                    bulk_g2s(dst, op.left.clv + goff, bytes, full);
+                    bulk_g2s(aux, op.left.scale + tile * kTileRows, sc_bytes, full);
+                    dst += kTileDoubles;
+                }
+                if (!kTipR) {
+                    bulk_g2s(dst, op.right.clv + goff, bytes, full);
+                    bulk_g2s(aux + (kTipL ? 0 : sc_bytes), op.right.scale + tile * kTileRows, sc_bytes, full);
+                }
+                if (kMixed) bulk_g2s(aux + 128, (kTipL ? op.left.codes : op.right.codes) + tile * kTileRows, kTileRows, full);
             }
-            if (!kTipR) bulk_g2s(dst, op.right.clv + goff, bytes, gfull + slot);
         }
-    };
-    const int first = blockIdx.x + grp * gridDim.x;
-    if (c == 0)
-        for (int d = 0; d < kDepth; ++d)
-            if (first + d * stride < ntiles) refill(first + d * stride, d);
+        return;
+    }
+    if (warp > kProducerWarp) return;
 
+    if (warp >= kMmaWarps) {
+        // ---------------------------------------------------------------------------------------------- epilogue
+        const int e = warp - kMmaWarps;
+        const int r = lane & 15;   // lanes 0-15 own one row each
+        int prev_slot = -1;
+        if (op.trace && blockIdx.x == 0 && lane == 0) op.trace[warp * 8 + 7] += clock64() - t_entry;  // entry -> loop
+        for (int n = e; n < cta_tiles; n += kEpiWarps) {
+            const int slot = n % kProdSlots;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
+            const bool tr = op.trace != nullptr && blockIdx.x == 0 && lane == 0;
+            const long long e0 = tr ? clock64() : 0;
+            mbar_wait(prod_full + slot, (n / kProdSlots) & 1);
+            const long long e1 = tr ? clock64() : 0;
+            const int* mx = s_max + slot * kCats * kTileRows;
+            const int big = max(max(mx[r], mx[kTileRows + r]), max(mx[2 * kTileRows + r], mx[3 * kTileRows + r]));
+            const bool rescale = big < kMinLikHi;
+            const unsigned flagged = __ballot_sync(0xffffffffu, rescale && lane < kTileRows);
+            double* prod = s_prod + (size_t)slot * kTileDoubles;
+            if (flagged) {  // rare: multiply the flagged rows in place before the tile leaves
+                for (unsigned rest = flagged; rest; rest &= rest - 1) {
+                    const int row = __ffs(rest) - 1;
+                    double* blk = prod + (row >> 3) * kBlockDoubles;
+                    const int gr = row & 7;
+                    for (int k = lane; k < kRow; k += 32) {
+                        const int cat = k / kStates, st = k % kStates;
+                        const int off = cat * kCatDoubles + (st < 8 ? gr * 8 + st : (st < 16 ? 64 + gr * 8 + (st - 8) : 128 + gr * 4 + (st - 16)));
+                        blk[off] *= kTwo256;
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+            }
+            if (lane == 0) {
+                bulk_s2g(op.out + (size_t)tile * kTileDoubles, prod, kTileDoubles * sizeof(double));
+                bulk_commit();
+            }
+            if (lane < kTileRows) op.out_scale[tile * kTileRows + r] = s_sc[slot * kTileRows + r] + (rescale ? 1 : 0);
+            // the previous tile of this warp has certainly been read out of shared memory once at most one store is pending
+            const long long e2 = tr ? clock64() : 0;
+            if (lane == 0) {
+                if (prev_slot >= 0) {
+                    bulk_wait_read<1>();
+                    mbar_arrive(prod_empty + prev_slot);
+                }
+            }
+            if (tr) {
+                const long long e3 = clock64();
+                op.trace[warp * 8 + 1] += e1 - e0;   // wait for products
+                op.trace[warp * 8 + 2] += e2 - e1;   // magnitude test, store issue, scaling counts
+                op.trace[warp * 8 + 3] += e3 - e2;   // wait until the previous store has left shared memory
+                op.trace[warp * 8 + 4] += 1;
+            }
+            prev_slot = slot;
+        }
+        const long long e4 = op.trace ? clock64() : 0;
+        if (lane == 0) bulk_wait_read<0>();
+        if (op.trace && blockIdx.x == 0 && lane == 0) {
+            op.trace[warp * 8 + 5] += clock64() - e4;  // final drain
+            op.trace[warp * 8 + 0] += clock64() - t_entry;  // whole kernel as seen by this epilogue warp
+            op.trace[warp * 8 + 6] += 1;
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------------------------------------- MMA warps
+    const int c = warp & 3, grp = warp >> 2, g = lane >> 2, t = lane & 3;
     double fragL[3][5], fragR[3][5];
     if (!kTipL) load_p_fragments(op.pleft, c, g, t, fragL);
     if (!kTipR) load_p_fragments(op.pright, c, g, t, fragR);
-
-    int next_code[2] = {0, 0};
-    if ((kTipL || kTipR) && first < ntiles) {
-        const uint8_t* codes = kTipL ? op.left.codes : op.right.codes;
-        next_code[0] = __ldg(codes + (int64_t)first * kTileRows + g);
-        next_code[1] = __ldg(codes + (int64_t)first * kTileRows + 8 + g);
-    }
-    int32_t next_sc[4] = {0, 0, 0, 0};
-    if (c == 0 && t == 0 && first < ntiles) {
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            if (!kTipL) next_sc[m] = __ldg(op.left.scale + (int64_t)first * kTileRows + m * 8 + g);
-            if (!kTipR) next_sc[2 + m] = __ldg(op.right.scale + (int64_t)first * kTileRows + m * 8 + g);
-        }
-    }
-    // every group runs the same number of rounds so that the MMA token keeps circulating; a group without a tile in the
-    // last round just passes it on
-    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int rounds = (cta_tiles + kGroups - 1) / kGroups;
-    mma_turn_init(grp);
-    for (int it = 0; it < rounds; ++it) {
-        const int tile = first + it * stride;
-        if (tile >= ntiles) {
-            mma_turn_begin(grp);
-            mma_turn_end(grp);
+    const int rounds = (cta_tiles + kMmaGroups - 1) / kMmaGroups;
+    if (op.trace && blockIdx.x == 0 && lane == 0) op.trace[warp * 8 + 7] += clock64() - t_entry;  // prologue
+    if (grp == kMmaGroups - 1) named_barrier_arrive(kTurnBarrier, 2 * 4 * 32);  // group 0 may start
+    for (int j = 0; j < rounds; ++j) {
+        const int n = j * kMmaGroups + grp;
+        if (n >= cta_tiles) {  // no tile left for this group: keep the MMA token moving
+            named_barrier(kTurnBarrier + grp, 2 * 4 * 32);
+            named_barrier_arrive(kTurnBarrier + (grp + 1) % kMmaGroups, 2 * 4 * 32);
             continue;
         }
-        const int slot = it % kDepth;
-        const int64_t row0 = (int64_t)tile * kTileRows;
-        // small global reads first so that their latency hides behind the wait for the stage
-        int code[2] = {next_code[0], next_code[1]};
-        if ((kTipL || kTipR) && tile + stride < ntiles) {  // the codes of the following tile travel while this one is computed
-            const uint8_t* codes = kTipL ? op.left.codes : op.right.codes;
-            next_code[0] = __ldg(codes + row0 + (int64_t)stride * kTileRows + g);
-            next_code[1] = __ldg(codes + row0 + (int64_t)stride * kTileRows + 8 + g);
+        const int slot = j % kDepth;
+        const bool tr = op.trace != nullptr && blockIdx.x == 0 && lane == 0;
+        long long tk0 = tr ? clock64() : 0;
+        mbar_wait(in_full + grp * kDepth + slot, (j / kDepth) & 1);
+        long long tk1 = tr ? clock64() : 0;
+        const double* stage = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
+        const unsigned char* aux = reinterpret_cast<const unsigned char*>(stage + Plan::kInner * kTileDoubles);
+        int code[2] = {0, 0};
+        if (kMixed) {
+            code[0] = aux[128 + g];
+            code[1] = aux[128 + 8 + g];
         }
-        // the children's scaling counts travel one iteration ahead (like the tip codes): their DRAM latency never stalls
-        // the category-0 warp, which would otherwise hold up the other three at the group barrier
-        const int32_t scl[2] = {next_sc[0], next_sc[1]}, scr[2] = {next_sc[2], next_sc[3]};
-        if (c == 0 && t == 0 && tile + stride < ntiles) {
-            const int64_t nrow = row0 + (int64_t)stride * kTileRows;
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                if (!kTipL) next_sc[m] = __ldg(op.left.scale + nrow + m * 8 + g);
-                if (!kTipR) next_sc[2 + m] = __ldg(op.right.scale + nrow + m * 8 + g);
-            }
+        int32_t sc_sum = 0;  // category-0 warp, lanes 0-15: scaling counts of the children of row `lane`
+        if (c == 0 && lane < kTileRows) {
+            const int32_t* sci = reinterpret_cast<const int32_t*>(aux);
+            sc_sum = sci[lane] + (Plan::kInner == 2 ? sci[kTileRows + lane] : 0);
         }
-        mbar_wait(gfull + slot, (it / kDepth) & 1);
-        const double* stage = gstage + (size_t)slot * Plan::kStageDoubles;
         double accL[2][3][2], accR[2][3][2];
         AFrag aL[2], aR[2];
 #pragma unroll
@@ -164,8 +257,9 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                 if (!kTipL) accL[m][nt][0] = accL[m][nt][1] = 0.0;
                 if (!kTipR) accR[m][nt][0] = accR[m][nt][1] = 0.0;
             }
-        // this group's turn on the FP64 tensor pipe; up to 12 independent accumulator chains lie between two dependent MMAs
-        mma_turn_begin(grp);
+        // this group's turn on the FP64 tensor pipe; 12 (6) independent accumulator chains lie between two dependent MMAs
+        named_barrier(kTurnBarrier + grp, 2 * 4 * 32);
+        long long tk2 = tr ? clock64() : 0;
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -175,41 +269,49 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_newview_mma(NewviewOp op, in
                     if (!kTipL) dmma(accL[m][nt][0], accL[m][nt][1], aL[m].v[kt], fragL[nt][kt]);
                     if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
                 }
-        mma_turn_end(grp);
-        // per-row magnitude over this category's 20 states, then over the four categories through shared memory
-        // magnitudes are compared through the high word of |x| on the integer pipe (2^-256 has a zero low word, so
-        // "|x| < 2^-256" is exactly "hi(|x|) < hi(2^-256)"): the FP64 pipe is left to the MMAs
-        int* mx = s_max + (((it & 1) * kGroups + grp) * kCats) * kTileRows;
+        long long tk3 = tr ? clock64() : 0;
+        named_barrier_arrive(kTurnBarrier + (grp + 1) % kMmaGroups, 2 * 4 * 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty + grp * kDepth + slot);  // the stage may be refilled
+        // products and, through the high word of |x| on the integer pipe, this category's magnitude of every row
+        // (2^-256 has a zero low word, so "|x| < 2^-256" is exactly "hi(|x|) < hi(2^-256)")
+        const int pslot = n % kProdSlots;
+        int big[2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            int big = 0;
+            big[m] = 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
                 accL[m][nt][0] *= accR[m][nt][0];
                 accL[m][nt][1] *= accR[m][nt][1];
-                if (nt < 2 || t < 2) big = max(big, max(__double2hiint(accL[m][nt][0]) & 0x7fffffff, __double2hiint(accL[m][nt][1]) & 0x7fffffff));
+                if (nt < 2 || t < 2) big[m] = max(big[m], max(__double2hiint(accL[m][nt][0]) & 0x7fffffff, __double2hiint(accL[m][nt][1]) & 0x7fffffff));
             }
-            big = max(big, __shfl_xor_sync(0xffffffffu, big, 1));
-            big = max(big, __shfl_xor_sync(0xffffffffu, big, 2));
-            if (t == 0) mx[c * kTileRows + m * 8 + g] = big;
+            big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 1));
+            big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 2));
         }
-        named_barrier(1 + grp, 4 * 32);
-        // every warp of the group has its fragments in registers: the slot can take the tile kDepth iterations ahead
-        if (c == 0 && tile + kDepth * stride < ntiles) refill(tile + kDepth * stride, slot);
+        long long tk4 = tr ? clock64() : 0;
+        mbar_wait(prod_empty + pslot, ((n / kProdSlots) & 1) ^ 1);
+        long long tk5 = tr ? clock64() : 0;
+        double* prod = s_prod + (size_t)pslot * kTileDoubles;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            const int r = m * 8 + g;
-            const int big = max(max(mx[r], mx[kTileRows + r]), max(mx[2 * kTileRows + r], mx[3 * kTileRows + r]));
-            const bool rescale = big < kMinLikHi;
-            if (rescale) {
-#pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    accL[m][nt][0] *= kTwo256;
-                    accL[m][nt][1] *= kTwo256;
-                }
-            }
-            store_d(op.out + (size_t)tile * kTileDoubles + m * kBlockDoubles, c, lane, accL[m]);
-            if (c == 0 && t == 0) op.out_scale[row0 + r] = scl[m] + scr[m] + (rescale ? 1 : 0);
+            store_d(prod + m * kBlockDoubles, c, lane, accL[m]);
+            if (t == 0) s_max[(pslot * kCats + c) * kTileRows + m * 8 + g] = big[m];
+        }
+        if (c == 0 && lane < kTileRows) s_sc[pslot * kTileRows + lane] = sc_sum;
+        fence_async_smem();  // the tile leaves through the async proxy (bulk store)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(prod_full + pslot);
+        if (tr) {  // phases: wait data | fragments + wait turn | MMAs | products + magnitudes | wait slot | store + fence | tiles
+            long long* row = op.trace + warp * 8;
+            const long long tk6 = clock64();
+            row[0] += tk1 - tk0;
+            row[1] += tk2 - tk1;
+            row[2] += tk3 - tk2;
+            row[3] += tk4 - tk3;
+            row[4] += tk5 - tk4;
+            row[5] += tk6 - tk5;
+            row[6] += 1;
         }
     }
 }
@@ -321,7 +423,7 @@ void launch_one(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
     using Plan = SmemPlan<kTipL, kTipR>;
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    k_newview_mma<kTipL, kTipR><<<grid, kThreadsMma, Plan::kBytes, stream>>>(op, ntiles);
+    k_newview_mma<kTipL, kTipR><<<grid, kThreadsNewview, Plan::kBytes, stream>>>(op, ntiles);
 }
 
 }  // namespace
