@@ -110,8 +110,9 @@ int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_la
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 
-/* profiling aid: while enabled, the CLV kernel accumulates per warp of its first CTA the clock cycles spent in each
- * pipeline phase (12 warps x 8 counters: wait data, fragments + wait turn, MMAs, products, wait slot, store, tiles, -) */
+/* profiling aid: while enabled (on = 1: CLV kernel, 2 / 3: branch kernel with two inner ends / a tip end, 0: off), the kernel accumulates per warp of its
+ * first CTA the clock cycles spent in each pipeline phase (12 warps x 8 counters: wait data, fragments + wait turn, MMAs,
+ * products, wait slot, store, tiles, prologue) */
 int pml_trace_enable(pml_ctx *, int on);
 int pml_trace_read(pml_ctx *, int64_t out[96]);
 

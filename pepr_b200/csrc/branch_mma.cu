@@ -5,13 +5,16 @@
 // (evaluateGTRGAMMAPROT) including per-pattern lnL.  The product table is only written out when the caller wants to
 // iterate Newton-Raphson on it (kStore).
 //
-// The streaming loop only leaves three sums (f, f', f'') per pattern; after its last tile every CTA turns the sums of its
-// own tiles into per-pattern lnL and weighted totals with all 384 threads (logs, divisions and integer weights stay out of
-// the loop whose FP64 pipe the MMAs need), and the CTA that draws the last ticket adds the CTA partials in a fixed order:
-// one launch replaces sumtable + core + reduce of the first engine generation and its result is bit-reproducible.
-//
-// Same pipeline as newview_mma.cu: three groups of four warps (one per rate category), each with a private ring of
-// shared-memory stages filled by TMA bulk copies, DMMA m8n8k4 with the fixed 20x20 matrices as B fragments in registers.
+// Persistent CTAs of 11 warps, warp-specialised like newview_mma.cu:
+//   warps 0-7   MMA warps, two groups of four (one warp per rate category) alternating on the FP64 tensor pipe; a group
+//               takes every second 16-pattern tile, contracts its products with the exponentials and leaves f, f', f''
+//               per row and category in a shared-memory slot.  They never touch global memory (except kStore).
+//   warps 8-9   finishing warps: 32 rows (the tiles of both groups) at a time they add the four categories, take the log,
+//               apply scaling counts and integer weights and keep running weighted sums; the logs and divisions stay off
+//               the MMA warps.  Nothing per-pattern goes back to HBM unless per-pattern lnL was asked for.
+//   warp 10     producer: TMA bulk copies of the CLV tiles and of the per-row side data (scaling counts, weights, codes).
+// The CTA that draws the last ticket adds the CTA partials in a fixed order (bit-reproducible) and, when asked to, does
+// the guarded Newton-Raphson step of raxmlHPC's topLevelMakenewz on the device: the branch length never visits the host.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -27,71 +30,252 @@ using namespace mma;
 
 constexpr double kLogMinLik = -177.445678223345993274;  // ln 2^-256
 constexpr int kTipVecPad = 22;                          // doubles per row of the 23 x 20 tip table
+constexpr int kThreadsBranch = (kProducerWarp + 1) * 32;  // 352: eleven warps leave 184 registers per thread
+constexpr int kBranchDepth = 4;                         // input stages per MMA group
+constexpr int kRedSlots = 4;                            // row-sum slots between MMA and finishing warps (tile n -> n % 4)
+constexpr int kFinishBarrier = 3;                       // named barrier of the two finishing warps
+constexpr int kStageBarrier = 2;                        // named barrier of all warps but the producer (prologue)
 
 template <bool kTipA>
 struct BranchPlan {
     static constexpr int kInner = kTipA ? 1 : 2;
-    static constexpr int kStages = kGroups * kDepth;
-    static constexpr int kStageDoubles = kInner * kTileDoubles;
+    // a stage = the CLV tiles of the inner ends + 256 B of per-row side data that travels with them:
+    // [0,64) scaling counts of b, [64,128) scaling counts of a, [128,192) pattern weights, [192,208) residue codes of a
+    static constexpr int kAuxDoubles = 32;
+    static constexpr int kStageDoubles = kInner * kTileDoubles + kAuxDoubles;
     static constexpr int kTipDoubles = kTipA ? kCodes * kTipVecPad : 0;
-    static constexpr int kRedDoubles = 2 * kGroups * kCats * kTileRows * 3;  // [parity][group][cat][row][f,f1,f2]
-    static constexpr int kFinalDoubles = 0;
-    static constexpr size_t kBytes = 128 + sizeof(double) * (size_t)(kTipDoubles + kRedDoubles + kFinalDoubles + kStages * kStageDoubles);
+    static constexpr int kRedDoubles = kRedSlots * kCats * kTileRows * 3;  // [slot][cat][row][f, f', f'']
+    static constexpr int kSideInts = kRedSlots * kTileRows * 2;            // [slot][row][scaling count, weight]
+    static constexpr int kExpDoubles = 3 * kCats * 24;                     // exp(lambda r t) * {1, lambda r, (lambda r)^2}, padded to 24 states
+    static constexpr int kMatDoubles = 2 * kStates * kStates;              // Vinv and pi V staged once per CTA
+    static constexpr size_t kBarBytes = 256;
+    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(kTipDoubles + kRedDoubles + 8 + kExpDoubles + kMatDoubles) +
+                                     sizeof(int) * kSideInts + sizeof(double) * (size_t)(kMmaGroups * kBranchDepth * kStageDoubles);
 };
 
 template <bool kTipA, bool kStore>
-__global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, int ntiles) {
+__global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs args, int ntiles) {
     using Plan = BranchPlan<kTipA>;
-    constexpr int ST = Plan::kStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    double* s_tip = reinterpret_cast<double*>(smem_raw + 128);
+    uint64_t* in_full = reinterpret_cast<uint64_t*>(smem_raw);     // [group][kBranchDepth]
+    uint64_t* in_empty = in_full + kMmaGroups * kBranchDepth;       // [group][kBranchDepth]
+    uint64_t* red_full = in_empty + kMmaGroups * kBranchDepth;      // [kRedSlots]
+    uint64_t* red_empty = red_full + kRedSlots;                     // [kRedSlots]
+    double* s_tip = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);
     double* s_red = s_tip + Plan::kTipDoubles;
-    double* s_final = s_red + Plan::kRedDoubles;
-    double* s_stage = s_final + Plan::kFinalDoubles;
+    double* s_fin = s_red + Plan::kRedDoubles;                      // [2 finishing warps][3] (+2 spare)
+    double* s_exp = s_fin + 8;                                      // [3][kCats][24]
+    double* s_vinv = s_exp + Plan::kExpDoubles;                     // [k][i]
+    double* s_piv = s_vinv + kStates * kStates;                     // [i][k]
+    int2* s_side = reinterpret_cast<int2*>(s_vinv + Plan::kMatDoubles);
+    double* s_stage = reinterpret_cast<double*>(s_side + kRedSlots * kTileRows);
     const DeviceModel* dm = args.dm;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST; ++s) mbar_init(full + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (kTipA) {
-        // tipvec[code][k] = sum over the residues the code allows of pi_i V[i][k]
-        for (int idx = threadIdx.x; idx < kCodes * kStates; idx += kThreadsMma) {
-            const int code = idx / kStates, k = idx % kStates;
-            double acc = 0.0;
-            if (code < 20) acc = dm->piV[code][k];
-            else if (code == 20) acc = dm->piV[2][k] + dm->piV[3][k];
-            else if (code == 21) acc = dm->piV[5][k] + dm->piV[6][k];
-            else
-                for (int i = 0; i < kStates; ++i) acc += dm->piV[i][k];
-            s_tip[code * kTipVecPad + k] = acc;
+    const bool tr = args.trace != nullptr && blockIdx.x == 0 && lane == 0;
+    const long long t_entry = tr ? clock64() : 0;
+    // The model constants are requested FIRST: once the producer has queued its first 160 KB of tiles every further load
+    // of this SM waits behind them (measured: 10,000 cycles of prologue when the order was the other way round).
+    constexpr int kStagers = kProducerWarp * 32;  // every warp but the producer
+    const int tid = threadIdx.x;
+    double pre_vinv[2] = {0.0, 0.0}, pre_piv[2] = {0.0, 0.0}, pre_lambda = 0.0, pre_rate = 0.0;
+    if (warp != kProducerWarp) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = tid + q * kStagers;
+            if (idx < kStates * kStates) {
+                pre_vinv[q] = (&dm->Vinv[0][0])[idx];
+                pre_piv[q] = (&dm->piV[0][0])[idx];
+            }
         }
+        if (tid < kCats * 24 && tid % 24 < kStates) {
+            pre_lambda = dm->lambda[tid % 24];
+            pre_rate = dm->rates[tid / 24];
+        }
+    }
+    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
+    const double tt = args.t_ptr ? nr_clamp_length(*args.t_ptr) : args.t;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMmaGroups * kBranchDepth; ++i) {
+            mbar_init(in_full + i, 1);
+            mbar_init(in_empty + i, 4);
+        }
+        for (int i = 0; i < kRedSlots; ++i) {
+            mbar_init(red_full + i, 4);
+            mbar_init(red_empty + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int c = warp & 3, grp = warp >> 2, g = lane >> 2, t = lane & 3;
-    uint64_t* gfull = full + grp * kDepth;
-    double* gstage = s_stage + (size_t)grp * kDepth * Plan::kStageDoubles;
-    const int stride = kGroups * gridDim.x;
-    auto refill = [&](int tile, int slot) {
-        if (lane == 0) {
-            constexpr uint32_t bytes = kTileDoubles * sizeof(double);
-            mbar_expect_tx(gfull + slot, Plan::kInner * bytes);
-            const size_t goff = (size_t)tile * kTileDoubles;
-            double* dst = gstage + (size_t)slot * Plan::kStageDoubles;
-            if (!kTipA) {
-                bulk_g2s(dst, args.a.clv + goff, bytes, gfull + slot);
-                dst += kTileDoubles;
+    // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, row-sum slot n % 4
+    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == kProducerWarp) {
+        // ---------------------------------------------------------------------------------------------- producer
+        // lane 0 waits for the stage and announces the bytes, then lanes 0-4 hand one bulk copy each to the TMA engine
+        constexpr uint32_t bytes = kTileDoubles * sizeof(double), int_bytes = kTileRows * sizeof(int32_t);
+        for (int n = 0; n < cta_tiles; ++n) {
+            const int grp = n % kMmaGroups, j = n / kMmaGroups, slot = j % kBranchDepth;
+            uint64_t* full = in_full + grp * kBranchDepth + slot;
+            if (lane == 0) {
+                mbar_wait(in_empty + grp * kBranchDepth + slot, ((j / kBranchDepth) & 1) ^ 1);
+                mbar_expect_tx(full, Plan::kInner * (bytes + int_bytes) + int_bytes + (kTipA ? kTileRows : 0));
             }
-            bulk_g2s(dst, args.b.clv + goff, bytes, gfull + slot);
+            __syncwarp();
+            const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
+            const size_t goff = tile * kTileDoubles;
+            double* dst = s_stage + (size_t)(grp * kBranchDepth + slot) * Plan::kStageDoubles;
+            unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
+            if (lane == 0) bulk_g2s(dst + (kTipA ? 0 : kTileDoubles), args.b.clv + goff, bytes, full);
+            else if (lane == 1) {
+                if (!kTipA) bulk_g2s(dst, args.a.clv + goff, bytes, full);
+                else bulk_g2s(aux + 192, args.a.codes + tile * kTileRows, kTileRows, full);
+            } else if (lane == 2) bulk_g2s(aux, args.b.scale + tile * kTileRows, int_bytes, full);
+            else if (lane == 3) bulk_g2s(aux + 128, args.weights + tile * kTileRows, int_bytes, full);
+            else if (lane == 4 && !kTipA) bulk_g2s(aux + 64, args.a.scale + tile * kTileRows, int_bytes, full);
         }
-    };
-    const int first = blockIdx.x + grp * gridDim.x;
-    if (c == 0)
-        for (int d = 0; d < kDepth; ++d)
-            if (first + d * stride < ntiles) refill(first + d * stride, d);
+        return;
+    }
+
+    // every other warp: model constants into shared memory, one exponential per thread
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int idx = tid + q * kStagers;
+        if (idx < kStates * kStates) {
+            s_vinv[idx] = pre_vinv[q];
+            s_piv[idx] = pre_piv[q];
+        }
+    }
+    if (tid < kCats * 24) {
+        const double a = pre_lambda * pre_rate;
+        const double e = tid % 24 < kStates ? exp(a * tt) : 0.0;
+        s_exp[tid] = e;
+        s_exp[kCats * 24 + tid] = a * e;
+        s_exp[2 * kCats * 24 + tid] = a * a * e;
+    }
+    if (kTipA) {
+        named_barrier(kStageBarrier, kStagers);
+        // tipvec[code][k] = sum over the residues the code allows of pi_i V[i][k]
+        for (int idx = tid; idx < kCodes * kStates; idx += kStagers) {
+            const int code = idx / kStates, k = idx % kStates;
+            double acc = 0.0;
+            if (code < 20) acc = s_piv[code * kStates + k];
+            else if (code == 20) acc = s_piv[2 * kStates + k] + s_piv[3 * kStates + k];
+            else if (code == 21) acc = s_piv[5 * kStates + k] + s_piv[6 * kStates + k];
+            else
+                for (int i = 0; i < kStates; ++i) acc += s_piv[i * kStates + k];
+            s_tip[code * kTipVecPad + k] = acc;
+        }
+    }
+    named_barrier(kStageBarrier, kStagers);
+
+    if (warp >= kMmaWarps) {
+        // ---------------------------------------------------------------------------------------------- finishing
+        // a pair of tiles (one per MMA group) = 32 rows = one row per lane
+        const int e = warp - kMmaWarps, half = lane >> 4, r = lane & 15;
+        double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;
+        const int pairs = (cta_tiles + 1) / 2;
+        if (tr) args.trace[warp * 8 + 7] += clock64() - t_entry;  // entry -> loop
+        for (int q = e; q < pairs; q += kEpiWarps) {
+            const int n0 = 2 * q, n1 = n0 + 1, n = n0 + half;
+            const long long f0 = tr ? clock64() : 0;
+            mbar_wait(red_full + n0 % kRedSlots, (n0 / kRedSlots) & 1);
+            if (n1 < cta_tiles) mbar_wait(red_full + n1 % kRedSlots, (n1 / kRedSlots) & 1);
+            const long long f1c = tr ? clock64() : 0;
+            if (n < cta_tiles) {
+                const int slot = n % kRedSlots;
+                const double* red = s_red + (size_t)slot * kCats * kTileRows * 3 + r * 3;
+                constexpr int cs = kTileRows * 3;
+                const double f = (red[0] + red[cs]) + (red[2 * cs] + red[3 * cs]);
+                const double f1 = (red[1] + red[cs + 1]) + (red[2 * cs + 1] + red[3 * cs + 1]);
+                const double f2 = (red[2] + red[cs + 2]) + (red[2 * cs + 2] + red[3 * cs + 2]);
+                const int2 side = s_side[slot * kTileRows + r];
+                const double w = (double)side.y;
+                const int64_t p = ((int64_t)blockIdx.x + (int64_t)n * gridDim.x) * kTileRows + r;
+                if (kStore) args.sum_scale[p] = side.x;
+                // every FP64 instruction of these two warps waits in line behind the MMA warps' DMMAs (~30 clk each):
+                // only what the caller asked for is computed
+                if (args.want_lnl) {
+                    const double lnl = log(0.25 * f) + side.x * kLogMinLik;
+                    if (args.site_lnl) args.site_lnl[p] = lnl;
+                    sum_l = fma(w, lnl, sum_l);
+                }
+                if (args.want_derivs) {
+                    const double inv = 1.0 / f, qd = f1 * inv;
+                    sum_d1 = fma(w, qd, sum_d1);
+                    sum_d2 = fma(w, f2 * inv - qd * qd, sum_d2);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(red_empty + n0 % kRedSlots);
+                if (n1 < cta_tiles) mbar_arrive(red_empty + n1 % kRedSlots);
+            }
+            if (tr) {
+                args.trace[warp * 8 + 1] += f1c - f0;          // wait for the row sums
+                args.trace[warp * 8 + 2] += clock64() - f1c;   // logs, divisions, weights
+                args.trace[warp * 8 + 4] += 1;
+            }
+        }
+        const long long f2c = tr ? clock64() : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum_l += __shfl_xor_sync(0xffffffffu, sum_l, o);
+            sum_d1 += __shfl_xor_sync(0xffffffffu, sum_d1, o);
+            sum_d2 += __shfl_xor_sync(0xffffffffu, sum_d2, o);
+        }
+        if (lane == 0) {
+            s_fin[e * 3 + 0] = sum_l;
+            s_fin[e * 3 + 1] = sum_d1;
+            s_fin[e * 3 + 2] = sum_d2;
+        }
+        named_barrier(kFinishBarrier, kEpiWarps * 32);
+        if (e != 0) return;
+        // CTA partials, then the CTA that draws the last ticket adds all of them in a fixed order
+        if (lane < 3) {
+            args.partials[(int64_t)lane * gridDim.x + blockIdx.x] = s_fin[lane] + s_fin[3 + lane];
+            __threadfence();
+        }
+        __syncwarp();
+        unsigned int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(args.ticket, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (tr) {
+            args.trace[warp * 8 + 3] += clock64() - f2c;     // CTA partial + ticket
+            args.trace[warp * 8 + 0] += clock64() - t_entry;  // whole kernel as seen by CTA 0
+            args.trace[warp * 8 + 6] += 1;
+        }
+        if (ticket != gridDim.x - 1) return;
+        const long long f3c = args.trace ? clock64() : 0;
+        __threadfence();
+        double r3[3] = {0.0, 0.0, 0.0};  // lane-strided, then a shuffle tree -- the same order every run
+        for (int i = lane; i < (int)gridDim.x; i += 32) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) r3[v] += __ldcg(args.partials + (int64_t)v * gridDim.x + i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int v = 0; v < 3; ++v) r3[v] += __shfl_xor_sync(0xffffffffu, r3[v], o);
+        }
+        if (lane == 0) {
+            args.result[0] = r3[0];
+            args.result[1] = r3[1];
+            args.result[2] = r3[2];
+            args.result[3] = tt;
+            *args.ticket = 0;
+            publish_result(args.pub, r3, tt);
+            if (args.trace) {
+                args.trace[88] += clock64() - f3c;  // last CTA: final sum, NR step, publication
+                args.trace[89] += 1;
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------------------------------------- MMA warps
+    const int c = warp & 3, grp = warp >> 2, g = lane >> 2, t = lane & 3;
     // B fragments: a-side contracts x with pi_i V[i][k] (output k), b-side with Vinv[k][i]
     double fragA[3][5], fragB[3][5];
 #pragma unroll
@@ -99,195 +283,158 @@ __global__ void __launch_bounds__(kThreadsMma, 1) k_branch_mma(BranchArgs args, 
         const int k = nt * 8 + g;
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt) {
-            fragA[nt][kt] = (!kTipA && k < kStates) ? dm->piV[kmap(kt, t)][k] : 0.0;
-            fragB[nt][kt] = k < kStates ? dm->Vinv[k][kmap(kt, t)] : 0.0;
+            fragA[nt][kt] = (!kTipA && k < kStates) ? s_piv[kmap(kt, t) * kStates + k] : 0.0;
+            fragB[nt][kt] = k < kStates ? s_vinv[k * kStates + kmap(kt, t)] : 0.0;
         }
     }
-    // exp(lambda_k r_c t) and its first two t-derivatives at the D-fragment positions k = nt*8 + 2t + {0,1}
-    double e0[3][2], e1[3][2], e2[3][2];
-    {
-        const double tt = args.t, rate = dm->rates[c];
+    // The contraction of the products with exp(lambda_k r_c t) * {1, lambda r, (lambda r)^2} is one more small matrix
+    // product, [8 rows x 24 states] x [24 states x 3], and runs on the tensor pipe as well: a product held at D-fragment
+    // position (row g, state nt*8 + 2t + j) is the A element (row g, k = t) of k-tile (nt, j), so the matching B fragment is
+    // efrag[nt][j] = e_n[nt*8 + 2t + j] for output column n = g < 3.  Lane t = 0 ends up with (f, f'), lane t = 1 with f''.
+    // (As plain DFMAs the same contraction took 60 FP64 instructions per tile which fought the other group's DMMAs.)
+    double efrag[3][2];
 #pragma unroll
-        for (int nt = 0; nt < 3; ++nt)
+    for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int k = nt * 8 + 2 * t + j;
-                const double a = k < kStates ? dm->lambda[k] * rate : 0.0;
-                const double e = k < kStates ? exp(a * tt) : 0.0;
-                e0[nt][j] = e;
-                e1[nt][j] = a * e;
-                e2[nt][j] = a * a * e;
-            }
-    }
-
-    int next_code[2] = {0, 0};
-    if (kTipA && first < ntiles) {
-        next_code[0] = __ldg(args.a.codes + (int64_t)first * kTileRows + g);
-        next_code[1] = __ldg(args.a.codes + (int64_t)first * kTileRows + 8 + g);
-    }
-    const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int rounds = (cta_tiles + kGroups - 1) / kGroups;
+        for (int jj = 0; jj < 2; ++jj) efrag[nt][jj] = g < 3 ? s_exp[(g * kCats + c) * 24 + nt * 8 + 2 * t + jj] : 0.0;
+    const int rounds = (cta_tiles + kMmaGroups - 1) / kMmaGroups;
+    if (tr) args.trace[warp * 8 + 7] += clock64() - t_entry;  // prologue
     mma_turn_init(grp);
-    for (int it = 0; it < rounds; ++it) {
-        const int tile = first + it * stride;
-        if (tile >= ntiles) {  // no tile left for this group: keep the MMA token moving
+    for (int j = 0; j < rounds; ++j) {
+        const int n = j * kMmaGroups + grp;
+        if (n >= cta_tiles) {  // no tile left for this group: keep the MMA token moving
             mma_turn_begin(grp);
             mma_turn_end(grp);
             continue;
         }
-        const int slot = it % kDepth;
-        const int64_t row0 = (int64_t)tile * kTileRows;
-        int code[2] = {next_code[0], next_code[1]};
-        if (kTipA && tile + stride < ntiles) {  // the codes of the following tile travel while this one is computed
-            next_code[0] = __ldg(args.a.codes + row0 + (int64_t)stride * kTileRows + g);
-            next_code[1] = __ldg(args.a.codes + row0 + (int64_t)stride * kTileRows + 8 + g);
+        const int slot = j % kBranchDepth;
+        const long long tk0 = tr ? clock64() : 0;
+        mbar_wait(in_full + grp * kBranchDepth + slot, (j / kBranchDepth) & 1);
+        const long long tk1 = tr ? clock64() : 0;
+        const double* stage = s_stage + (size_t)(grp * kBranchDepth + slot) * Plan::kStageDoubles;
+        const unsigned char* aux = reinterpret_cast<const unsigned char*>(stage + Plan::kInner * kTileDoubles);
+        int2 side = make_int2(0, 0);  // category-0 warp, lanes 0-15: scaling counts and weight of row `lane`
+        if (c == 0 && lane < kTileRows) {
+            const int32_t* ai = reinterpret_cast<const int32_t*>(aux);
+            side.x = ai[lane] + (kTipA ? 0 : ai[kTileRows + lane]);
+            side.y = ai[2 * kTileRows + lane];
         }
-        // per-row integers are only needed after the MMAs: issue the loads now, consume them at the end
-        mbar_wait(gfull + slot, (it / kDepth) & 1);
-        const double* stage = gstage + (size_t)slot * Plan::kStageDoubles;
         AFrag fa[2], fb[2];
+        double accA[2][3][2], accB[2][3][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             if (!kTipA) fa[m] = load_a(stage + m * kBlockDoubles, c, lane);
             fb[m] = load_a(stage + (kTipA ? 0 : kTileDoubles) + m * kBlockDoubles, c, lane);
-        }
-        double accA[2][3][2], accB[2][3][2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
+            const int code = kTipA ? aux[192 + m * 8 + g] : 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
                 accB[m][nt][0] = accB[m][nt][1] = 0.0;
                 if (kTipA) {
                     const bool ok = nt < 2 || t < 2;
-                    const double* row = s_tip + code[m] * kTipVecPad + nt * 8 + 2 * t;
+                    const double* row = s_tip + code * kTipVecPad + nt * 8 + 2 * t;
                     accA[m][nt][0] = ok ? row[0] : 0.0;
                     accA[m][nt][1] = ok ? row[1] : 0.0;
                 } else {
                     accA[m][nt][0] = accA[m][nt][1] = 0.0;
                 }
             }
+        }
         mma_turn_begin(grp);  // see mma_common.cuh: the groups take turns on the FP64 tensor pipe
+        const long long tk2 = tr ? clock64() : 0;
+        // block by block; the whole contraction stays inside this group's turn (issued after the token is passed, its
+        // FP64 instructions and the other group's DMMAs slow each other down: measured 1,500 instead of 1,215 clk per tile)
 #pragma unroll
-        for (int kt = 0; kt < 5; ++kt)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
+            for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt) {
                     if (!kTipA) dmma(accA[m][nt][0], accA[m][nt][1], fa[m].v[kt], fragA[nt][kt]);
                     dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
                 }
+        // products of the two sides, then the contraction: four accumulator chains (2 per block) of three DMMAs each
+        double fs[2][2][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) fs[m][0][0] = fs[m][0][1] = fs[m][1][0] = fs[m][1][1] = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            accA[0][nt][0] *= accB[0][nt][0];
+            accA[0][nt][1] *= accB[0][nt][1];
+        }
+        dmma(fs[0][0][0], fs[0][0][1], accA[0][0][0], efrag[0][0]);
+        dmma(fs[0][1][0], fs[0][1][1], accA[0][0][1], efrag[0][1]);
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            accA[1][nt][0] *= accB[1][nt][0];
+            accA[1][nt][1] *= accB[1][nt][1];
+        }
+        dmma(fs[1][0][0], fs[1][0][1], accA[1][0][0], efrag[0][0]);
+        dmma(fs[1][1][0], fs[1][1][1], accA[1][0][1], efrag[0][1]);
+#pragma unroll
+        for (int nt = 1; nt < 3; ++nt)
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                dmma(fs[m][0][0], fs[m][0][1], accA[m][nt][0], efrag[nt][0]);
+                dmma(fs[m][1][0], fs[m][1][1], accA[m][nt][1], efrag[nt][1]);
+            }
+        const long long tk3 = tr ? clock64() : 0;
         mma_turn_end(grp);
-        double* red = s_red + (((it & 1) * kGroups + grp) * kCats) * kTileRows * 3;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_empty + grp * kBranchDepth + slot);  // the stage may be refilled
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            double f = 0.0, f1 = 0.0, f2 = 0.0;
-#pragma unroll
-            for (int nt = 0; nt < 3; ++nt)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const double sv = accA[m][nt][j] * accB[m][nt][j];
-                    accA[m][nt][j] = sv;
-                    f = fma(sv, e0[nt][j], f);
-                    f1 = fma(sv, e1[nt][j], f1);
-                    f2 = fma(sv, e2[nt][j], f2);
-                }
-            f += __shfl_xor_sync(0xffffffffu, f, 1);
-            f1 += __shfl_xor_sync(0xffffffffu, f1, 1);
-            f2 += __shfl_xor_sync(0xffffffffu, f2, 1);
-            f += __shfl_xor_sync(0xffffffffu, f, 2);
-            f1 += __shfl_xor_sync(0xffffffffu, f1, 2);
-            f2 += __shfl_xor_sync(0xffffffffu, f2, 2);
-            if (t == 0) {
-                double* dst = red + (c * kTileRows + m * 8 + g) * 3;
-                dst[0] = f;
-                dst[1] = f1;
-                dst[2] = f2;
-            }
+            fs[m][0][0] += fs[m][1][0];
+            fs[m][0][1] += fs[m][1][1];
             if (kStore) {
+                const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)n * gridDim.x) * kTileRows;
                 double* out = args.sumtable + (row0 + m * 8 + g) * kRow + c * kStates + 2 * t;
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt)
                     if (nt < 2 || t < 2) *reinterpret_cast<double2*>(out + nt * 8) = make_double2(accA[m][nt][0], accA[m][nt][1]);
             }
         }
-        named_barrier(1 + grp, 4 * 32);
-        if (c == 0 && tile + kDepth * stride < ntiles) refill(tile + kDepth * stride, slot);
-        // the four warps of a group share the row sums: warp c adds the categories of rows 4c .. 4c+3 (3 values each)
-        if (lane < 12) {
-            const int r = c * 4 + lane / 3, v = lane % 3;
-            const double sum = (red[(0 * kTileRows + r) * 3 + v] + red[(1 * kTileRows + r) * 3 + v]) +
-                               (red[(2 * kTileRows + r) * 3 + v] + red[(3 * kTileRows + r) * 3 + v]);
-            args.rowsum[(row0 + r) * 3 + v] = sum;
+        const int rslot = n % kRedSlots;
+        const long long tk4 = tr ? clock64() : 0;
+        mbar_wait(red_empty + rslot, ((n / kRedSlots) & 1) ^ 1);
+        const long long tk5 = tr ? clock64() : 0;
+        double* red = s_red + ((size_t)rslot * kCats + c) * kTileRows * 3;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            double* dst = red + (m * 8 + g) * 3;
+            if (t == 0) {
+                dst[0] = fs[m][0][0];
+                dst[1] = fs[m][0][1];
+            } else if (t == 1) {
+                dst[2] = fs[m][0][0];
+            }
+        }
+        if (c == 0 && lane < kTileRows) s_side[rslot * kTileRows + lane] = side;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(red_full + rslot);
+        if (tr) {  // phases: wait data | fragments + wait turn | MMAs | contraction | wait slot | row sums out | tiles
+            long long* row = args.trace + warp * 8;
+            const long long tk6 = clock64();
+            row[0] += tk1 - tk0;
+            row[1] += tk2 - tk1;
+            row[2] += tk3 - tk2;
+            row[3] += tk4 - tk3;
+            row[4] += tk5 - tk4;
+            row[5] += tk6 - tk5;
+            row[6] += 1;
         }
     }
+}
 
-    // ---- finish: the rows of this CTA's own tiles, all threads -------------------------------------------------
-    __syncthreads();
-    double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;
-    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    for (int idx = threadIdx.x; idx < my_tiles * kTileRows; idx += kThreadsMma) {
-        const int64_t p = ((int64_t)blockIdx.x + (int64_t)(idx / kTileRows) * gridDim.x) * kTileRows + idx % kTileRows;
-        const double f = args.rowsum[p * 3], f1 = args.rowsum[p * 3 + 1], f2 = args.rowsum[p * 3 + 2];
-        int32_t sc = __ldg(args.b.scale + p);
-        if (!kTipA) sc += __ldg(args.a.scale + p);
-        const double w = (double)__ldg(args.weights + p), inv = 1.0 / f, q = f1 * inv;
-        const double lnl = log(0.25 * f) + sc * kLogMinLik;
-        if (args.site_lnl) args.site_lnl[p] = lnl;
-        if (kStore) args.sum_scale[p] = sc;
-        sum_l = fma(w, lnl, sum_l);
-        sum_d1 = fma(w, q, sum_d1);
-        sum_d2 = fma(w, f2 * inv - q * q, sum_d2);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum_l += __shfl_xor_sync(0xffffffffu, sum_l, o);
-        sum_d1 += __shfl_xor_sync(0xffffffffu, sum_d1, o);
-        sum_d2 += __shfl_xor_sync(0xffffffffu, sum_d2, o);
-    }
-    double* s_fin = s_red;           // the exchange buffer of the loop is free now
-    __shared__ bool s_last;
-    if (lane == 0) {
-        s_fin[warp * 3 + 0] = sum_l;
-        s_fin[warp * 3 + 1] = sum_d1;
-        s_fin[warp * 3 + 2] = sum_d2;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double v = 0.0;
-        for (int k = 0; k < kComputeWarps; ++k) v += s_fin[k * 3 + threadIdx.x];
-        args.partials[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
-        __threadfence();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(args.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (warp < 3) {  // warp v adds value v over the CTAs: lane-strided, then a shuffle tree -- the same order every run
-        double acc = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) acc += args.partials[(int64_t)warp * gridDim.x + i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            args.result[warp] = acc;
-            if (args.host_result) args.host_result[warp] = acc;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *args.ticket = 0;
-        if (args.host_result) {
-            __threadfence_system();
-            args.host_result[3] = args.sequence;
-        }
-    }
+__global__ void k_publish(const double* result, Publish pub) {
+    const double r[3] = {result[0], result[1], result[2]};
+    publish_result(pub, r, result[3]);
 }
 
 template <bool kTipA, bool kStore>
 void launch_one(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    k_branch_mma<kTipA, kStore><<<grid, kThreadsMma, BranchPlan<kTipA>::kBytes, stream>>>(args, ntiles);
+    k_branch_mma<kTipA, kStore><<<grid, kThreadsBranch, BranchPlan<kTipA>::kBytes, stream>>>(args, ntiles);
 }
 
 }  // namespace
@@ -305,5 +452,7 @@ void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t
     if (tip) store ? launch_one<true, true>(args, np, sms, stream) : launch_one<true, false>(args, np, sms, stream);
     else store ? launch_one<false, true>(args, np, sms, stream) : launch_one<false, false>(args, np, sms, stream);
 }
+
+void launch_publish(const double* result, const Publish& pub, cudaStream_t stream) { k_publish<<<1, 1, 0, stream>>>(result, pub); }
 
 }  // namespace pml

@@ -67,15 +67,40 @@ struct pml_ctx {
     uint8_t* h_stage = nullptr;
     size_t stage_cap = 0, stage_used = 0;
     double* h_result = nullptr;
-    // zero-copy result slot: the branch kernel writes {lnL, d1, d2, sequence} here and the host polls the sequence, which
-    // saves a D2H copy and a stream synchronisation per Newton-Raphson step (single-rank contexts only)
+    // zero-copy result ring in mapped pinned memory: a branch pass publishes {lnL, d1, d2, length, NR status, sequence} in
+    // slot (sequence mod kRing) and the host polls the sequence -- no D2H copy, no stream synchronisation per branch
+    static constexpr int kRing = 8;
     volatile double* h_mapped = nullptr;
     double* d_mapped = nullptr;
     double sequence = 0.0;
+    int* d_poison = nullptr;  // see Publish in kernels.h
+    volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
+    double* slot_dev(double seq) const { return d_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
+    // waits until the pass with this sequence number has published; out = {lnL, d1, d2, length, status}
+    bool wait_slot(double seq, double out[5]) {
+        volatile double* s = slot_host(seq);
+        long spins = 0;
+        for (int i = 0; i < 5; ++i) {
+            while (s[2 * i + 1] != seq) {  // each (value, seq) pair arrives as one 16-byte write
+                if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(stream) != cudaErrorNotReady) {
+                    if (s[2 * i + 1] == seq) break;
+                    cuda(cudaStreamSynchronize(stream), "branch kernel");
+                    if (err.empty()) err = "branch kernel finished without publishing its result";
+                    return false;
+                }
+            }
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            out[i] = s[2 * i];
+        }
+        return true;
+    }
     // optional per-launch device timing (pml_profile_begin/end)
     struct Timed { int kind; int64_t rows; cudaEvent_t t0, t1; };
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
-    long long* d_trace = nullptr;  // pml_trace_enable
+    long long* d_trace = nullptr;  // pml_trace_enable (1: CLV kernel, 2: branch kernel)
+    long long* d_trace_buf = nullptr;
+    long long* d_trace_branch = nullptr;
+    bool trace_branch_tip = false;
     bool profiling = false;
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> spare_events;
@@ -184,7 +209,6 @@ struct pml_aln {
     double* d_partials = nullptr;
     double* d_result = nullptr;  // 16 doubles
     double* d_scalar = nullptr;  // branch length handed to the NR core
-    double* d_rowsum = nullptr;  // npad x 3: per-pattern f, f', f'' of the branch kernel
     unsigned int* d_ticket = nullptr;
     double* d_sumtable = nullptr;
     int32_t* d_sumscale = nullptr;
@@ -222,7 +246,6 @@ namespace {
 
 constexpr int kPad = 128;            // pattern rows are padded to a multiple of this (tile height of the CLV kernels)
 constexpr int kOpsPerBatch = 512;    // traversal entries whose P blocks are built by one launch
-constexpr double kZmin = 1.0e-15, kZmax = 1.0 - 1.0e-6;  // NR bounds on z = exp(-t) (raxmlHPC topLevelMakenewz)
 constexpr double kDefaultLen = 0.1;
 
 bool upload_model(pml_aln* a) {
@@ -344,7 +367,8 @@ bool ensure_sumtable(pml_aln* a) {
 // One pass over the two CLVs at the ends of branch e: out = {lnL, dlnL/dt, d2lnL/dt2} at length len, summed over ranks.
 // keep_table stores the eigen-space product table so that further lengths can be tried without re-reading the CLVs;
 // site_lnl fills the per-pattern lnL buffer (root evaluate).
-bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, double out[3]) {
+enum : int { kWantLnl = 1, kWantDerivs = 2, kWantAll = 3 };
+bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, double out[3], int want = kWantAll) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     if (keep_table && !ensure_sumtable(a)) return false;
@@ -357,49 +381,44 @@ bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_ta
     args.weights = dw;
     args.t = len;
     args.site_lnl = site_lnl ? a->d_site_lnl : nullptr;
+    args.want_lnl = want & 1;
+    args.want_derivs = (want >> 1) & 1;
     args.sumtable = keep_table ? a->d_sumtable : nullptr;
     args.sum_scale = keep_table ? a->d_sumscale : nullptr;
-    args.rowsum = a->d_rowsum;
     args.partials = a->d_partials;
     args.ticket = a->d_ticket;
     args.result = a->d_result;
-    const bool zero_copy = c->nranks == 1;
-    if (zero_copy) {
-        args.host_result = c->d_mapped;
-        args.sequence = (c->sequence += 1.0);
-    }
+    args.trace = c->trace_branch_tip == (args.a.clv == nullptr) ? c->d_trace_branch : nullptr;
+    Publish pub{};
+    pub.seq = (c->sequence += 1.0);
+    pub.slot = c->slot_dev(pub.seq);
+    if (c->nranks == 1) args.pub = pub;
     const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
     launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
     if (!c->cuda(cudaGetLastError(), "branch kernel")) return false;
-    if (zero_copy) {
-        // everything queued before the kernel has completed once its result is visible, so the staging area is free again
-        long spins = 0;
-        while (c->h_mapped[3] != args.sequence) {
-            if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(c->stream) != cudaErrorNotReady) {
-                if (c->h_mapped[3] == args.sequence) break;
-                c->cuda(cudaStreamSynchronize(c->stream), "branch kernel");
-                if (c->err.empty()) c->err = "branch kernel finished without publishing its result";
-                return false;
-            }
-        }
-        out[0] = c->h_mapped[0];
-        out[1] = c->h_mapped[1];
-        out[2] = c->h_mapped[2];
-        c->stage_used = 0;
-        return true;
+    if (c->nranks > 1) {
+        if (!c->allreduce(a->d_result, 3)) return false;
+        launch_publish(a->d_result, pub, c->stream);
+        t->launches += 1;
     }
-    if (!c->allreduce(a->d_result, 3)) return false;
-    return fetch_result(c, a->d_result, 3, out);
+    // everything queued before the pass has completed once its result is visible, so the staging area is free again
+    double r[5];
+    if (!c->wait_slot(pub.seq, r)) return false;
+    c->stage_used = 0;
+    out[0] = r[0];
+    out[1] = r[1];
+    out[2] = r[2];
+    return true;
 }
 
 int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     double r[3];
-    if (!branch_pass(t, e, dw, t->topo.len[e], false, true, r)) return t->aln->ctx->err.rfind("nccl", 0) == 0 ? PML_ECOMM : PML_ENODEVICE;
+    if (!branch_pass(t, e, dw, t->topo.len[e], false, true, r, kWantLnl)) return t->aln->ctx->err.rfind("nccl", 0) == 0 ? PML_ECOMM : PML_ENODEVICE;
     *lnl = r[0];
     return PML_OK;
 }
@@ -443,7 +462,7 @@ bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z
         z = std::min(std::max(z, kZmin), kZmax);
         double r[3];
         if (first || !keep) {
-            if (!branch_pass(t, e, dw, -std::log(z), keep, false, r)) return false;
+            if (!branch_pass(t, e, dw, -std::log(z), keep, false, r, kWantDerivs)) return false;
         } else if (!core_at(t, dw, -std::log(z), r)) return false;
         first = false;
         const double d1 = -r[1], d2 = r[2];  // derivatives in lz = log z = -t
@@ -586,7 +605,7 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
 // lnL of the tree at branch e without touching parameters (weights already on the device)
 bool lnl_at(pml_tree* t, int e, const int32_t* dw, double& lnl) {
     double r[3];
-    if (!branch_pass(t, e, dw, t->topo.len[e], false, false, r)) return false;
+    if (!branch_pass(t, e, dw, t->topo.len[e], false, false, r, kWantLnl)) return false;
     lnl = r[0];
     return true;
 }
@@ -696,10 +715,11 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     c->stage_cap = 1 << 20;
     if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
         !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc") ||
-        !c->cuda(cudaHostAlloc((void**)&c->h_mapped, 64, cudaHostAllocMapped), "mapped alloc") ||
-        !c->cuda(cudaHostGetDevicePointer((void**)&c->d_mapped, (void*)c->h_mapped, 0), "mapped pointer"))
+        !c->cuda(cudaHostAlloc((void**)&c->h_mapped, sizeof(double) * pml_ctx::kRing * kSlotDoubles, cudaHostAllocMapped), "mapped alloc") ||
+        !c->cuda(cudaHostGetDevicePointer((void**)&c->d_mapped, (void*)c->h_mapped, 0), "mapped pointer") ||
+        !c->cuda(cudaMalloc(&c->d_poison, sizeof(int)), "flag alloc") || !c->cuda(cudaMemset(c->d_poison, 0, sizeof(int)), "flag init"))
         return fail(nullptr, PML_ENOMEM, c->err);
-    c->h_mapped[3] = 0.0;
+    for (int i = 0; i < pml_ctx::kRing * kSlotDoubles; ++i) c->h_mapped[i] = 0.0;
     if (nranks > 1) {
         if (!unique_id) return fail(nullptr, PML_EINVAL, "unique_id required when nranks > 1");
         std::string err;
@@ -725,6 +745,8 @@ void pml_ctx_destroy(pml_ctx* c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->h_mapped) cudaFreeHost((void*)c->h_mapped);
+    if (c->d_poison) cudaFree(c->d_poison);
+    if (c->d_trace_buf) cudaFree(c->d_trace_buf);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
     for (auto e : c->spare_events) cudaEventDestroy(e);
     delete c;
@@ -739,20 +761,19 @@ int pml_ctx_sync(pml_ctx* c) {
 
 int pml_trace_enable(pml_ctx* c, int on) {
     if (!c || !c->bind() || !c->sync()) return PML_EINVAL;
-    if (on && !c->d_trace) {
-        if (!c->cuda(cudaMalloc(&c->d_trace, 96 * sizeof(long long)), "trace alloc")) return PML_ENOMEM;
+    if (on && !c->d_trace_buf) {
+        if (!c->cuda(cudaMalloc(&c->d_trace_buf, 96 * sizeof(long long)), "trace alloc")) return PML_ENOMEM;
     }
-    if (c->d_trace) cudaMemset(c->d_trace, 0, 96 * sizeof(long long));
-    if (!on && c->d_trace) {
-        cudaFree(c->d_trace);
-        c->d_trace = nullptr;
-    }
+    if (c->d_trace_buf) cudaMemset(c->d_trace_buf, 0, 96 * sizeof(long long));
+    c->d_trace = on == 1 ? c->d_trace_buf : nullptr;
+    c->d_trace_branch = on >= 2 ? c->d_trace_buf : nullptr;
+    c->trace_branch_tip = on == 3;
     return PML_OK;
 }
 
 int pml_trace_read(pml_ctx* c, int64_t out[96]) {
-    if (!c || !out || !c->d_trace || !c->bind() || !c->sync()) return PML_EINVAL;
-    return c->cuda(cudaMemcpy(out, c->d_trace, 96 * sizeof(long long), cudaMemcpyDeviceToHost), "trace read") ? PML_OK : PML_ENODEVICE;
+    if (!c || !out || !c->d_trace_buf || !c->bind() || !c->sync()) return PML_EINVAL;
+    return c->cuda(cudaMemcpy(out, c->d_trace_buf, 96 * sizeof(long long), cudaMemcpyDeviceToHost), "trace read") ? PML_OK : PML_ENODEVICE;
 }
 
 int pml_timer_start(pml_ctx* c) {
@@ -830,7 +851,6 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
               c->cuda(c->dev_alloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
               c->cuda(c->dev_alloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
               c->cuda(c->dev_alloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
-              c->cuda(c->dev_alloc(&a->d_rowsum, sizeof(double) * 3 * a->npad), "row sum alloc") &&
               c->cuda(c->dev_alloc(&a->d_ticket, 64), "ticket alloc") &&
               c->cuda(cudaMemset(a->d_ticket, 0, 64), "ticket clear") &&
               c->cuda(cudaMemcpy(a->d_codes, hc.data(), hc.size(), cudaMemcpyHostToDevice), "codes upload") &&
@@ -875,7 +895,6 @@ void pml_aln_free(pml_aln* a) {
     a->ctx->dev_free(a->d_partials);
     a->ctx->dev_free(a->d_result);
     a->ctx->dev_free(a->d_scalar);
-    a->ctx->dev_free(a->d_rowsum);
     a->ctx->dev_free(a->d_ticket);
     a->ctx->dev_free(a->d_sumtable);
     a->ctx->dev_free(a->d_sumscale);

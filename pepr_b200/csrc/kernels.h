@@ -56,25 +56,98 @@ void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t s
 // raises the dynamic shared-memory limit of the tensor-path kernels on the current device (once per context)
 void configure_mma_kernels();
 
-// One pass over the two ends of a branch (b inner, a inner or tip): lnL, dlnL/dt, d2lnL/dt2 at length *d_t as CTA partials
+// ---- guarded Newton-Raphson step on one branch (raxmlHPC topLevelMakenewz / makenewzGeneric) ----------
+// z = exp(-t) is updated in log z; d1t, d2t are dlnL/dt and d2lnL/dt2 at length t.
+//   bad curvature (d2 >= 0 in log z, z < zmax)  ->  z = 0.37 z + 0.63, the derivatives must be taken again (kNrRetry)
+//   otherwise z *= exp(-d1/d2) when that exponent is < 100, capped at 0.25 z + 0.75 and at zmax (kNrDone)
+constexpr double kZmin = 1.0e-15, kZmax = 1.0 - 1.0e-6;
+enum NrStatus : int { kNrNone = 0, kNrDone = 1, kNrRetry = 2, kNrSkipped = 3 };
+__host__ __device__ inline double nr_clamp_length(double t) {
+    double z = exp(-t);
+    z = z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
+    return -log(z);
+}
+__host__ __device__ inline int nr_step(double t, double d1t, double d2t, double* t_new) {
+    double z = exp(-t);
+    z = z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
+    const double d1 = -d1t, d2 = d2t;  // derivatives in lz = log z = -t
+    if (d2 >= 0.0 && z < kZmax) {
+        *t_new = -log(0.37 * z + 0.63);
+        return kNrRetry;
+    }
+    const double zprev = z;
+    if (d2 < 0.0) {
+        const double step = -d1 / d2;
+        if (step < 100.0) {
+            z *= exp(step);
+            z = z < kZmin ? kZmin : z;
+            const double cap = 0.25 * zprev + 0.75;
+            z = z > cap ? cap : z;
+        } else {
+            z = 0.25 * zprev + 0.75;
+        }
+    }
+    z = z > kZmax ? kZmax : z;
+    *t_new = -log(z);
+    return kNrDone;
+}
+
+// Where a branch pass leaves its outcome.  `slot` is mapped pinned host memory the host polls: five (value, seq) pairs,
+// each written with ONE 16-byte store -- a pair is valid as soon as its seq matches, so no system-wide fence is needed:
+//   pair 0..2 = lnL, dlnL/dt, d2lnL/dt2 (summed over ranks), pair 3 = the branch length after the step, pair 4 = NrStatus.
+// With `len` set the guarded NR step is done on the device and stored to *len unless *poison is set; a step that ends in
+// kNrRetry sets *poison, so that work queued behind it cannot move other branches before the host has dealt with the retry.
+constexpr int kSlotDoubles = 10;
+struct Publish {
+    double* slot;   // nullptr: nothing is published
+    double seq;
+    double* len;    // nullptr: no NR step
+    int* poison;
+};
+// tail of a branch pass on one thread: NR step (optional) and publication; r = {lnL, d1, d2}, t = the length they were taken at
+__device__ __forceinline__ void publish_result(const Publish& pub, const double r[3], double t) {
+    double t_new = t;
+    int status = kNrNone;
+    if (pub.len) {
+        if (*pub.poison) status = kNrSkipped;
+        else {
+            status = nr_step(t, r[1], r[2], &t_new);
+            *pub.len = t_new;
+            if (status == kNrRetry) *pub.poison = 1;
+        }
+    }
+    if (pub.slot) {
+        double2* pairs = reinterpret_cast<double2*>(pub.slot);
+        pairs[0] = make_double2(r[0], pub.seq);
+        pairs[1] = make_double2(r[1], pub.seq);
+        pairs[2] = make_double2(r[2], pub.seq);
+        pairs[3] = make_double2(t_new, pub.seq);
+        pairs[4] = make_double2((double)status, pub.seq);
+    }
+}
+
+// One pass over the two ends of a branch (b inner, a inner or tip): lnL, dlnL/dt, d2lnL/dt2 at the given length
 // (+ per-pattern lnL when site_lnl != nullptr, + the eigen-space product table when sumtable != nullptr).
 struct BranchArgs {
     Side a, b;
     const DeviceModel* dm;
     const int32_t* weights;
-    double t;             // branch length the sums are evaluated at
+    double t;             // branch length the sums are evaluated at ...
+    const double* t_ptr;  // ... or, when set, where to read it on the device (clamped to the NR range)
     double* site_lnl;     // optional
+    int want_lnl, want_derivs;  // which of the sums the caller will look at (the others come back as 0)
     double* sumtable;     // optional: np x 80
     int32_t* sum_scale;   // with sumtable
-    double* rowsum;       // np x 3 scratch: f, f', f'' per pattern
     double* partials;     // 3 x grid doubles
     unsigned int* ticket; // zero-initialised; the CTA drawing the last ticket adds the partials and resets it
-    double* result;       // 3 doubles in device memory (input of the NCCL allreduce when ranks > 1)
-    volatile double* host_result;  // optional: 4 doubles in mapped pinned memory; [3] receives `sequence` after [0..2]
-    double sequence;
+    double* result;       // 4 doubles in device memory: lnL, d1, d2 of this rank's patterns (input of the allreduce), length used
+    Publish pub;          // single-rank contexts: the kernel itself publishes; otherwise launch_publish after the allreduce
+    long long* trace;     // optional (profiling aid), as NewviewOp::trace
 };
 void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
 void configure_branch_kernels();
+// NR step + publication from result[0..3] (after the allreduce of result[0..2] when ranks > 1)
+void launch_publish(const double* result, const Publish& pub, cudaStream_t stream);
 // fixed-order sum of `nblocks` partials for each of `nvals` values
 void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream);
 

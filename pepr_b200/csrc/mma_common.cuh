@@ -25,10 +25,13 @@ constexpr int kBlockDoubles = kBlockRows * kRow;  // 640
 constexpr int kCatDoubles = kBlockRows * kStates; // 160
 constexpr int kTileDoubles = kTileRows * kRow;    // one child's share of a stage
 constexpr int kTipPad = 82;                  // doubles per padded tip-table row
-constexpr int kGroups = 3;                   // independent groups of 4 warps (one warp per rate category)
-constexpr int kDepth = 3;                    // stages in each group's private ring
-constexpr int kComputeWarps = 4 * kGroups;
-constexpr int kThreadsMma = kComputeWarps * 32;  // 384: no dedicated producer warp, the register budget stays at 168
+// warp roles of the streaming kernels (newview_mma.cu, branch_mma.cu): 8 MMA warps in two groups of four (one warp per
+// rate category), 2 epilogue / finishing warps, 1 producer warp
+constexpr int kMmaGroups = 2;
+constexpr int kMmaWarps = 4 * kMmaGroups;
+constexpr int kEpiWarps = 2;
+constexpr int kProducerWarp = kMmaWarps + kEpiWarps;
+constexpr int kDepth = 3;                    // stages in each group's private input ring (newview)
 constexpr double kTwo256 = 1.157920892373161954235709850086879078532699846656405640394575840079131296399e77;
 constexpr double kMinLik = 8.636168555094444625386351862800399571116000364436281385023703470168591803162e-78;
 constexpr int kMinLikHi = 0x2FF00000;        // high word of 2^-256 (biased exponent 1023 - 256 = 0x2FF, mantissa 0)
@@ -68,18 +71,28 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// MMA turn-taking between the groups of a CTA.  The FP64 tensor pipe is one unit per SM (4 clk per DMMA.8x8x4) and ONE group
-// -- four warps, one per SM sub-partition, each issuing a DMMA every 16 clk -- already saturates it.  Left to the
-// round-robin warp scheduler, all twelve warps crawl through their MMA bursts together and then do their epilogues
-// together, leaving the pipe idle (measured: 56 % busy).  With the token below the bursts of the three groups follow each
-// other and every group's loads, scaling test and stores run under another group's MMAs (the "ping-pong" schedule of
-// warp-specialised GEMMs).  Barrier kTurnBarrier + g is shared by group g (sync) and group g-1 (arrive).
+// MMA turn-taking between the two groups of a CTA.  The FP64 tensor pipe is one unit per SM (4 clk per DMMA.8x8x4) and ONE
+// group -- four warps, one per SM sub-partition, each issuing a DMMA every 16 clk -- already saturates it.  Left to the
+// round-robin warp scheduler all MMA warps crawl through their bursts together and then do their other work together,
+// leaving the pipe idle (measured: 56 % busy).  With the token below the bursts of the groups follow each other and
+// every group's loads, products and stores run under the other group's MMAs (the "ping-pong" schedule of warp-specialised
+// GEMMs).  Barrier kTurnBarrier + g is shared by group g (sync) and the other group (arrive).
 constexpr int kTurnBarrier = 4;
-__device__ __forceinline__ void mma_turn_begin(int grp) { named_barrier(kTurnBarrier + grp, 2 * 4 * 32); }
-__device__ __forceinline__ void mma_turn_end(int grp) { named_barrier_arrive(kTurnBarrier + (grp + 1) % kGroups, 2 * 4 * 32); }
+constexpr int kTurnThreads = 2 * 4 * 32;
+__device__ __forceinline__ void mma_turn_begin(int grp) { named_barrier(kTurnBarrier + grp, kTurnThreads); }
+__device__ __forceinline__ void mma_turn_end(int grp) { named_barrier_arrive(kTurnBarrier + (grp + 1) % kMmaGroups, kTurnThreads); }
 __device__ __forceinline__ void mma_turn_init(int grp) {
-    if (grp == kGroups - 1) named_barrier_arrive(kTurnBarrier, 2 * 4 * 32);  // group 0 may start
+    if (grp == kMmaGroups - 1) named_barrier_arrive(kTurnBarrier, kTurnThreads);  // group 0 may start
 }
+
+// TMA engine bulk copy shared -> global (bulk async-group completion) and the proxy fence a generic-proxy writer needs
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // state index that lane t feeds into k-tile kt: pairs of k-tiles share one 128-bit shared-memory load
 __device__ __forceinline__ int kmap(int kt, int t) { return kt < 4 ? (kt >> 1) * 8 + 2 * t + (kt & 1) : 16 + t; }

@@ -48,10 +48,6 @@ __device__ __forceinline__ void lookup_rows(const double* table, int code, int c
 //               write the scaling counts.
 //   warp 10     producer: refills the stages with one bulk copy per inner child as soon as a stage has been consumed.
 // Everything an MMA warp does besides its 60 DMMAs is ~70 instructions, so the pipe stays busy; stores cost no LSU work.
-constexpr int kMmaGroups = 2;
-constexpr int kMmaWarps = 4 * kMmaGroups;
-constexpr int kEpiWarps = 2;
-constexpr int kProducerWarp = kMmaWarps + kEpiWarps;
 constexpr int kThreadsNewview = 384;   // warp 11 idles: 12 warps keep the register budget at 168
 constexpr int kProdSlots = 4;
 
@@ -68,14 +64,6 @@ struct SmemPlan {
     static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(kInner == 2 ? 0 : kTipDoubles) + sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
                                      sizeof(double) * (size_t)(kProdSlots * kTileDoubles + kMmaGroups * kDepth * kStageDoubles);
 };
-
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // at least one child is an inner node (the tip-tip case has its own kernel below)
 template <bool kTipL, bool kTipR>
@@ -216,12 +204,12 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     if (!kTipR) load_p_fragments(op.pright, c, g, t, fragR);
     const int rounds = (cta_tiles + kMmaGroups - 1) / kMmaGroups;
     if (op.trace && blockIdx.x == 0 && lane == 0) op.trace[warp * 8 + 7] += clock64() - t_entry;  // prologue
-    if (grp == kMmaGroups - 1) named_barrier_arrive(kTurnBarrier, 2 * 4 * 32);  // group 0 may start
+    mma_turn_init(grp);
     for (int j = 0; j < rounds; ++j) {
         const int n = j * kMmaGroups + grp;
         if (n >= cta_tiles) {  // no tile left for this group: keep the MMA token moving
-            named_barrier(kTurnBarrier + grp, 2 * 4 * 32);
-            named_barrier_arrive(kTurnBarrier + (grp + 1) % kMmaGroups, 2 * 4 * 32);
+            mma_turn_begin(grp);
+            mma_turn_end(grp);
             continue;
         }
         const int slot = j % kDepth;
@@ -258,7 +246,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
                 if (!kTipR) accR[m][nt][0] = accR[m][nt][1] = 0.0;
             }
         // this group's turn on the FP64 tensor pipe; 12 (6) independent accumulator chains lie between two dependent MMAs
-        named_barrier(kTurnBarrier + grp, 2 * 4 * 32);
+        mma_turn_begin(grp);
         long long tk2 = tr ? clock64() : 0;
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt)
@@ -270,7 +258,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
                     if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
                 }
         long long tk3 = tr ? clock64() : 0;
-        named_barrier_arrive(kTurnBarrier + (grp + 1) % kMmaGroups, 2 * 4 * 32);
+        mma_turn_end(grp);
         __syncwarp();
         if (lane == 0) mbar_arrive(in_empty + grp * kDepth + slot);  // the stage may be refilled
         // products and, through the high word of |x| on the integer pipe, this category's magnitude of every row
