@@ -221,10 +221,9 @@ struct pml_tree {
     ViewState views;
     double* d_clv = nullptr;      // (ntax-2) x npad x 80
     int32_t* d_scale = nullptr;   // (ntax-2) x npad
-    PBlock* d_pblocks = nullptr;
-    int pblock_cap = 0;
-    double* d_lengths = nullptr;
-    uint8_t* d_wanttip = nullptr;
+    double* d_len = nullptr;      // branch lengths as the kernels read them (one double per branch id)
+    std::vector<double> len_dev;  // what d_len holds (mirror), so that host-side edits of topo.len are uploaded lazily
+    int64_t nr_retries = 0;       // Newton-Raphson passes that ended in the bad-curvature retry
     int prepared_branch = -1;     // branch whose sumtable is resident
     int64_t site_updates[3] = {0, 0, 0};
     int64_t launches = 0;
@@ -245,7 +244,6 @@ struct pml_tree {
 namespace {
 
 constexpr int kPad = 128;            // pattern rows are padded to a multiple of this (tile height of the CLV kernels)
-constexpr int kOpsPerBatch = 512;    // traversal entries whose P blocks are built by one launch
 constexpr double kDefaultLen = 0.1;
 
 bool upload_model(pml_aln* a) {
@@ -276,17 +274,31 @@ const int32_t* device_weights(pml_aln* a, const int32_t* weights) {
     return a->d_wcustom;
 }
 
-// one CLV kernel per traversal entry; entry i of the batch uses P blocks 2i and 2i+1
-void launch_entries(pml_tree* t, const std::vector<ViewOp>& ops, size_t base, int n) {
+// host-side edits of branch lengths (set_branch, SPR moves, a freshly loaded tree) reach the device before the next launch
+bool sync_lengths(pml_tree* t) {
+    pml_ctx* c = t->aln->ctx;
+    const std::vector<double>& len = t->topo.len;
+    if (t->len_dev.size() == len.size() && std::memcmp(t->len_dev.data(), len.data(), sizeof(double) * len.size()) == 0) return true;
+    auto* h = (double*)c->stage(sizeof(double) * len.size());
+    if (!h) return false;
+    std::memcpy(h, len.data(), sizeof(double) * len.size());
+    if (!c->cuda(cudaMemcpyAsync(t->d_len, h, sizeof(double) * len.size(), cudaMemcpyHostToDevice, c->stream), "lengths upload")) return false;
+    t->len_dev = len;
+    return true;
+}
+
+// executes a traversal descriptor: one CLV kernel per entry; each builds its own P matrices from the device lengths
+bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
-    for (int i = 0; i < n; ++i) {
-        const ViewOp& op = ops[base + i];
+    if (!sync_lengths(t)) return false;
+    for (const ViewOp& op : ops) {
         NewviewOp nv{};
         nv.left = t->side(op.child[0]);
         nv.right = t->side(op.child[1]);
-        nv.pleft = t->d_pblocks + 2 * i;
-        nv.pright = t->d_pblocks + 2 * i + 1;
+        nv.len_left = t->d_len + op.cedge[0];
+        nv.len_right = t->d_len + op.cedge[1];
+        nv.dm = a->d_model;
         nv.out = t->clv(op.node);
         nv.out_scale = t->scale(op.node);
         nv.trace = c->d_trace;
@@ -297,45 +309,7 @@ void launch_entries(pml_tree* t, const std::vector<ViewOp>& ops, size_t base, in
         ++t->launches;
         t->site_updates[2 - ntip] += a->nloc;
     }
-}
-
-// executes a traversal descriptor: P blocks for every entry in one launch, then one CLV kernel per entry
-bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
-    pml_aln* a = t->aln;
-    pml_ctx* c = a->ctx;
-    for (size_t base = 0; base < ops.size(); base += kOpsPerBatch) {
-        const int n = (int)std::min<size_t>(kOpsPerBatch, ops.size() - base);
-        if (2 * n <= kMakePInline) {
-            // the usual case while smoothing (1-3 entries): branch lengths ride in the kernel arguments
-            MakePInline batch{};
-            for (int i = 0; i < n; ++i)
-                for (int k = 0; k < 2; ++k) {
-                    batch.length[2 * i + k] = t->topo.len[ops[base + i].cedge[k]];
-                    batch.want_tip[2 * i + k] = t->topo.is_tip(ops[base + i].child[k]) ? 1 : 0;
-                }
-            launch_make_p_inline(a->d_model, batch, t->d_pblocks, 2 * n, c->stream);
-            ++t->launches;
-            launch_entries(t, ops, base, n);
-            continue;
-        }
-        auto* hl = (double*)c->stage(sizeof(double) * 2 * n + 2 * n);
-        if (!hl) return false;
-        auto* ht = (uint8_t*)(hl + 2 * n);
-        for (int i = 0; i < n; ++i) {
-            const ViewOp& op = ops[base + i];
-            for (int k = 0; k < 2; ++k) {
-                hl[2 * i + k] = t->topo.len[op.cedge[k]];
-                ht[2 * i + k] = t->topo.is_tip(op.child[k]) ? 1 : 0;
-            }
-        }
-        if (!c->cuda(cudaMemcpyAsync(t->d_lengths, hl, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream), "lengths upload") ||
-            !c->cuda(cudaMemcpyAsync(t->d_wanttip, ht, 2 * n, cudaMemcpyHostToDevice, c->stream), "flags upload"))
-            return false;
-        launch_make_p(a->d_model, t->d_lengths, t->d_wanttip, t->d_pblocks, 2 * n, c->stream);
-        ++t->launches;
-        launch_entries(t, ops, base, n);
-    }
-    return c->cuda(cudaGetLastError(), "CLV kernels");
+    return ops.empty() || c->cuda(cudaGetLastError(), "CLV kernels");
 }
 
 // brings both ends of branch e up to date; (a, b) is returned with b inner and a the tip end if there is one
@@ -364,22 +338,26 @@ bool ensure_sumtable(pml_aln* a) {
            c->cuda(c->dev_alloc(&a->d_sumscale, sizeof(int32_t) * a->npad), "sumtable scale alloc");
 }
 
-// One pass over the two CLVs at the ends of branch e: out = {lnL, dlnL/dt, d2lnL/dt2} at length len, summed over ranks.
-// keep_table stores the eigen-space product table so that further lengths can be tried without re-reading the CLVs;
-// site_lnl fills the per-pattern lnL buffer (root evaluate).
+// One pass over the two CLVs at the ends of branch e: {lnL, dlnL/dt, d2lnL/dt2} summed over ranks, published in the
+// context's result ring under the returned sequence number (0 on failure).
+//   device_nr = false: sums at length len; keep_table stores the eigen-space product table so that further lengths can be
+//               tried without re-reading the CLVs; site_lnl fills the per-pattern lnL buffer (root evaluate)
+//   device_nr = true:  sums at the branch's length in the tree's device array, followed on the device by the guarded
+//               Newton-Raphson step that overwrites it (see Publish in kernels.h); len is ignored
 enum : int { kWantLnl = 1, kWantDerivs = 2, kWantAll = 3 };
-bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, double out[3], int want = kWantAll) {
+double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, int want, bool device_nr) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
-    if (keep_table && !ensure_sumtable(a)) return false;
+    if (keep_table && !ensure_sumtable(a)) return 0.0;
     int x, y;
-    if (!orient_branch(t, e, x, y)) return false;
+    if (!orient_branch(t, e, x, y) || !sync_lengths(t)) return 0.0;
     BranchArgs args{};
     args.a = t->side(x);
     args.b = t->side(y);
     args.dm = a->d_model;
     args.weights = dw;
     args.t = len;
+    args.t_ptr = device_nr ? t->d_len + e : nullptr;
     args.site_lnl = site_lnl ? a->d_site_lnl : nullptr;
     args.want_lnl = want & 1;
     args.want_derivs = (want >> 1) & 1;
@@ -392,21 +370,31 @@ bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_ta
     Publish pub{};
     pub.seq = (c->sequence += 1.0);
     pub.slot = c->slot_dev(pub.seq);
+    if (device_nr) {
+        pub.len = t->d_len + e;
+        pub.poison = c->d_poison;
+    }
     if (c->nranks == 1) args.pub = pub;
     const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
     launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
-    if (!c->cuda(cudaGetLastError(), "branch kernel")) return false;
+    if (!c->cuda(cudaGetLastError(), "branch kernel")) return 0.0;
     if (c->nranks > 1) {
-        if (!c->allreduce(a->d_result, 3)) return false;
+        if (!c->allreduce(a->d_result, 3)) return 0.0;
         launch_publish(a->d_result, pub, c->stream);
         t->launches += 1;
     }
+    return pub.seq;
+}
+
+bool branch_pass(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, double out[3], int want = kWantAll) {
+    pml_ctx* c = t->aln->ctx;
+    const double seq = branch_launch(t, e, dw, len, keep_table, site_lnl, want, false);
     // everything queued before the pass has completed once its result is visible, so the staging area is free again
     double r[5];
-    if (!c->wait_slot(pub.seq, r)) return false;
+    if (seq == 0.0 || !c->wait_slot(seq, r)) return false;
     c->stage_used = 0;
     out[0] = r[0];
     out[1] = r[1];
@@ -488,25 +476,77 @@ bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z
     return true;
 }
 
-// one sweep: depth-first over all branches starting at taxon 0's branch, one guarded NR step each (raxmlHPC smoothTree/update)
+// One sweep: depth-first over all branches starting at taxon 0's branch, one guarded NR step each (raxmlHPC
+// smoothTree/update).  The step itself runs on the device (branch kernel tail / k_publish) and the host stays one branch
+// ahead: while the GPU works on branch i the host has already queued branch i+1 and only then looks at the published
+// outcome of branch i.  The speculation is that the step did not end in the bad-curvature retry (it never did on the bench
+// workload); if it did, the device has refused the step queued behind it (poison flag), the host repeats the pass until
+// the curvature is fine and queues the next branch again.
 bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
     smoothed = true;
-    const Topology& T = t->topo;
-    std::vector<std::pair<int, int>> stack;  // (branch, far node)
-    stack.push_back({T.edge[0][0], T.nbr[0][0]});
-    while (!stack.empty()) {
-        const auto [e, far] = stack.back();
-        stack.pop_back();
-        const double z0 = std::min(std::max(std::exp(-T.len[e]), kZmin), kZmax);
-        double z;
-        if (!newton_branch(t, e, dw, 1, z)) return false;
-        if (std::fabs(z - z0) > 1.0e-5) smoothed = false;
-        set_branch(t, e, -std::log(z));
-        if (!T.is_tip(far)) {
-            const int near = T.ea[e] == far ? T.eb[e] : T.ea[e];
-            for (int s = 2; s >= 0; --s)
-                if (T.nbr[far][s] != near) stack.push_back({T.edge[far][s], T.nbr[far][s]});
+    pml_ctx* c = t->aln->ctx;
+    Topology& T = t->topo;
+    std::vector<int> order;
+    {
+        std::vector<std::pair<int, int>> stack;  // (branch, far node)
+        stack.push_back({T.edge[0][0], T.nbr[0][0]});
+        while (!stack.empty()) {
+            const auto [e, far] = stack.back();
+            stack.pop_back();
+            order.push_back(e);
+            if (!T.is_tip(far)) {
+                const int near = T.ea[e] == far ? T.eb[e] : T.ea[e];
+                for (int s = 2; s >= 0; --s)
+                    if (T.nbr[far][s] != near) stack.push_back({T.edge[far][s], T.nbr[far][s]});
+            }
         }
+    }
+    struct Pending { int e; double seq; };
+    // adopts the outcome of a queued step: host mirror of the length, convergence flag; false = retry needed / error
+    auto adopt = [&](const Pending& p, double r[5]) {
+        if (!c->wait_slot(p.seq, r)) return false;
+        const int status = (int)r[4];
+        if (status == kNrSkipped) return true;
+        const double z0 = std::min(std::max(std::exp(-T.len[p.e]), kZmin), kZmax);
+        T.len[p.e] = t->len_dev[p.e] = r[3];
+        if (status == kNrDone && std::fabs(std::exp(-r[3]) - z0) > 1.0e-5) smoothed = false;
+        return true;
+    };
+    auto queue_step = [&](int e) {
+        Pending p{e, branch_launch(t, e, dw, 0.0, false, false, kWantDerivs, true)};
+        t->views.branch_changed(T, e);  // the length is about to change
+        t->prepared_branch = -1;
+        return p;
+    };
+    size_t i = 0;
+    Pending prev{-1, 0.0};
+    while (i < order.size() || prev.e >= 0) {
+        Pending cur{-1, 0.0};
+        if (i < order.size()) {
+            cur = queue_step(order[i]);
+            if (cur.seq == 0.0) return false;
+        }
+        if (prev.e >= 0) {
+            double r[5];
+            if (!adopt(prev, r)) return false;
+            if ((int)r[4] == kNrRetry) {
+                ++t->nr_retries;
+                // the step queued behind (cur) was refused on the device: wait for it, lift the flag, redo prev until it is done
+                if (cur.e >= 0 && !c->wait_slot(cur.seq, r)) return false;
+                if (!c->cuda(cudaMemsetAsync(c->d_poison, 0, sizeof(int), c->stream), "flag clear")) return false;
+                for (int guard = 0; guard < 64; ++guard) {
+                    const Pending again = queue_step(prev.e);
+                    if (again.seq == 0.0 || !adopt(again, r)) return false;
+                    if ((int)r[4] != kNrRetry) break;
+                    ++t->nr_retries;
+                    if (!c->cuda(cudaMemsetAsync(c->d_poison, 0, sizeof(int), c->stream), "flag clear")) return false;
+                }
+                prev = Pending{-1, 0.0};
+                continue;  // cur is queued again on the next trip (i was not advanced)
+            }
+        }
+        prev = cur;
+        if (cur.e >= 0) ++i;
     }
     return true;
 }
@@ -968,12 +1008,9 @@ int pml_tree_load(pml_aln* a, const char* newick, pml_tree** out) {
     if (!parse_newick(newick, a->pat.names, kDefaultLen, t->topo, err)) return fail(c, PML_EINVAL, err);
     t->views.reset(t->topo);
     const size_t inner = (size_t)a->pat.ntax - 2;
-    t->pblock_cap = 2 * kOpsPerBatch + 1;
     bool ok = c->cuda(c->dev_alloc(&t->d_clv, sizeof(double) * inner * a->npad * kRow), "CLV arena alloc") &&
               c->cuda(c->dev_alloc(&t->d_scale, sizeof(int32_t) * inner * a->npad), "scaler alloc") &&
-              c->cuda(c->dev_alloc(&t->d_pblocks, sizeof(PBlock) * t->pblock_cap), "P block alloc") &&
-              c->cuda(c->dev_alloc(&t->d_lengths, sizeof(double) * t->pblock_cap), "lengths alloc") &&
-              c->cuda(c->dev_alloc(&t->d_wanttip, t->pblock_cap), "flags alloc");
+              c->cuda(c->dev_alloc(&t->d_len, sizeof(double) * std::max(1, t->topo.nedges())), "lengths alloc");
     if (!ok) {
         pml_tree_free(t.release());
         return PML_ENOMEM;
@@ -989,9 +1026,7 @@ void pml_tree_free(pml_tree* t) {
     cudaStreamSynchronize(t->aln->ctx->stream);
     t->aln->ctx->dev_free(t->d_clv);
     t->aln->ctx->dev_free(t->d_scale);
-    t->aln->ctx->dev_free(t->d_pblocks);
-    t->aln->ctx->dev_free(t->d_lengths);
-    t->aln->ctx->dev_free(t->d_wanttip);
+    t->aln->ctx->dev_free(t->d_len);
     delete t;
 }
 

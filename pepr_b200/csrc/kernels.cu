@@ -1,4 +1,4 @@
-// Small CUDA kernels of the likelihood path (sm_100a): batched P(t) construction, the Newton-Raphson core on a stored
+// Small CUDA kernels of the likelihood path (sm_100a): the Newton-Raphson core on a stored
 // product table, the fixed-order second stage of every reduction, replicate lnL.  The CLV-streaming kernels live in
 // newview_mma.cu and branch_mma.cu.
 #include "kernels.h"
@@ -21,57 +21,6 @@ __device__ __forceinline__ void load_row20(const double* __restrict__ src, doubl
         const double2 t = __ldg(s2 + j);
         v[2 * j] = t.x;
         v[2 * j + 1] = t.y;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ P(t) ----
-__device__ __forceinline__ void make_p_block(const DeviceModel* __restrict__ dm, double t, bool want_tip, PBlock* __restrict__ blocks);
-
-__global__ void __launch_bounds__(256) k_make_p(const DeviceModel* __restrict__ dm, const double* __restrict__ lengths,
-                                                const uint8_t* __restrict__ want_tip, PBlock* __restrict__ blocks) {
-    make_p_block(dm, lengths[blockIdx.x], want_tip[blockIdx.x] != 0, blocks);
-}
-
-__global__ void __launch_bounds__(256) k_make_p_inline(const DeviceModel* __restrict__ dm, const MakePInline batch, PBlock* __restrict__ blocks) {
-    make_p_block(dm, batch.length[blockIdx.x], batch.want_tip[blockIdx.x] != 0, blocks);
-}
-
-__device__ __forceinline__ void make_p_block(const DeviceModel* __restrict__ dm, const double t, const bool want_tip, PBlock* __restrict__ blocks) {
-    __shared__ double s_exp[kCats][kStates];
-    __shared__ double s_P[kCats][kStates][kStates];
-    __shared__ double s_V[kStates][kStates + 1], s_Vinv[kStates][kStates];
-    const int b = blockIdx.x;
-    if (threadIdx.x < kRow) {
-        const int c = threadIdx.x / kStates, k = threadIdx.x % kStates;
-        s_exp[c][k] = exp(dm->lambda[k] * dm->rates[c] * t);
-    }
-    for (int idx = threadIdx.x; idx < kStates * kStates; idx += blockDim.x) {
-        s_V[idx / kStates][idx % kStates] = (&dm->V[0][0])[idx];
-        (&s_Vinv[0][0])[idx] = (&dm->Vinv[0][0])[idx];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kCats * kStates * kStates; idx += blockDim.x) {
-        const int c = idx / (kStates * kStates), i = (idx / kStates) % kStates, j = idx % kStates;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < kStates; ++k) acc = fma(s_V[i][k] * s_exp[c][k], s_Vinv[k][j], acc);
-        s_P[c][i][j] = acc;
-        blocks[b].P[c][i][j] = acc;
-    }
-    if (!want_tip) return;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kCodes * kRow; idx += blockDim.x) {
-        const int code = idx / kRow, c = (idx % kRow) / kStates, i = idx % kStates;
-        double acc;
-        if (code < 20) acc = s_P[c][i][code];
-        else if (code == 20) acc = s_P[c][i][2] + s_P[c][i][3];
-        else if (code == 21) acc = s_P[c][i][5] + s_P[c][i][6];
-        else {
-            acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < kStates; ++j) acc += s_P[c][i][j];
-        }
-        blocks[b].tip[code][c * kStates + i] = acc;
     }
 }
 
@@ -172,15 +121,6 @@ __global__ void __launch_bounds__(256) k_replicate_lnl(const int32_t* __restrict
 inline int blocks_for(int64_t np) { return (int)((np + kPatternsPerBlock - 1) / kPatternsPerBlock); }
 
 }  // namespace
-
-void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t* d_want_tip, PBlock* d_blocks, int nblocks,
-                   cudaStream_t stream) {
-    if (nblocks > 0) k_make_p<<<nblocks, 256, 0, stream>>>(dm, d_lengths, d_want_tip, d_blocks);
-}
-
-void launch_make_p_inline(const DeviceModel* dm, const MakePInline& batch, PBlock* d_blocks, int nblocks, cudaStream_t stream) {
-    if (nblocks > 0) k_make_p_inline<<<nblocks, 256, 0, stream>>>(dm, batch, d_blocks);
-}
 
 void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np,
                  double t, double* partials, double* result, cudaStream_t stream) {

@@ -1,6 +1,6 @@
 // Device-side interface of the engine: every function enqueues work on `stream` and returns immediately.
-// One "PBlock" per (traversal entry, child) carries the four 20x20 transition matrices of that branch and, for tip
-// children, the 23 x 80 lookup of P applied to each residue code's indicator vector.
+// The transition matrices P(t) are built inside the CLV kernels (pmatrix.cuh) from the eigensystem below and the branch
+// lengths in the tree's device array.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -9,11 +9,6 @@
 #include "model.h"
 
 namespace pml {
-
-struct PBlock {
-    double P[kCats][kStates][kStates];  // P_c(i->j)
-    double tip[kCodes][kRow];           // tip[code][c*20+i] = sum_j P_c[i][j] * indicator(code)[j]
-};
 
 // model constants in device memory, one copy per alignment (eigenvalues, V, Vinv, pi, rates)
 struct DeviceModel {
@@ -34,22 +29,13 @@ struct Side {
 
 struct NewviewOp {
     Side left, right;
-    const PBlock* pleft;
-    const PBlock* pright;
+    const double* len_left;   // the two branch lengths, read on the device (tree's length array)
+    const double* len_right;
+    const DeviceModel* dm;
     double* out;
     int32_t* out_scale;
     long long* trace;  // optional (profiling aid): per warp of CTA 0, cycles spent in each phase of the pipeline
 };
-
-// P(t) for `nblocks` branches: lengths[b] in expected substitutions per site; tips[b] != 0 also fills PBlock::tip
-// small batches travel as kernel arguments (no staging copy): up to kMakePInline branches
-constexpr int kMakePInline = 32;
-struct MakePInline {
-    double length[kMakePInline];
-    uint8_t want_tip[kMakePInline];
-};
-void launch_make_p_inline(const DeviceModel* dm, const MakePInline& batch, PBlock* d_blocks, int nblocks, cudaStream_t stream);
-void launch_make_p(const DeviceModel* dm, const double* d_lengths, const uint8_t* d_want_tip, PBlock* d_blocks, int nblocks, cudaStream_t stream);
 
 // CLV update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 64 and all buffers hold np rows
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream);

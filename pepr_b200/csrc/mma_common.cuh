@@ -97,13 +97,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // state index that lane t feeds into k-tile kt: pairs of k-tiles share one 128-bit shared-memory load
 __device__ __forceinline__ int kmap(int kt, int t) { return kt < 4 ? (kt >> 1) * 8 + 2 * t + (kt & 1) : 16 + t; }
 
-// B fragments of P_c^T for one child: frag[nt][kt] = P_c[nt*8 + g][kmap(kt, t)] (0 beyond state 19)
-__device__ __forceinline__ void load_p_fragments(const PBlock* pb, int c, int g, int t, double (&frag)[3][5]) {
+// B fragments of P_c^T for one child from P_c[i][j] (row-major 20 x 20, shared memory):
+// frag[nt][kt] = P_c[nt*8 + g][kmap(kt, t)] (0 beyond state 19)
+__device__ __forceinline__ void load_p_fragments(const double* Pc, int g, int t, double (&frag)[3][5]) {
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
         const int i = nt * 8 + g;
 #pragma unroll
-        for (int kt = 0; kt < 5; ++kt) frag[nt][kt] = i < kStates ? pb->P[c][i][kmap(kt, t)] : 0.0;
+        for (int kt = 0; kt < 5; ++kt) frag[nt][kt] = i < kStates ? Pc[i * kStates + kmap(kt, t)] : 0.0;
     }
 }
 

@@ -15,6 +15,7 @@
 
 #include "kernels.h"
 #include "mma_common.cuh"
+#include "pmatrix.cuh"
 
 namespace pml {
 
@@ -48,8 +49,10 @@ __device__ __forceinline__ void lookup_rows(const double* table, int code, int c
 //               write the scaling counts.
 //   warp 10     producer: refills the stages with one bulk copy per inner child as soon as a stage has been consumed.
 // Everything an MMA warp does besides its 60 DMMAs is ~70 instructions, so the pipe stays busy; stores cost no LSU work.
-constexpr int kThreadsNewview = 384;   // warp 11 idles: 12 warps keep the register budget at 168
+constexpr int kThreadsNewview = 384;   // warp 11 only helps with the P matrices: 12 warps keep the register budget at 168
 constexpr int kProdSlots = 4;
+constexpr int kStagers = kThreadsNewview - 32;  // every warp but the producer takes part in the prologue
+constexpr int kStageBarrier = 2;
 
 template <bool kTipL, bool kTipR>
 struct SmemPlan {
@@ -61,7 +64,9 @@ struct SmemPlan {
     static constexpr int kTipDoubles = kCodes * kTipPad;             // exactly one child is a tip in the mixed case
     static constexpr int kMaxInts = kProdSlots * kCats * kTileRows;  // [slot][cat][row]
     static constexpr size_t kBarBytes = 256;
-    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(kInner == 2 ? 0 : kTipDoubles) + sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
+    static_assert(kProdSlots * kTileDoubles >= pmat::kPDoubles, "the product slots double as the staging area of the P matrices");
+    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(pmat::kModelDoubles + (kInner == 2 ? 0 : kTipDoubles)) +
+                                     sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
                                      sizeof(double) * (size_t)(kProdSlots * kTileDoubles + kMmaGroups * kDepth * kStageDoubles);
 };
 
@@ -75,14 +80,20 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     uint64_t* in_empty = in_full + kMmaGroups * kDepth;            // [group][kDepth]
     uint64_t* prod_full = in_empty + kMmaGroups * kDepth;          // [kProdSlots]
     uint64_t* prod_empty = prod_full + kProdSlots;                 // [kProdSlots]
-    double* s_tip = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);
+    double* s_model = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);
+    double* s_tip = s_model + pmat::kModelDoubles;
     int* s_max = reinterpret_cast<int*>(s_tip + (kMixed ? Plan::kTipDoubles : 0));
     int* s_sc = s_max + Plan::kMaxInts;                            // [kProdSlots][16] summed scaling counts of the children
     double* s_prod = reinterpret_cast<double*>(s_sc + kProdSlots * kTileRows);
     double* s_stage = s_prod + kProdSlots * kTileDoubles;
+    double* s_P = s_prod;                                          // prologue only: P[child][c][i][j]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_entry = op.trace ? clock64() : 0;
+    // model constants and branch lengths are requested before the producer queues the first tiles (see branch_mma.cu)
+    const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
+    pmat::ModelRegs regs{};
+    if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, op.len_left, op.len_right, stid);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMmaGroups * kDepth; ++i) {
             mbar_init(in_full + i, 1);
@@ -94,10 +105,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (kMixed) {
-        const double* src = kTipL ? &op.pleft->tip[0][0] : &op.pright->tip[0][0];
-        for (int i = threadIdx.x; i < kCodes * kRow; i += kThreadsNewview) s_tip[(i / kRow) * kTipPad + i % kRow] = src[i];
-    }
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
@@ -105,32 +112,48 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
 
     if (warp == kProducerWarp) {
         // ---------------------------------------------------------------------------------------------- producer
-        if (lane == 0) {
-            constexpr uint32_t bytes = kTileDoubles * sizeof(double);
-            for (int n = 0; n < cta_tiles; ++n) {
-                const int grp = n % kMmaGroups, j = n / kMmaGroups, slot = j % kDepth;
-                uint64_t* full = in_full + grp * kDepth + slot;
+        // lane 0 waits for the stage and announces the bytes, then lanes 0-3 hand one bulk copy each to the TMA engine
+        constexpr uint32_t bytes = kTileDoubles * sizeof(double), sc_bytes = kTileRows * sizeof(int32_t);
+        for (int n = 0; n < cta_tiles; ++n) {
+            const int grp = n % kMmaGroups, j = n / kMmaGroups, slot = j % kDepth;
+            uint64_t* full = in_full + grp * kDepth + slot;
+            if (lane == 0) {
                 mbar_wait(in_empty + grp * kDepth + slot, ((j / kDepth) & 1) ^ 1);
-                constexpr uint32_t sc_bytes = kTileRows * sizeof(int32_t);
                 mbar_expect_tx(full, Plan::kInner * (bytes + sc_bytes) + (kMixed ? kTileRows : 0));
-                const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
-                const size_t goff = tile * kTileDoubles;
-                double* dst = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
-                unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
-                if (!kTipL) {
-                    bulk_g2s(dst, op.left.clv + goff, bytes, full);
-                    bulk_g2s(aux, op.left.scale + tile * kTileRows, sc_bytes, full);
-                    dst += kTileDoubles;
-                }
-                if (!kTipR) {
-                    bulk_g2s(dst, op.right.clv + goff, bytes, full);
-                    bulk_g2s(aux + (kTipL ? 0 : sc_bytes), op.right.scale + tile * kTileRows, sc_bytes, full);
-                }
-                if (kMixed) bulk_g2s(aux + 128, (kTipL ? op.left.codes : op.right.codes) + tile * kTileRows, kTileRows, full);
+            }
+            __syncwarp();
+            const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
+            const size_t goff = tile * kTileDoubles;
+            double* dst = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
+            unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
+            if (lane == 0) {
+                if (!kTipL) bulk_g2s(dst, op.left.clv + goff, bytes, full);
+                else bulk_g2s(dst, op.right.clv + goff, bytes, full);
+            } else if (lane == 1) {
+                if (!kMixed) bulk_g2s(dst + kTileDoubles, op.right.clv + goff, bytes, full);
+                else bulk_g2s(aux + 128, (kTipL ? op.left.codes : op.right.codes) + tile * kTileRows, kTileRows, full);
+            } else if (lane == 2) {
+                bulk_g2s(aux, (kTipL ? op.right.scale : op.left.scale) + tile * kTileRows, sc_bytes, full);
+            } else if (lane == 3 && !kMixed) {
+                bulk_g2s(aux + sc_bytes, op.right.scale + tile * kTileRows, sc_bytes, full);
             }
         }
         return;
     }
+
+    // every other warp: P matrices of both branches in shared memory (product slots, free until the first tile is done)
+    pmat::model_to_smem<kStagers>(regs, stid, s_model);
+    named_barrier(kStageBarrier, kStagers);
+    pmat::build_p<kStagers>(s_model, stid, s_P);
+    named_barrier(kStageBarrier, kStagers);
+    if (kMixed) pmat::build_tip_lookup<kStagers>(s_P + (kTipL ? 0 : kCats * pmat::kMat), stid, s_tip, kTipPad);
+    double fragL[3][5], fragR[3][5];
+    if (warp < kMmaWarps) {
+        const int c = warp & 3, g = lane >> 2, t = lane & 3;
+        if (!kTipL) load_p_fragments(s_P + c * pmat::kMat, g, t, fragL);
+        if (!kTipR) load_p_fragments(s_P + (kCats + c) * pmat::kMat, g, t, fragR);
+    }
+    named_barrier(kStageBarrier, kStagers);
     if (warp > kProducerWarp) return;
 
     if (warp >= kMmaWarps) {
@@ -199,9 +222,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
 
     // -------------------------------------------------------------------------------------------------- MMA warps
     const int c = warp & 3, grp = warp >> 2, g = lane >> 2, t = lane & 3;
-    double fragL[3][5], fragR[3][5];
-    if (!kTipL) load_p_fragments(op.pleft, c, g, t, fragL);
-    if (!kTipR) load_p_fragments(op.pright, c, g, t, fragR);
     const int rounds = (cta_tiles + kMmaGroups - 1) / kMmaGroups;
     if (op.trace && blockIdx.x == 0 && lane == 0) op.trace[warp * 8 + 7] += clock64() - t_entry;  // prologue
     mma_turn_init(grp);
@@ -306,34 +326,43 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
 
 // ---------------------------------------------------------------------------------------------- tip-tip -----
 // Both children are tips: the row is the product of two lookup rows, so the whole update is a gather + 640 B write.
-// Whether a (code, code) pair needs the x2^256 rescale is decided once per CTA for all 529 pairs; the streaming loop
-// then has no cross-thread traffic and its stores are fully coalesced (consecutive threads, consecutive 16 B).
-constexpr int kTipTipThreads = 256;
-constexpr int kTipTipRows = 128;  // one CTA per 128-row tile; many small CTAs per SM hide the code-load latency
-__global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op) {
-    __shared__ __align__(16) double s_l[kCodes * kTipPad];  // rows padded: the 8 rows a warp gathers from hit different banks
-    __shared__ __align__(16) double s_r[kCodes * kTipPad];
-    __shared__ double s_maxl[kCodes], s_maxr[kCodes];
-    __shared__ int s_argl[kCodes];
-    __shared__ uint8_t s_flag[kCodes * kCodes];
-    __shared__ uint8_t s_pair[kTipTipRows][2];
-    const int64_t row0 = (int64_t)blockIdx.x * kTipTipRows;
-    // the residue codes of the tile are requested first; the table set-up below hides their latency
+// Persistent CTAs (one per SM): each builds the two P matrices and lookups once, decides once for all 529 (code, code)
+// pairs whether the x2^256 rescale applies, and then streams 128-row chunks with fully coalesced 16-byte stores.
+constexpr int kTipTipThreads = 512;
+constexpr int kTipTipRows = 128;
+struct TipTipSmem {
+    double model[pmat::kModelDoubles];
+    double P[pmat::kPDoubles];
+    double l[kCodes * kTipPad];  // rows padded: the 8 rows a warp gathers from hit different banks
+    double r[kCodes * kTipPad];
+    double maxl[kCodes], maxr[kCodes];
+    int argl[kCodes];
+    uint8_t flag[kCodes * kCodes];
+    uint8_t pair[2][kTipTipRows][2];
+};
+__global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp op, int nchunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TipTipSmem& sm = *reinterpret_cast<TipTipSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const pmat::ModelRegs regs = pmat::model_prefetch<kTipTipThreads>(op.dm, op.len_left, op.len_right, tid);
+    // the residue codes of the first chunk are requested right away; the table set-up below hides their latency
     uint8_t my_l = 0, my_r = 0;
-    if (threadIdx.x < kTipTipRows) {
-        my_l = __ldg(op.left.codes + row0 + threadIdx.x);
-        my_r = __ldg(op.right.codes + row0 + threadIdx.x);
+    if (tid < kTipTipRows && (int)blockIdx.x < nchunks) {
+        my_l = __ldg(op.left.codes + (int64_t)blockIdx.x * kTipTipRows + tid);
+        my_r = __ldg(op.right.codes + (int64_t)blockIdx.x * kTipTipRows + tid);
     }
-    for (int i = threadIdx.x; i < kCodes * kRow; i += kTipTipThreads) {
-        s_l[(i / kRow) * kTipPad + i % kRow] = (&op.pleft->tip[0][0])[i];
-        s_r[(i / kRow) * kTipPad + i % kRow] = (&op.pright->tip[0][0])[i];
-    }
+    pmat::model_to_smem<kTipTipThreads>(regs, tid, sm.model);
+    __syncthreads();
+    pmat::build_p<kTipTipThreads>(sm.model, tid, sm.P);
+    __syncthreads();
+    pmat::build_tip_lookup<kTipTipThreads>(sm.P, tid, sm.l, kTipPad);
+    pmat::build_tip_lookup<kTipTipThreads>(sm.P + kCats * pmat::kMat, tid, sm.r, kTipPad);
     __syncthreads();
     // row maxima of both lookups bound every product: max_l * max_r from above, l[arg] * r[arg] from below
-    for (int rowid = threadIdx.x >> 5; rowid < 2 * kCodes; rowid += kTipTipThreads / 32) {  // one warp per lookup row
+    for (int rowid = tid >> 5; rowid < 2 * kCodes; rowid += kTipTipThreads / 32) {  // one warp per lookup row
         const bool right = rowid >= kCodes;
-        const int code = rowid - (right ? kCodes : 0), lane = threadIdx.x & 31;
-        const double* row = (right ? s_r : s_l) + code * kTipPad;
+        const int code = rowid - (right ? kCodes : 0), lane = tid & 31;
+        const double* row = (right ? sm.r : sm.l) + code * kTipPad;
         double big = -1.0;
         int arg = 0;
         for (int k = lane; k < kRow; k += 32)
@@ -351,59 +380,70 @@ __global__ void __launch_bounds__(kTipTipThreads) k_newview_tiptip(NewviewOp op)
             }
         }
         if (lane == 0) {
-            if (right) s_maxr[code] = big;
+            if (right) sm.maxr[code] = big;
             else {
-                s_maxl[code] = big;
-                s_argl[code] = arg;
+                sm.maxl[code] = big;
+                sm.argl[code] = arg;
             }
         }
     }
     __syncthreads();
-    for (int pair = threadIdx.x; pair < kCodes * kCodes; pair += kTipTipThreads) {
+    for (int pair = tid; pair < kCodes * kCodes; pair += kTipTipThreads) {
         const int cl = pair / kCodes, cr = pair % kCodes;
-        const double* a = s_l + cl * kTipPad;
-        const double* b = s_r + cr * kTipPad;
+        const double* a = sm.l + cl * kTipPad;
+        const double* b = sm.r + cr * kTipPad;
         uint8_t flag;
-        if (s_maxl[cl] * s_maxr[cr] < kMinLik) flag = 1;                               // every product is below 2^-256
-        else if (fabs(a[s_argl[cl]] * b[s_argl[cl]]) >= kMinLik) flag = 0;            // one product is certainly not
-        else {                                                                         // undecided: test all 80
+        if (sm.maxl[cl] * sm.maxr[cr] < kMinLik) flag = 1;                               // every product is below 2^-256
+        else if (fabs(a[sm.argl[cl]] * b[sm.argl[cl]]) >= kMinLik) flag = 0;            // one product is certainly not
+        else {                                                                           // undecided: test all 80
             double big = 0.0;
             for (int i = 0; i < kRow; ++i) big = fmax(big, fabs(a[i] * b[i]));
             flag = big < kMinLik ? 1 : 0;
         }
-        s_flag[pair] = flag;
+        sm.flag[pair] = flag;
     }
-    if (threadIdx.x < kTipTipRows) {
-        s_pair[threadIdx.x][0] = my_l;
-        s_pair[threadIdx.x][1] = my_r;
-    }
-    __syncthreads();
-    double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
+    int buf = 0;
+    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, buf ^= 1) {
+        const int64_t row0 = (int64_t)chunk * kTipTipRows;
+        if (tid < kTipTipRows) {
+            sm.pair[buf][tid][0] = my_l;
+            sm.pair[buf][tid][1] = my_r;
+        }
+        __syncthreads();  // also covers sm.flag on the first trip; the other pair buffer is free for the next trip
+        if (tid < kTipTipRows) {
+            op.out_scale[row0 + tid] = sm.flag[my_l * kCodes + my_r];
+            const int next = chunk + gridDim.x;
+            if (next < nchunks) {  // the codes of the following chunk travel while this one is written
+                my_l = __ldg(op.left.codes + (int64_t)next * kTipTipRows + tid);
+                my_r = __ldg(op.right.codes + (int64_t)next * kTipTipRows + tid);
+            }
+        }
+        double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
 #pragma unroll 4
-    for (int q = threadIdx.x; q < kTipTipRows * (kRow / 2); q += kTipTipThreads) {
-        // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
-        const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
-        const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
-        int g, st;
-        if (u < 64) {
-            g = (u & 31) >> 2;
-            st = (u >> 5) * 8 + (u & 3) * 2;
-        } else {
-            g = (u - 64) >> 1;
-            st = 16 + ((u - 64) & 1) * 2;
+        for (int q = tid; q < kTipTipRows * (kRow / 2); q += kTipTipThreads) {
+            // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
+            const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
+            const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
+            int g, st;
+            if (u < 64) {
+                g = (u & 31) >> 2;
+                st = (u >> 5) * 8 + (u & 3) * 2;
+            } else {
+                g = (u - 64) >> 1;
+                st = 16 + ((u - 64) & 1) * 2;
+            }
+            const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
+            const int cl = sm.pair[buf][r][0], cr = sm.pair[buf][r][1];
+            const double2 a = reinterpret_cast<const double2*>(sm.l + cl * kTipPad)[k];
+            const double2 b = reinterpret_cast<const double2*>(sm.r + cr * kTipPad)[k];
+            double2 v = make_double2(a.x * b.x, a.y * b.y);
+            if (sm.flag[cl * kCodes + cr]) {
+                v.x *= kTwo256;
+                v.y *= kTwo256;
+            }
+            out[q] = v;
         }
-        const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
-        const int cl = s_pair[r][0], cr = s_pair[r][1];
-        const double2 a = reinterpret_cast<const double2*>(s_l + cl * kTipPad)[k];
-        const double2 b = reinterpret_cast<const double2*>(s_r + cr * kTipPad)[k];
-        double2 v = make_double2(a.x * b.x, a.y * b.y);
-        if (s_flag[cl * kCodes + cr]) {
-            v.x *= kTwo256;
-            v.y *= kTwo256;
-        }
-        out[q] = v;
     }
-    if (threadIdx.x < kTipTipRows) op.out_scale[row0 + threadIdx.x] = s_flag[my_l * kCodes + my_r];
 }
 
 template <bool kTipL, bool kTipR>
@@ -420,13 +460,15 @@ void configure_mma_kernels() {
     cudaFuncSetAttribute(k_newview_mma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<true, false>::kBytes);
     cudaFuncSetAttribute(k_newview_mma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<false, true>::kBytes);
     cudaFuncSetAttribute(k_newview_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<false, false>::kBytes);
+    cudaFuncSetAttribute(k_newview_tiptip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TipTipSmem));
 }
 
 // np must be a multiple of 128 (the engine pads pattern rows to 128)
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
     const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr;
     if (tl && tr) {
-        k_newview_tiptip<<<(int)(np / kTipTipRows), kTipTipThreads, 0, stream>>>(op);
+        const int nchunks = (int)(np / kTipTipRows);
+        k_newview_tiptip<<<nchunks < sms ? nchunks : sms, kTipTipThreads, sizeof(TipTipSmem), stream>>>(op, nchunks);
     } else if (tl) launch_one<true, false>(op, np, sms, stream);
     else if (tr) launch_one<false, true>(op, np, sms, stream);
     else launch_one<false, false>(op, np, sms, stream);
