@@ -253,7 +253,6 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ctx.profile_begin()
     ctx.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -262,9 +261,17 @@ def main():
     ms = ctx.timer_stop()
     barrier()
     wall = time.perf_counter() - t0
+    su1, ln1 = counts()
+    # the same K steps once more with a pair of CUDA events around EVERY launch (per-kernel times for the roofline); kept
+    # out of the region above because an event between two kernels forbids their programmatic overlap
+    ctx.profile_begin()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        reset()
+        tree.optimize(True, 0.1)
+    ms_profiled = ctx.timer_stop()
     prof = ctx.profile_end()
     clocks = sampler.stop() if rank == 0 else None
-    su1, ln1 = counts()
     ms_all = torch.tensor([ms], dtype=torch.float64, device="cuda")
     su_all = torch.tensor([float(su1 - su0)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -371,6 +378,7 @@ def main():
             "likelihood_pass": {"value": pass_value, "unit": UNIT, "ms": pass_all.item()},
             "kernels": kernels,
             "wall_s_timed_region": wall,
+            "ms_per_step_with_per_launch_events": ms_profiled / args.steps,
             "site_updates_per_pattern": (su1 - su0) / args.steps / max(npat_local, 1),
         }
         if boot:

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     constexpr int kStagers = kProducerWarp * 32;  // every warp but the producer
     const int tid = threadIdx.x;
     double pre_vinv[2] = {0.0, 0.0}, pre_piv[2] = {0.0, 0.0}, pre_lambda = 0.0, pre_rate = 0.0;
+    pdl_launch_dependents();
     if (warp != kProducerWarp) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -93,8 +94,6 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             pre_rate = dm->rates[tid / 24];
         }
     }
-    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
-    const double tt = args.t_ptr ? nr_clamp_length(*args.t_ptr) : args.t;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMmaGroups * kBranchDepth; ++i) {
             mbar_init(in_full + i, 1);
@@ -106,6 +105,9 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // from here on the kernel touches what its predecessors wrote (see mma_common.cuh)
+    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
+    const double tt = args.t_ptr ? nr_clamp_length(*args.t_ptr) : args.t;
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, row-sum slot n % 4
@@ -434,7 +436,7 @@ template <bool kTipA, bool kStore>
 void launch_one(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    k_branch_mma<kTipA, kStore><<<grid, kThreadsBranch, BranchPlan<kTipA>::kBytes, stream>>>(args, ntiles);
+    launch_pdl(k_branch_mma<kTipA, kStore>, grid, kThreadsBranch, BranchPlan<kTipA>::kBytes, stream, args, ntiles);
 }
 
 }  // namespace

@@ -71,6 +71,29 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_barrier_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// Programmatic dependent launch: the streaming kernels are launched with programmatic stream serialisation, so a kernel's
+// CTAs may start (barrier set-up, loads of the static model constants) while the previous kernel on the stream is still
+// draining; pdl_wait() returns once that kernel has completed and its writes are visible.  Every kernel triggers its own
+// dependents right away -- they cannot take an SM before this grid's CTA there has exited (shared memory), so the trigger
+// only removes the launch latency between two dependent kernels.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename Kernel, typename... Args>
+inline void launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // MMA turn-taking between the two groups of a CTA.  The FP64 tensor pipe is one unit per SM (4 clk per DMMA.8x8x4) and ONE
 // group -- four warps, one per SM sub-partition, each issuing a DMMA every 16 clk -- already saturates it.  Left to the
 // round-robin warp scheduler all MMA warps crawl through their bursts together and then do their other work together,

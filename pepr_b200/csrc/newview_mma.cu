@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     // model constants and branch lengths are requested before the producer queues the first tiles (see branch_mma.cu)
     const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
     pmat::ModelRegs regs{};
-    if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, op.len_left, op.len_right, stid);
+    pdl_launch_dependents();
+    if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, stid);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMmaGroups * kDepth; ++i) {
             mbar_init(in_full + i, 1);
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
+    if (warp != kProducerWarp) pmat::length_prefetch(regs, op.len_left, op.len_right);
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
@@ -344,7 +347,10 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TipTipSmem& sm = *reinterpret_cast<TipTipSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const pmat::ModelRegs regs = pmat::model_prefetch<kTipTipThreads>(op.dm, op.len_left, op.len_right, tid);
+    pdl_launch_dependents();
+    pmat::ModelRegs regs = pmat::model_prefetch<kTipTipThreads>(op.dm, tid);
+    pdl_wait();
+    pmat::length_prefetch(regs, op.len_left, op.len_right);
     // the residue codes of the first chunk are requested right away; the table set-up below hides their latency
     uint8_t my_l = 0, my_r = 0;
     if (tid < kTipTipRows && (int)blockIdx.x < nchunks) {
@@ -451,7 +457,7 @@ void launch_one(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
     using Plan = SmemPlan<kTipL, kTipR>;
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    k_newview_mma<kTipL, kTipR><<<grid, kThreadsNewview, Plan::kBytes, stream>>>(op, ntiles);
+    launch_pdl(k_newview_mma<kTipL, kTipR>, grid, kThreadsNewview, Plan::kBytes, stream, op, ntiles);
 }
 
 }  // namespace
@@ -468,7 +474,7 @@ void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t s
     const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr;
     if (tl && tr) {
         const int nchunks = (int)(np / kTipTipRows);
-        k_newview_tiptip<<<nchunks < sms ? nchunks : sms, kTipTipThreads, sizeof(TipTipSmem), stream>>>(op, nchunks);
+        launch_pdl(k_newview_tiptip, nchunks < sms ? nchunks : sms, kTipTipThreads, sizeof(TipTipSmem), stream, op, nchunks);
     } else if (tl) launch_one<true, false>(op, np, sms, stream);
     else if (tr) launch_one<false, true>(op, np, sms, stream);
     else launch_one<false, false>(op, np, sms, stream);

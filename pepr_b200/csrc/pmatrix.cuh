@@ -6,6 +6,7 @@
 //
 // Usage (all threads of the CTA that take part, `nthreads` of them with ranks `tid` = 0 .. nthreads-1):
 //   ModelRegs r = model_prefetch(...)      -- global loads issued; do this BEFORE the CTA queues its bulk loads
+//   pdl_wait(); length_prefetch(r, ...)    -- the branch lengths may have been written by the preceding kernel
 //   model_to_smem(...);  barrier           -- V, Vinv, exp tables in shared memory
 //   build_p(...);        barrier           -- s_P[child][c][i][j]
 //   build_tip_lookup(...) / load_p_fragments_smem(...)
@@ -27,8 +28,9 @@ struct ModelRegs {
     double len[2];
 };
 
+// static part: nothing a preceding kernel may have written (safe before pdl_wait)
 template <int kThreads>
-__device__ __forceinline__ ModelRegs model_prefetch(const DeviceModel* dm, const double* len_l, const double* len_r, int tid) {
+__device__ __forceinline__ ModelRegs model_prefetch(const DeviceModel* dm, int tid) {
     static_assert(2 * kThreads >= kMat, "two rounds must cover a 20 x 20 matrix");
     ModelRegs r{};
 #pragma unroll
@@ -43,9 +45,11 @@ __device__ __forceinline__ ModelRegs model_prefetch(const DeviceModel* dm, const
         r.lambda = dm->lambda[tid % kStates];
         r.rate = dm->rates[(tid % kRow) / kStates];
     }
+    return r;
+}
+__device__ __forceinline__ void length_prefetch(ModelRegs& r, const double* len_l, const double* len_r) {
     r.len[0] = *len_l;
     r.len[1] = *len_r;
-    return r;
 }
 
 // s_model: [V 400][Vinv 400][exp child 0: 80][exp child 1: 80]
