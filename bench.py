@@ -366,6 +366,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "synthetic 100 taxa x 100k sites/GPU WAG+G4 (seed 3): -f e (alpha + branch lengths, fixed topology)",
                        "taxa": NTAX, "sites_per_gpu": sites, "patterns": npat, "partition": "sites (pattern blocks)",
+                       "collective": ctx.collective,
                        "cache": "CLV working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)" % ((NTAX - 2) * npat_local * 640 / 1e9),
                        "final_lnl": lnl, "final_alpha": alpha},
             "clocks": clocks,

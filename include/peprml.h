@@ -48,6 +48,9 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char *unique
 void pml_ctx_destroy(pml_ctx *);
 const char *pml_last_error(const pml_ctx *); /* ctx may be NULL: last creation error of this thread */
 int pml_ctx_sync(pml_ctx *);
+/* how the 1-3 doubles of a branch pass are summed over the ranks: 0 = single rank, 1 = NCCL allreduce on the stream,
+ * 2 = inside the branch kernel over NVLink peer memory (CUDA IPC mailboxes; the default whenever peers can be mapped) */
+int pml_ctx_collective(const pml_ctx *);
 
 /* ---- alignment -------------------------------------------------------------------------------------------
  * Replaces the phylip hand-off SequenceAlignment.getAlignmentAsExtendedPhylipUsingTaxonNames -> `-s file`

@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
                     print(" ".join(cmd))
                 subprocess.run(cmd, check=True)
             objs.append(o)
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

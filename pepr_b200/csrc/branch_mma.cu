@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
 #pragma unroll
             for (int v = 0; v < 3; ++v) r3[v] += __shfl_xor_sync(0xffffffffu, r3[v], o);
         }
+        if (args.peer.mail) peer_allreduce3(args.peer, args.pub.seq, r3);
         if (lane == 0) {
             args.result[0] = r3[0];
             args.result[1] = r3[1];

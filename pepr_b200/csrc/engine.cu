@@ -74,6 +74,11 @@ struct pml_ctx {
     double* d_mapped = nullptr;
     double sequence = 0.0;
     int* d_poison = nullptr;  // see Publish in kernels.h
+    // in-kernel reduction over NVLink peer memory (see PeerReduce in kernels.h); falls back to NCCL when IPC is unavailable
+    double* d_mail = nullptr;
+    double** d_mail_ptrs = nullptr;
+    std::vector<void*> peer_opened;
+    bool peer_ok = false;
     volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     double* slot_dev(double seq) const { return d_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     // waits until the pass with this sequence number has published; out = {lnL, d1, d2, length, status}
@@ -374,14 +379,16 @@ double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool kee
         pub.len = t->d_len + e;
         pub.poison = c->d_poison;
     }
-    if (c->nranks == 1) args.pub = pub;
+    const bool in_kernel = c->nranks == 1 || c->peer_ok;
+    if (in_kernel) args.pub = pub;
+    if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks};
     const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
     launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
     if (!c->cuda(cudaGetLastError(), "branch kernel")) return 0.0;
-    if (c->nranks > 1) {
+    if (!in_kernel) {
         if (!c->allreduce(a->d_result, 3)) return 0.0;
         launch_publish(a->d_result, pub, c->stream);
         t->launches += 1;
@@ -716,6 +723,65 @@ int fail(pml_ctx* c, int code, const std::string& msg) {
     return code;
 }
 
+// Opens every rank's mailbox in every other rank (CUDA IPC over NVLink).  The 64-byte handles are gathered with the NCCL
+// communicator that already exists (sum of zero-padded int32 arrays = gather).  Any failure leaves peer_ok = false and the
+// engine on the NCCL path; set PEPRML_NO_PEER=1 to force that path.
+void setup_peer_mail(pml_ctx* c) {
+    if (c->nranks < 2 || c->nranks > kMaxPeers || getenv("PEPRML_NO_PEER")) return;
+    const size_t bytes = sizeof(double) * kPeerRing * c->nranks * 6;
+    constexpr int kWords = (int)(sizeof(cudaIpcMemHandle_t) / sizeof(int32_t));
+    int32_t* d_gather = nullptr;
+    std::vector<int32_t> h((size_t)kWords * c->nranks + c->nranks, 0);
+    cudaIpcMemHandle_t mine;
+    bool ok = cudaMalloc(&c->d_mail, bytes) == cudaSuccess && cudaMemset(c->d_mail, 0, bytes) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, c->d_mail) == cudaSuccess && cudaMalloc(&d_gather, sizeof(int32_t) * h.size()) == cudaSuccess;
+    // every rank must take part in the collectives below, whatever happened locally: a flag per rank travels with the handles
+    if (ok) {
+        std::memcpy(h.data() + (size_t)kWords * c->rank, &mine, sizeof mine);
+        h[(size_t)kWords * c->nranks + c->rank] = 1;
+    }
+    if (!d_gather && cudaMalloc(&d_gather, sizeof(int32_t) * h.size()) != cudaSuccess) {
+        cudaGetLastError();
+        return;  // cannot even take part; the other ranks will time out in NCCL -- as they would on any allocation failure
+    }
+    cudaMemcpy(d_gather, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice);
+    const bool gathered = g_nccl.AllReduce(d_gather, d_gather, h.size(), ncclInt32, ncclSum, c->comm, c->stream) == ncclSuccess &&
+                          cudaStreamSynchronize(c->stream) == cudaSuccess &&
+                          cudaMemcpy(h.data(), d_gather, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+    int good = 0;
+    for (int r = 0; r < c->nranks; ++r) good += h[(size_t)kWords * c->nranks + r];
+    std::vector<double*> ptrs(c->nranks, nullptr);
+    bool opened = gathered && good == c->nranks;
+    for (int r = 0; opened && r < c->nranks; ++r) {
+        if (r == c->rank) {
+            ptrs[r] = c->d_mail;
+            continue;
+        }
+        cudaIpcMemHandle_t hr;
+        std::memcpy(&hr, h.data() + (size_t)kWords * r, sizeof hr);
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            opened = false;
+            break;
+        }
+        c->peer_opened.push_back(p);
+        ptrs[r] = (double*)p;
+    }
+    if (opened)
+        opened = cudaMalloc(&c->d_mail_ptrs, sizeof(double*) * c->nranks) == cudaSuccess &&
+                 cudaMemcpy(c->d_mail_ptrs, ptrs.data(), sizeof(double*) * c->nranks, cudaMemcpyHostToDevice) == cudaSuccess;
+    // second round: the in-kernel path is used only if EVERY rank opened every mailbox (it doubles as the barrier that keeps
+    // a fast rank from writing into a mailbox that is still being cleared)
+    int32_t flag = opened ? 1 : 0;
+    cudaMemcpy(d_gather, &flag, sizeof flag, cudaMemcpyHostToDevice);
+    if (g_nccl.AllReduce(d_gather, d_gather, 1, ncclInt32, ncclSum, c->comm, c->stream) == ncclSuccess &&
+        cudaStreamSynchronize(c->stream) == cudaSuccess && cudaMemcpy(&flag, d_gather, sizeof flag, cudaMemcpyDeviceToHost) == cudaSuccess)
+        c->peer_ok = flag == c->nranks;
+    cudaFree(d_gather);
+    cudaGetLastError();
+}
+
 }  // namespace
 
 // =============================================================================================== C ABI ======
@@ -768,6 +834,7 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
         std::memcpy(&u, unique_id, sizeof u);
         ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
         if (r != ncclSuccess) return fail(nullptr, PML_ECOMM, "ncclCommInitRank failed");
+        setup_peer_mail(c.get());
     }
     *out = c.release();
     return PML_OK;
@@ -786,6 +853,9 @@ void pml_ctx_destroy(pml_ctx* c) {
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->h_mapped) cudaFreeHost((void*)c->h_mapped);
     if (c->d_poison) cudaFree(c->d_poison);
+    for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
+    if (c->d_mail_ptrs) cudaFree(c->d_mail_ptrs);
+    if (c->d_mail) cudaFree(c->d_mail);
     if (c->d_trace_buf) cudaFree(c->d_trace_buf);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
     for (auto e : c->spare_events) cudaEventDestroy(e);
@@ -793,6 +863,8 @@ void pml_ctx_destroy(pml_ctx* c) {
 }
 
 const char* pml_last_error(const pml_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int pml_ctx_collective(const pml_ctx* c) { return !c ? PML_EINVAL : (c->nranks == 1 ? 0 : (c->peer_ok ? 2 : 1)); }
 
 int pml_ctx_sync(pml_ctx* c) {
     if (!c) return PML_EINVAL;

@@ -1,6 +1,7 @@
 #include "host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,36 +10,135 @@
 #include <functional>
 #include <numeric>
 #include <sstream>
+#include <thread>
 
 #include "model.h"
 
 namespace pml {
 
 // =========================================================================================== alignment ======
+namespace {
+
+int crunch_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(8, std::max<unsigned>(1, hw));
+}
+
+// runs fn(i) for i = 0 .. n-1 on up to `threads` host threads (work stealing through an atomic counter)
+template <typename F>
+void parallel_for(int64_t n, int threads, F fn) {
+    if (threads <= 1 || n <= 1) {
+        for (int64_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    std::vector<std::thread> pool;
+    const int nt = (int)std::min<int64_t>(threads, n);
+    for (int k = 0; k < nt; ++k)
+        pool.emplace_back([&] {
+            for (int64_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
+// Lexicographic order of alignment columns by residue code in taxon order (ties: column index), as an MSD radix sort that
+// works on the caller's taxon-major letters directly: level t partitions a bucket by the codes of row t, and row t (one
+// byte per site) stays cache resident while it is gathered from.  Random protein columns separate after ~5 levels.
+struct ColumnSorter {
+    int ntax;
+    int64_t nsites;
+    const uint8_t* chars;
+    uint8_t lut[256];
+    int code(int t, int64_t s) const { return lut[chars[(size_t)t * nsites + s]]; }
+    // first taxon >= from at which the two columns differ (ntax if none)
+    int first_difference(int64_t a, int64_t b, int from) const {
+        for (int t = from; t < ntax; ++t)
+            if (code(t, a) != code(t, b)) return t;
+        return ntax;
+    }
+    bool less(int64_t a, int64_t b, int from) const {
+        const int t = first_difference(a, b, from);
+        return t < ntax ? code(t, a) < code(t, b) : a < b;
+    }
+    // sorts order[lo, hi), whose columns agree on taxa < level; tmp is scratch of the same extent
+    void sort_range(int64_t* order, int64_t* tmp, int64_t lo, int64_t hi, int level) const {
+        struct Job { int64_t lo, hi; int level; };
+        std::vector<Job> stack{{lo, hi, level}};
+        while (!stack.empty()) {
+            const Job j = stack.back();
+            stack.pop_back();
+            const int64_t n = j.hi - j.lo;
+            if (n <= 1 || j.level >= ntax) continue;  // identical columns keep their index order (every pass is stable)
+            if (n <= 24) {
+                for (int64_t i = j.lo + 1; i < j.hi; ++i) {
+                    const int64_t v = order[i];
+                    int64_t k = i;
+                    while (k > j.lo && less(v, order[k - 1], j.level)) {
+                        order[k] = order[k - 1];
+                        --k;
+                    }
+                    order[k] = v;
+                }
+                continue;
+            }
+            const uint8_t* row = chars + (size_t)j.level * nsites;
+            int64_t count[kCodes + 1] = {0};
+            for (int64_t i = j.lo; i < j.hi; ++i) ++count[lut[row[order[i]]] + 1];
+            int used = 0;
+            for (int c = 0; c < kCodes; ++c) used += count[c + 1] != 0;
+            if (used == 1) {  // nothing to move
+                stack.push_back({j.lo, j.hi, j.level + 1});
+                continue;
+            }
+            for (int c = 0; c < kCodes; ++c) count[c + 1] += count[c];
+            int64_t pos[kCodes];
+            for (int c = 0; c < kCodes; ++c) pos[c] = j.lo + count[c];
+            for (int64_t i = j.lo; i < j.hi; ++i) tmp[pos[lut[row[order[i]]]]++] = order[i];
+            std::memcpy(order + j.lo, tmp + j.lo, sizeof(int64_t) * (size_t)n);
+            for (int c = 0; c < kCodes; ++c)
+                if (count[c + 1] - count[c] > 1) stack.push_back({j.lo + count[c], j.lo + count[c + 1], j.level + 1});
+        }
+    }
+};
+
+}  // namespace
+
 void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out) {
     out.ntax = ntax;
     out.nsites = nsites;
-    // column-major copy of the residue codes so that one column is one contiguous key of ntax bytes
-    std::vector<uint8_t> cols((size_t)ntax * (size_t)nsites);
-    for (int t = 0; t < ntax; ++t) {
-        const uint8_t* row = chars + (size_t)t * nsites;
-        for (int64_t s = 0; s < nsites; ++s) cols[(size_t)s * ntax + t] = (uint8_t)residue_code(row[s]);
-    }
+    ColumnSorter cs{ntax, nsites, chars, {}};
+    for (int ch = 0; ch < 256; ++ch) cs.lut[ch] = (uint8_t)residue_code((unsigned char)ch);
+    const int threads = nsites >= 20000 ? crunch_threads() : 1;
     std::vector<int64_t> order;
     order.reserve(nsites);
     for (int64_t s = 0; s < nsites; ++s)
         if (!site_w || site_w[s] > 0) order.push_back(s);
-    const uint8_t* base = cols.data();
-    std::sort(order.begin(), order.end(), [base, ntax](int64_t a, int64_t b) {
-        const int c = std::memcmp(base + (size_t)a * ntax, base + (size_t)b * ntax, ntax);
-        return c != 0 ? c < 0 : a < b;
+    const int64_t n = (int64_t)order.size();
+    std::vector<int64_t> tmp(order.size());
+    {
+        // level 0 by hand, so that its (up to 23) buckets can be sorted by different threads
+        int64_t count[kCodes + 1] = {0};
+        for (int64_t i = 0; i < n; ++i) ++count[cs.lut[chars[order[i]]] + 1];
+        for (int c = 0; c < kCodes; ++c) count[c + 1] += count[c];
+        int64_t pos[kCodes];
+        for (int c = 0; c < kCodes; ++c) pos[c] = count[c];
+        for (int64_t i = 0; i < n; ++i) tmp[pos[cs.lut[chars[order[i]]]]++] = order[i];
+        order.swap(tmp);
+        parallel_for(kCodes, threads, [&](int64_t c) { cs.sort_range(order.data(), tmp.data(), count[c], count[c + 1], 1); });
+    }
+    // pattern boundaries: does sorted column k differ from its predecessor?
+    std::vector<uint8_t> fresh(order.size(), 1);
+    const int64_t chunk = 1 << 14;
+    parallel_for((n + chunk - 1) / chunk, threads, [&](int64_t b) {
+        for (int64_t k = std::max<int64_t>(1, b * chunk); k < std::min(n, (b + 1) * chunk); ++k)
+            fresh[k] = cs.first_difference(order[k], order[k - 1], 0) < ntax;
     });
     out.site_to_pat.assign(nsites, -1);
     std::vector<int64_t> first;  // representative column of each pattern
     out.weight.clear();
-    for (size_t k = 0; k < order.size(); ++k) {
+    for (int64_t k = 0; k < n; ++k) {
         const int64_t s = order[k];
-        if (k == 0 || std::memcmp(base + (size_t)s * ntax, base + (size_t)order[k - 1] * ntax, ntax) != 0) {
+        if (fresh[k]) {
             first.push_back(s);
             out.weight.push_back(0);
         }
@@ -47,8 +147,11 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
     }
     out.npat = (int64_t)first.size();
     out.codes.assign((size_t)ntax * out.npat, 22);
-    for (int64_t p = 0; p < out.npat; ++p)
-        for (int t = 0; t < ntax; ++t) out.codes[(size_t)t * out.npat + p] = cols[(size_t)first[p] * ntax + t];
+    parallel_for(ntax, threads, [&](int64_t t) {
+        const uint8_t* row = chars + (size_t)t * nsites;
+        uint8_t* dst = out.codes.data() + (size_t)t * out.npat;
+        for (int64_t p = 0; p < out.npat; ++p) dst[p] = cs.lut[row[first[p]]];
+    });
 }
 
 bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,

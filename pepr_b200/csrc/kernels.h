@@ -112,6 +112,55 @@ __device__ __forceinline__ void publish_result(const Publish& pub, const double 
     }
 }
 
+// Sum of the three doubles of a branch pass over the ranks of a site-sharded group, done INSIDE the branch kernel's tail over
+// NVLink peer memory instead of a separate NCCL launch (which costs ~20 us per branch visit in launch gaps and latency).
+// Every rank owns a mailbox [kPeerRing][nranks][3] of (value, seq) pairs that all peers can write: the last CTA stores this
+// rank's three sums into slot (seq mod kPeerRing, rank) of EVERY mailbox with 16-byte system-scope stores, then polls its own
+// mailbox until all nranks entries carry seq, and adds them in rank order -- identical bits on every rank.  Ranks run the
+// same passes in lock step and can be at most one pass apart, so a ring of 4 is never overwritten early.
+constexpr int kPeerRing = 4;
+constexpr int kMaxPeers = 16;
+struct PeerReduce {
+    double* const* mail;  // device array of nranks mailbox pointers (own included); nullptr: single rank or NCCL path
+    int rank, nranks;
+};
+__device__ __forceinline__ void st_pair_sys(double* p, double v, double seq) {
+    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
+}
+__device__ __forceinline__ double2 ld_pair_sys(const double* p) {
+    double2 r;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+// called by one full warp; r3 = this rank's sums in, the group's sums out (same in every lane)
+__device__ __forceinline__ void peer_allreduce3(const PeerReduce& pr, double seq, double r3[3]) {
+    const int lane = threadIdx.x & 31;
+    const size_t slot = (size_t)((long long)seq % kPeerRing) * pr.nranks;
+    if (lane < pr.nranks) {
+        double* dst = pr.mail[lane] + (slot + pr.rank) * 6;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) st_pair_sys(dst + 2 * v, r3[v], seq);
+    }
+    double mine[3] = {0.0, 0.0, 0.0};
+    if (lane < pr.nranks) {
+        const double* src = pr.mail[pr.rank] + (slot + lane) * 6;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            double2 x;
+            do x = ld_pair_sys(src + 2 * v);
+            while (x.y != seq);
+            mine[v] = x.x;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        double acc = 0.0;
+        for (int r = 0; r < pr.nranks; ++r) acc += __shfl_sync(0xffffffffu, mine[v], r);
+        r3[v] = acc;
+    }
+}
+
 // One pass over the two ends of a branch (b inner, a inner or tip): lnL, dlnL/dt, d2lnL/dt2 at the given length
 // (+ per-pattern lnL when site_lnl != nullptr, + the eigen-space product table when sumtable != nullptr).
 struct BranchArgs {
@@ -127,7 +176,8 @@ struct BranchArgs {
     double* partials;     // 3 x grid doubles
     unsigned int* ticket; // zero-initialised; the CTA drawing the last ticket adds the partials and resets it
     double* result;       // 4 doubles in device memory: lnL, d1, d2 of this rank's patterns (input of the allreduce), length used
-    Publish pub;          // single-rank contexts: the kernel itself publishes; otherwise launch_publish after the allreduce
+    Publish pub;          // the kernel itself publishes (single rank, or ranks joined by `peer`); otherwise launch_publish
+    PeerReduce peer;      // ranks > 1 with peer access: the sums are added over NVLink inside the kernel
     long long* trace;     // optional (profiling aid), as NewviewOp::trace
 };
 void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);

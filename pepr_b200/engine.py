@@ -34,6 +34,9 @@ def lib():
         L.pml_ctx_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
         L.pml_ctx_destroy.argtypes = [C.c_void_p]
         L.pml_ctx_sync.argtypes = [C.c_void_p]
+        L.pml_ctx_collective.argtypes = [C.c_void_p]
+        L.pml_trace_enable.argtypes = [C.c_void_p, C.c_int]
+        L.pml_trace_read.argtypes = [C.c_void_p, C.c_void_p]
         L.pml_aln_load.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_void_p)]
         L.pml_aln_load_phylip.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
@@ -111,6 +114,11 @@ class Context:
 
     def sync(self):
         self.check(lib().pml_ctx_sync(self.h), "pml_ctx_sync")
+
+    @property
+    def collective(self):
+        """how branch-pass sums cross the ranks: 'none' (one rank), 'nccl', or 'in-kernel nvlink' (peer mailboxes)"""
+        return ("none", "nccl", "in-kernel nvlink")[lib().pml_ctx_collective(self.h)]
 
     def timer_start(self):
         self.check(lib().pml_timer_start(self.h), "pml_timer_start")
