@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -60,15 +61,21 @@ struct ColumnSorter {
         const int t = first_difference(a, b, from);
         return t < ntax ? code(t, a) < code(t, b) : a < b;
     }
-    // sorts order[lo, hi), whose columns agree on taxa < level; tmp is scratch of the same extent
-    void sort_range(int64_t* order, int64_t* tmp, int64_t lo, int64_t hi, int level) const {
+    // sorts order[lo, hi), whose columns agree on taxa < level; tmp is scratch of the same extent.  fresh[k] (preset to 1)
+    // is cleared wherever sorted column k equals column k-1: such pairs end up together in a bucket that survived all levels
+    // or in a small bucket finished by insertion sort, so the pattern boundaries cost no extra pass over the alignment.
+    void sort_range(int64_t* order, int64_t* tmp, uint8_t* fresh, int64_t lo, int64_t hi, int level) const {
         struct Job { int64_t lo, hi; int level; };
         std::vector<Job> stack{{lo, hi, level}};
         while (!stack.empty()) {
             const Job j = stack.back();
             stack.pop_back();
             const int64_t n = j.hi - j.lo;
-            if (n <= 1 || j.level >= ntax) continue;  // identical columns keep their index order (every pass is stable)
+            if (n <= 1) continue;
+            if (j.level >= ntax) {  // identical columns keep their index order (every pass is stable)
+                for (int64_t k = j.lo + 1; k < j.hi; ++k) fresh[k] = 0;
+                continue;
+            }
             if (n <= 24) {
                 for (int64_t i = j.lo + 1; i < j.hi; ++i) {
                     const int64_t v = order[i];
@@ -79,6 +86,7 @@ struct ColumnSorter {
                     }
                     order[k] = v;
                 }
+                for (int64_t k = j.lo + 1; k < j.hi; ++k) fresh[k] = first_difference(order[k], order[k - 1], j.level) < ntax;
                 continue;
             }
             const uint8_t* row = chars + (size_t)j.level * nsites;
@@ -109,12 +117,24 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
     ColumnSorter cs{ntax, nsites, chars, {}};
     for (int ch = 0; ch < 256; ++ch) cs.lut[ch] = (uint8_t)residue_code((unsigned char)ch);
     const int threads = nsites >= 20000 ? crunch_threads() : 1;
+    const bool timing = getenv("PEPRML_CRUNCH_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](const char* what) {
+        if (timing) {
+            const double t1 = now();
+            fprintf(stderr, "crunch %-12s %.1f ms\n", what, t1 - t0);
+            t0 = t1;
+        }
+    };
     std::vector<int64_t> order;
     order.reserve(nsites);
     for (int64_t s = 0; s < nsites; ++s)
         if (!site_w || site_w[s] > 0) order.push_back(s);
     const int64_t n = (int64_t)order.size();
     std::vector<int64_t> tmp(order.size());
+    std::vector<uint8_t> fresh(order.size(), 1);
+    lap("setup");
     {
         // level 0 by hand, so that its (up to 23) buckets can be sorted by different threads
         int64_t count[kCodes + 1] = {0};
@@ -124,34 +144,61 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
         for (int c = 0; c < kCodes; ++c) pos[c] = count[c];
         for (int64_t i = 0; i < n; ++i) tmp[pos[cs.lut[chars[order[i]]]]++] = order[i];
         order.swap(tmp);
-        parallel_for(kCodes, threads, [&](int64_t c) { cs.sort_range(order.data(), tmp.data(), count[c], count[c + 1], 1); });
+        lap("level 0");
+        parallel_for(kCodes, threads, [&](int64_t c) { cs.sort_range(order.data(), tmp.data(), fresh.data(), count[c], count[c + 1], 1); });
     }
-    // pattern boundaries: does sorted column k differ from its predecessor?
-    std::vector<uint8_t> fresh(order.size(), 1);
-    const int64_t chunk = 1 << 14;
-    parallel_for((n + chunk - 1) / chunk, threads, [&](int64_t b) {
-        for (int64_t k = std::max<int64_t>(1, b * chunk); k < std::min(n, (b + 1) * chunk); ++k)
-            fresh[k] = cs.first_difference(order[k], order[k - 1], 0) < ntax;
+    lap("radix");
+    // pattern index of every sorted column = running count of boundaries (two parallel passes over chunks)
+    const int64_t chunk = 1 << 15, nchunks = (n + chunk - 1) / chunk;
+    std::vector<int64_t> base(nchunks + 1, 0);
+    parallel_for(nchunks, threads, [&](int64_t b) {
+        int64_t cnt = 0;
+        for (int64_t k = b * chunk; k < std::min(n, (b + 1) * chunk); ++k) cnt += fresh[k];
+        base[b + 1] = cnt;
     });
+    for (int64_t b = 0; b < nchunks; ++b) base[b + 1] += base[b];
+    out.npat = base[nchunks];
     out.site_to_pat.assign(nsites, -1);
-    std::vector<int64_t> first;  // representative column of each pattern
-    out.weight.clear();
-    for (int64_t k = 0; k < n; ++k) {
-        const int64_t s = order[k];
-        if (fresh[k]) {
-            first.push_back(s);
-            out.weight.push_back(0);
+    std::vector<int64_t> first(out.npat);  // representative column of each pattern
+    out.weight.assign(out.npat, 0);
+    parallel_for(nchunks, threads, [&](int64_t b) {
+        int64_t p = base[b] - 1;
+        const int64_t lo = b * chunk, hi = std::min(n, (b + 1) * chunk);
+        // a pattern may straddle chunk boundaries: every chunk adds its share of a pattern's weight with one atomic add
+        int64_t acc = 0;
+        for (int64_t k = lo; k < hi; ++k) {
+            const int64_t s = order[k];
+            if (fresh[k]) {
+                if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
+                acc = 0;
+                first[++p] = s;
+            }
+            acc += site_w ? site_w[s] : 1;
+            out.site_to_pat[s] = p;
         }
-        out.weight.back() += site_w ? site_w[s] : 1;
-        out.site_to_pat[s] = (int64_t)first.size() - 1;
-    }
-    out.npat = (int64_t)first.size();
-    out.codes.assign((size_t)ntax * out.npat, 22);
-    parallel_for(ntax, threads, [&](int64_t t) {
-        const uint8_t* row = chars + (size_t)t * nsites;
-        uint8_t* dst = out.codes.data() + (size_t)t * out.npat;
-        for (int64_t p = 0; p < out.npat; ++p) dst[p] = cs.lut[row[first[p]]];
+        if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
     });
+    out.npat = (int64_t)first.size();
+    lap("weights");
+    out.codes.assign((size_t)ntax * out.npat, 22);
+    // gather of the representatives' codes, two taxon rows per pass over the (32-bit) column list: the pass is bound by
+    // streaming that list, the rows themselves stay cache resident
+    std::vector<uint32_t> first32;
+    const bool narrow = nsites < (int64_t)1 << 32;
+    if (narrow) first32.assign(first.begin(), first.end());
+    parallel_for((ntax + 1) / 2, threads, [&](int64_t pair) {
+        const int t0r = (int)(2 * pair), t1r = std::min(ntax - 1, t0r + 1);
+        const uint8_t* row0 = chars + (size_t)t0r * nsites;
+        const uint8_t* row1 = chars + (size_t)t1r * nsites;
+        uint8_t* dst0 = out.codes.data() + (size_t)t0r * out.npat;
+        uint8_t* dst1 = out.codes.data() + (size_t)t1r * out.npat;
+        for (int64_t p = 0; p < out.npat; ++p) {
+            const size_t s = narrow ? (size_t)first32[p] : (size_t)first[p];
+            dst0[p] = cs.lut[row0[s]];
+            dst1[p] = cs.lut[row1[s]];
+        }
+    });
+    lap("codes");
 }
 
 bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,
