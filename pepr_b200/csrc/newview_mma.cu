@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     double* s_P = s_prod;                                          // prologue only: P[child][c][i][j]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long t_entry = op.trace ? clock64() : 0;
+    long long t_entry = 0;
     // model constants and branch lengths are requested before the producer queues the first tiles (see branch_mma.cu)
     const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
     pmat::ModelRegs regs{};
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
+    if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
     if (warp != kProducerWarp) pmat::length_prefetch(regs, op.len_left, op.len_right);
     __syncthreads();
 
@@ -145,10 +146,14 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     }
 
     // every other warp: P matrices of both branches in shared memory (product slots, free until the first tile is done)
+    const bool trp = op.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (trp) op.trace[90] += clock64() - t_entry;
     pmat::model_to_smem<kStagers>(regs, stid, s_model);
     named_barrier(kStageBarrier, kStagers);
+    if (trp) op.trace[91] += clock64() - t_entry;
     pmat::build_p<kStagers>(s_model, stid, s_P);
     named_barrier(kStageBarrier, kStagers);
+    if (trp) op.trace[92] += clock64() - t_entry;
     if (kMixed) pmat::build_tip_lookup<kStagers>(s_P + (kTipL ? 0 : kCats * pmat::kMat), stid, s_tip, kTipPad);
     double fragL[3][5], fragR[3][5];
     if (warp < kMmaWarps) {
