@@ -190,8 +190,8 @@ def main():
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU, help="sites per GPU (default: the named workload)")
     ap.add_argument("--ref-sites", type=int, default=0, help="cap of the CPU sample (columns)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--bootstrap-reps", type=int, default=0,
-                    help="also time this many bootstrap-replicate trees (second half of BASELINE.json's metric); off by default")
+    ap.add_argument("--bootstrap-reps", type=int, default=2,
+                    help="also time this many bootstrap-replicate trees (second half of BASELINE.json's metric); 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -304,13 +304,15 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for r in range(args.bootstrap_reps):
-            bt = pb.Tree(aln, parsimony_seed=12346 + r)
+            bt = pb.Tree(aln, parsimony_seed=12346 + r, weights=W[r])
             bt.optimize(False, 5.0, weights=W[r])
             bl, bm = bt.search(radius=5, max_rounds=1, eps=0.1, weights=W[r])
             bt.close()
         barrier()
         boot = {"bootstrap_tree_wall_s": (time.perf_counter() - t0) / args.bootstrap_reps, "replicates": args.bootstrap_reps,
-                "what": "replicate site weights (raxmlHPC stream, seed 12345) -> parsimony start tree -> one lazy-SPR round (radius 5) -> branch lengths"}
+                "what": "replicate site weights (raxmlHPC stream, seed 12345) -> parsimony start tree on the replicate (GPU Fitch scans) -> "
+                        "branch lengths (eps 5) -> one lazy-SPR round (radius 5) with branch smoothing; wall seconds per replicate tree, "
+                        "replicates run one after the other on every rank's pattern shard"}
 
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------------------
     tree.close()

@@ -139,14 +139,16 @@ int pml_smooth_branches(pml_tree *, int sweeps, const int32_t *weights, int *con
  * Takes over what `-f d` does inside raxmlHPC (makeParsimonyTree, treeOptimizeRapid/rearrangeBIG/testInsertBIG) for
  * RAxMLRunner.run (RAxMLRunner.java:79-152).  The search is a heuristic: it is compared with the reference by the lnL of
  * the tree it finds, not move by move.
- * pml_tree_start_parsimony: randomised stepwise addition under Fitch parsimony (taxon order from the randum stream).
+ * pml_tree_start_parsimony: randomised stepwise addition under Fitch parsimony (taxon order from the randum stream) on
+ *   the patterns weighted by `weights` (a bootstrap replicate); the per-pattern Fitch scans run on the GPU, one launch per
+ *   added taxon, and give exactly the tree of the host-only pml_parsimony_tree.
  * pml_score_spr_candidates: prune inner node `node` together with the subtree behind its neighbour `keep`, insert it
  *   into every branch within `radius` steps (halved branch, unchanged subtree branch: raxmlHPC's lazy insertion) and
  *   return the lnL of each candidate; the tree is left unchanged.  targets/lnl: caller arrays of capacity *ncand in,
  *   number filled out.
  * pml_search: repeat { for every (node, subtree): best lazy candidate -> apply, re-optimise the branches around the
  *   insertion, keep if lnL improves } until a whole round gains < eps or max_rounds is reached. */
-int pml_tree_start_parsimony(pml_aln *, int64_t seed, pml_tree **out);
+int pml_tree_start_parsimony(pml_aln *, int64_t seed, const int32_t *weights /* NULL = alignment's */, pml_tree **out);
 /* host-only (no GPU): the same start tree as newick text + its parsimony score */
 int64_t pml_parsimony_tree(int ntax, int64_t nsites, const char *const *names, const uint8_t *chars, int64_t seed, char *buf,
                            size_t cap, int64_t *score);

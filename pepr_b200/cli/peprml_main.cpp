@@ -214,7 +214,7 @@ int main(int argc, char** argv) {
         auto search_tree = [&](const int32_t* w, int64_t pseed, int rounds, bool final_opt, double* lnl_out, double* alpha_out) {
             pml_tree* t = nullptr;
             check(ctx, pml_model_set(aln, a.model.c_str(), 1.0), "model");
-            check(ctx, pml_tree_start_parsimony(aln, pseed, &t), "parsimony start tree");
+            check(ctx, pml_tree_start_parsimony(aln, pseed, w, &t), "parsimony start tree");
             double lnl = 0.0, alpha = 1.0;
             check(ctx, pml_optimize(t, 1, 5.0, w, &lnl, &alpha), "initial optimisation");
             int moves = 0;
@@ -226,7 +226,7 @@ int main(int argc, char** argv) {
         };
         if (a.parsimony_only) {  // `-y`: stop after the parsimony start tree (RAxMLRunner.runRaxmlParsimonyWithBranchLengths, 1st run)
             pml_tree* t = nullptr;
-            check(ctx, pml_tree_start_parsimony(aln, a.pseed, &t), "parsimony start tree");
+            check(ctx, pml_tree_start_parsimony(aln, a.pseed, nullptr, &t), "parsimony start tree");
             std::string s = tree_string(t);
             std::ofstream(dir + "RAxML_parsimonyTree." + a.name) << s << "\n";
             return 0;

@@ -1210,12 +1210,61 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
     return PML_OK;
 }
 
-int pml_tree_start_parsimony(pml_aln* a, int64_t seed, pml_tree** out) {
+int pml_tree_start_parsimony(pml_aln* a, int64_t seed, const int32_t* weights, pml_tree** out) {
     if (!a || !out) return PML_EINVAL;
     pml_ctx* c = a->ctx;
     *out = nullptr;
+    if (!c->bind()) return PML_ENODEVICE;
+    const int32_t* dw = device_weights(a, weights);
+    if (!dw) return PML_ENODEVICE;
+    // host control flow (host.cpp) + one device scan per added taxon (parsimony.cu)
+    const int maxnodes = 2 * a->pat.ntax;
+    uint32_t *d_down = nullptr, *d_up = nullptr;
+    int4* d_nodes = nullptr;
+    int* d_pre = nullptr;
+    unsigned long long* d_out = nullptr;
+    bool ok = c->cuda(c->dev_alloc(&d_down, sizeof(uint32_t) * (size_t)maxnodes * a->npad), "parsimony alloc") &&
+              c->cuda(c->dev_alloc(&d_up, sizeof(uint32_t) * (size_t)maxnodes * a->npad), "parsimony alloc") &&
+              c->cuda(c->dev_alloc(&d_nodes, sizeof(int4) * maxnodes), "parsimony alloc") &&
+              c->cuda(c->dev_alloc(&d_pre, sizeof(int) * maxnodes), "parsimony alloc") &&
+              c->cuda(c->dev_alloc(&d_out, sizeof(unsigned long long) * (maxnodes + 1)), "parsimony alloc");
+    std::vector<unsigned long long> h_out(maxnodes + 1);
+    ParsimonyScan scan = [&](const GrowTree& g, const std::vector<int>& pre, int next_taxon, int64_t& score, std::vector<int64_t>& cost) {
+        const int N = (int)g.parent.size(), npre = (int)pre.size();
+        auto* hn = (int4*)c->stage(sizeof(int4) * N + sizeof(int) * npre);
+        if (!hn) return false;
+        int* hp = (int*)(hn + N);
+        for (int v = 0; v < N; ++v) hn[v] = make_int4(g.left[v], g.right[v], g.taxon[v], g.parent[v]);
+        std::copy(pre.begin(), pre.end(), hp);
+        ParsimonyArgs pa{a->d_codes, dw, a->npad, a->nloc, d_nodes, d_pre, npre, g.left[0], g.taxon[0], next_taxon, d_down, d_up, d_out};
+        if (!c->cuda(cudaMemcpyAsync(d_nodes, hn, sizeof(int4) * N, cudaMemcpyHostToDevice, c->stream), "parsimony upload") ||
+            !c->cuda(cudaMemcpyAsync(d_pre, hp, sizeof(int) * npre, cudaMemcpyHostToDevice, c->stream), "parsimony upload") ||
+            !c->cuda(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long) * (npre + 1), c->stream), "parsimony clear"))
+            return false;
+        launch_parsimony_scan(pa, c->stream);
+        if (c->nranks > 1 &&
+            g_nccl.AllReduce(d_out, d_out, (size_t)npre + 1, ncclUint64, ncclSum, c->comm, c->stream) != ncclSuccess) {
+            c->err = "ncclAllReduce: parsimony costs";
+            return false;
+        }
+        if (!c->cuda(cudaMemcpyAsync(h_out.data(), d_out, sizeof(unsigned long long) * (npre + 1), cudaMemcpyDeviceToHost, c->stream),
+                     "parsimony download") ||
+            !c->sync())
+            return false;
+        score = (int64_t)h_out[0];
+        cost.assign(npre, 0);
+        for (int i = 0; i < npre; ++i) cost[i] = (int64_t)h_out[1 + i];
+        return true;
+    };
     Topology topo;
-    parsimony_start_tree(a->pat, seed, kDefaultLen, topo, nullptr);
+    ok = ok && parsimony_start_tree(a->pat, seed, kDefaultLen, topo, nullptr, &scan);
+    c->sync();
+    c->dev_free(d_down);
+    c->dev_free(d_up);
+    c->dev_free(d_nodes);
+    c->dev_free(d_pre);
+    c->dev_free(d_out);
+    if (!ok) return c->err.empty() ? fail(c, PML_EINVAL, "parsimony start tree failed") : PML_ENODEVICE;
     if (topo.ntax != a->pat.ntax) return fail(c, PML_EINVAL, "parsimony start tree failed");
     const std::string text = write_newick_result(topo, a->pat.names);
     return pml_tree_load(a, text.substr(0, text.size() - 5).append(";").c_str(), out);

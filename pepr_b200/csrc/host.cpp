@@ -9,6 +9,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <memory>
 #include <numeric>
 #include <sstream>
 #include <thread>
@@ -809,71 +810,22 @@ std::vector<int> spr_targets(const Topology& T, int p, int s, int radius) {
 // =========================================================================================== parsimony ======
 namespace {
 
-inline uint32_t code_mask(int code) {
-    if (code < 20) return 1u << code;
-    if (code == 20) return (1u << 2) | (1u << 3);
-    if (code == 21) return (1u << 5) | (1u << 6);
-    return 0xFFFFFu;
-}
-
-struct GrowTree {
-    // rooted at the first taxon: node 0 = root tip; every other node has a parent; inner nodes have two children
-    std::vector<int> parent, left, right, taxon;
-    int add_node(int tx) {
-        parent.push_back(-1);
-        left.push_back(-1);
-        right.push_back(-1);
-        taxon.push_back(tx);
-        return (int)parent.size() - 1;
+// reference implementation of ParsimonyScan on the host (pml_parsimony_tree, which has no context and no GPU)
+struct HostParsimony {
+    const Patterns& pat;
+    std::vector<std::vector<uint32_t>> tipmask, down, up;
+    explicit HostParsimony(const Patterns& p) : pat(p), tipmask(p.ntax, std::vector<uint32_t>((size_t)p.npat)) {
+        for (int t = 0; t < pat.ntax; ++t)
+            for (int64_t s = 0; s < pat.npat; ++s) tipmask[t][s] = parsimony_code_mask(pat.codes[(size_t)t * pat.npat + s]);
     }
-};
-
-}  // namespace
-
-void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score_out) {
-    const int n = pat.ntax;
-    const int64_t P = pat.npat;
-    std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    for (int i = n - 1; i > 0; --i) {  // Fisher-Yates on the randum stream
-        const int j = (int)((double)(i + 1) * randum(&seed));
-        std::swap(order[i], order[j < 0 ? 0 : (j > i ? i : j)]);
-    }
-    std::vector<std::vector<uint32_t>> tipmask(n, std::vector<uint32_t>((size_t)P));
-    for (int t = 0; t < n; ++t)
-        for (int64_t s = 0; s < P; ++s) tipmask[t][s] = code_mask(pat.codes[(size_t)t * P + s]);
-
-    GrowTree g;
-    const int root = g.add_node(order[0]);  // the root tip hangs above the single top node
-    int top = g.add_node(-1);
-    {
-        const int a = g.add_node(order[1]), b = g.add_node(order[2]);
-        g.left[top] = a;
-        g.right[top] = b;
-        g.parent[a] = g.parent[b] = top;
-        g.parent[top] = root;
-        g.left[root] = top;
-    }
-    std::vector<std::vector<uint32_t>> down, up;  // per node: Fitch set of the subtree below / of everything above
-    int64_t total_score = 0;
-    for (int k = 3; k <= n; ++k) {
-        const int N = (int)g.parent.size();
+    bool operator()(const GrowTree& g, const std::vector<int>& pre, int next_taxon, int64_t& score_out, std::vector<int64_t>& cost) {
+        const int64_t P = pat.npat;
+        const int N = (int)g.parent.size(), root = 0;
         down.assign(N, {});
         up.assign(N, {});
-        // post-order
-        std::vector<int> post, stack{g.left[root]};
-        while (!stack.empty()) {
-            const int v = stack.back();
-            stack.pop_back();
-            post.push_back(v);
-            if (g.left[v] >= 0) {
-                stack.push_back(g.left[v]);
-                stack.push_back(g.right[v]);
-            }
-        }
         int64_t score = 0;
-        for (int i = (int)post.size() - 1; i >= 0; --i) {
-            const int v = post[i];
+        for (int i = (int)pre.size() - 1; i >= 0; --i) {  // children first
+            const int v = pre[i];
             if (g.left[v] < 0) {
                 down[v] = tipmask[g.taxon[v]];
                 continue;
@@ -894,11 +846,11 @@ void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len,
             for (int64_t s = 0; s < P; ++s)
                 if (!(A[s] & B[s])) score += pat.weight[s];
         }
-        total_score = score;
-        if (k == n) break;
-        // pre-order: set above each node
+        score_out = score;
+        if (next_taxon < 0) return true;
+        // parents first: set above each node
         up[g.left[root]] = tipmask[g.taxon[root]];
-        for (int v : post) {
+        for (int v : pre) {
             if (g.left[v] < 0) continue;
             for (int side = 0; side < 2; ++side) {
                 const int c = side ? g.right[v] : g.left[v], sib = side ? g.left[v] : g.right[v];
@@ -910,23 +862,78 @@ void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len,
                 }
             }
         }
-        // cheapest branch (above node v) for the next taxon
-        const std::vector<uint32_t>& X = tipmask[order[k]];
-        int best_v = -1;
-        int64_t best_cost = 0;
-        for (int v : post) {
-            const auto &U = up[v], &D = down[v];
-            int64_t cost = 0;
+        const std::vector<uint32_t>& X = tipmask[next_taxon];
+        cost.assign(pre.size(), 0);
+        for (size_t i = 0; i < pre.size(); ++i) {
+            const auto &U = up[pre[i]], &D = down[pre[i]];
+            int64_t c = 0;
             for (int64_t s = 0; s < P; ++s) {
                 uint32_t e = U[s] & D[s];
                 if (!e) e = U[s] | D[s];
-                if (!(e & X[s])) cost += pat.weight[s];
+                if (!(e & X[s])) c += pat.weight[s];
             }
-            if (best_v < 0 || cost < best_cost) {
-                best_v = v;
-                best_cost = cost;
+            cost[i] = c;
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score_out,
+                          const ParsimonyScan* scan) {
+    const int n = pat.ntax;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    for (int i = n - 1; i > 0; --i) {  // Fisher-Yates on the randum stream
+        const int j = (int)((double)(i + 1) * randum(&seed));
+        std::swap(order[i], order[j < 0 ? 0 : (j > i ? i : j)]);
+    }
+    std::unique_ptr<HostParsimony> host;
+    ParsimonyScan host_scan;
+    if (!scan) {
+        host = std::make_unique<HostParsimony>(pat);
+        host_scan = [&](const GrowTree& g, const std::vector<int>& pre, int next, int64_t& sc, std::vector<int64_t>& cost) {
+            return (*host)(g, pre, next, sc, cost);
+        };
+        scan = &host_scan;
+    }
+
+    GrowTree g;
+    const int root = g.add_node(order[0]);  // the root tip hangs above the single top node
+    int top = g.add_node(-1);
+    {
+        const int a = g.add_node(order[1]), b = g.add_node(order[2]);
+        g.left[top] = a;
+        g.right[top] = b;
+        g.parent[a] = g.parent[b] = top;
+        g.parent[top] = root;
+        g.left[root] = top;
+    }
+    int64_t total_score = 0;
+    std::vector<int64_t> cost;
+    for (int k = 3; k <= n; ++k) {
+        // nodes below the root tip, parents first
+        std::vector<int> pre, stack{g.left[root]};
+        while (!stack.empty()) {
+            const int v = stack.back();
+            stack.pop_back();
+            pre.push_back(v);
+            if (g.left[v] >= 0) {
+                stack.push_back(g.left[v]);
+                stack.push_back(g.right[v]);
             }
         }
+        if (!(*scan)(g, pre, k < n ? order[k] : -1, total_score, cost)) return false;
+        if (k == n) break;
+        // cheapest branch (above node v) for the next taxon; the first one in `pre` wins a tie
+        int best_v = -1;
+        int64_t best_cost = 0;
+        for (size_t i = 0; i < pre.size(); ++i)
+            if (best_v < 0 || cost[i] < best_cost) {
+                best_v = pre[i];
+                best_cost = cost[i];
+            }
         // insert a new inner node above best_v
         const int w = g.add_node(-1), x = g.add_node(order[k]);
         const int par = g.parent[best_v];
@@ -947,7 +954,7 @@ void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len,
     if (g.left[t0] >= 0) text = "(" + pat.names[g.taxon[root]] + "," + nw(g.left[t0]) + "," + nw(g.right[t0]) + ");";
     else text = "(" + pat.names[g.taxon[root]] + "," + nw(t0) + ");";
     std::string err;
-    parse_newick(text, pat.names, default_len, out, err);
+    return parse_newick(text, pat.names, default_len, out, err);
 }
 
 }  // namespace pml

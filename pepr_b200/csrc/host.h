@@ -3,6 +3,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -93,7 +94,29 @@ std::vector<int> spr_targets(const Topology& T, int p, int s, int radius);
 
 // ---- parsimony starting tree ---------------------------------------------------------------------------------
 // randomised stepwise addition under Fitch parsimony on the weighted patterns (raxmlHPC makeParsimonyTree's role);
-// taxa are added in a random order drawn from randum(seed); all branch lengths are set to default_len
-void parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score);
+// taxa are added in a random order drawn from randum(seed); all branch lengths are set to default_len.
+// The tree grows rooted at the first taxon: node 0 = root tip; every other node has a parent; inner nodes have two children.
+struct GrowTree {
+    std::vector<int> parent, left, right, taxon;
+    int add_node(int tx) {
+        parent.push_back(-1);
+        left.push_back(-1);
+        right.push_back(-1);
+        taxon.push_back(tx);
+        return (int)parent.size() - 1;
+    }
+};
+// One addition step over all patterns: `pre` lists the nodes below the root tip parents-first.  Returns the weighted Fitch
+// score of the current tree and, when next_taxon >= 0, cost[i] = weighted number of patterns that gain a change if
+// next_taxon is attached to the branch above pre[i].  The engine supplies a GPU implementation (csrc/parsimony.cu).
+using ParsimonyScan = std::function<bool(const GrowTree& g, const std::vector<int>& pre, int next_taxon, int64_t& score, std::vector<int64_t>& cost)>;
+bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score,
+                          const ParsimonyScan* scan = nullptr);
+inline uint32_t parsimony_code_mask(int code) {
+    if (code < 20) return 1u << code;
+    if (code == 20) return (1u << 2) | (1u << 3);
+    if (code == 21) return (1u << 5) | (1u << 6);
+    return 0xFFFFFu;
+}
 
 }  // namespace pml

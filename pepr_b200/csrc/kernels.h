@@ -195,6 +195,21 @@ void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* s
 void launch_replicate_lnl(const int32_t* W, int nrep, int64_t np, int64_t ldw, const double* site_lnl, double* lnl,
                           cudaStream_t stream);
 
+// one Fitch parsimony scan over this rank's patterns (parsimony.cu); out[0] += score, out[1 + i] += cost of attaching
+// next_taxon above pre[i] (all weighted, exact integers); down / up: [nnodes][npad] scratch
+struct ParsimonyArgs {
+    const uint8_t* codes;     // [ntax][npad]
+    const int32_t* weights;   // [npad]
+    int64_t npad, nloc;
+    const int4* nodes;        // per node: left, right, taxon, parent
+    const int* pre;           // nodes below the root tip, parents first
+    int npre, top, root_taxon, next_taxon;
+    uint32_t* down;
+    uint32_t* up;
+    unsigned long long* out;  // 1 + npre, zeroed by the caller
+};
+void launch_parsimony_scan(const ParsimonyArgs& a, cudaStream_t stream);
+
 int64_t reduce_partials_capacity(int64_t np);  // doubles needed in `partials`
 
 }  // namespace pml

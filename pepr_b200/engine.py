@@ -70,7 +70,7 @@ def lib():
         L.pml_parsimony_tree.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_int64, C.c_char_p, C.c_size_t, c_i64p]
         L.pml_tree_spr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.pml_tree_neighbors.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.pml_tree_start_parsimony.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.pml_tree_start_parsimony.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p)]
         L.pml_search.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, c_f64p, C.POINTER(C.c_int)]
         L.pml_score_spr_candidates.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.pml_profile_begin.argtypes = [C.c_void_p]
@@ -200,15 +200,16 @@ class Alignment:
 
 
 class Tree:
-    def __init__(self, aln, newick=None, parsimony_seed=None):
+    def __init__(self, aln, newick=None, parsimony_seed=None, weights=None):
         """newick: a given topology; parsimony_seed: randomised stepwise-addition parsimony start tree"""
         self.aln, self.ctx = aln, aln.ctx
         h = C.c_void_p()
         if newick is not None:
             self.ctx.check(lib().pml_tree_load(aln.h, newick.encode(), C.byref(h)), "pml_tree_load")
         else:
+            w = _weights(weights)
             self.ctx.check(lib().pml_tree_start_parsimony(aln.h, C.c_int64(12345 if parsimony_seed is None else parsimony_seed),
-                                                           C.byref(h)), "pml_tree_start_parsimony")
+                                                           _ptr(w), C.byref(h)), "pml_tree_start_parsimony")
         self.h = h
 
     @property

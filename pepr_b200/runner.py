@@ -141,7 +141,7 @@ class B200MLRunner:
             aln.close()
 
     def _search_one(self, aln, weights, seed, rounds, final):
-        tree = _e.Tree(aln, parsimony_seed=seed)
+        tree = _e.Tree(aln, parsimony_seed=seed, weights=weights)
         aln.set_model(1.0, self.matrix)
         tree.optimize(True, 5.0, weights=weights)
         lnl, _ = tree.search(radius=5, max_rounds=rounds, eps=self.eps, weights=weights)

@@ -47,6 +47,23 @@ def test_lazy_spr_scores_match_oracle(gpu_ctx, golden):
     tree.close(); aln.close()
 
 
+@pytest.mark.parametrize("case", ["search", "deep", "small"])
+def test_device_parsimony_scan_gives_the_host_tree(gpu_ctx, golden, case):
+    """integer work: the GPU Fitch scans must pick exactly the branches the host implementation picks (same seed)"""
+    g = golden(case)
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=1.0)
+    for seed in (12345, 777):
+        tree = pb.Tree(aln, parsimony_seed=seed)
+        want, _ = pb.parsimony_tree(g.names, g.seqs, seed)
+        assert _splits(_strip(tree.newick())) == _splits(_strip(want))
+        tree.close()
+    # a replicate's weights change the costs and (usually) the tree; zero-weight patterns must not count
+    W, _ = aln.bootstrap_weights(4242, 1)
+    t1 = pb.Tree(aln, parsimony_seed=12345, weights=W[0])
+    assert t1.num_branches == 2 * len(g.names) - 3
+    t1.close(); aln.close()
+
+
 def test_search_finds_reference_tree(gpu_ctx, golden):
     g = golden("search")
     fd = g.meta["fd"]
