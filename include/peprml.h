@@ -104,6 +104,9 @@ int pml_evaluate(pml_tree *, const int32_t *weights, double *lnl, double *per_si
 int pml_tree_invalidate(pml_tree *);
 /* counters since tree creation: CLV site-updates by case (0 tip-tip, 1 tip-inner, 2 inner-inner) and kernel launches */
 int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_launches);
+/* Newton-Raphson passes since tree creation that ended in raxmlHPC's bad-curvature retry (z = 0.37 z + 0.63): each one makes
+ * the smoothing pipeline drop the branch it had queued speculatively */
+int64_t pml_tree_nr_retries(const pml_tree *);
 
 /* ---- device-side timing of the engine's own kernels (CUDA events on the context's stream) -------------------
  * Between begin and end every launch of kind k is bracketed by a pair of events; end() synchronises and returns, per

@@ -79,6 +79,7 @@ struct pml_ctx {
     double** d_mail_ptrs = nullptr;
     std::vector<void*> peer_opened;
     bool peer_ok = false;
+    bool host_nr = false;  // PEPRML_HOST_NR=1: Newton-Raphson steps on the host, one wait per branch (reference mode for tests)
     volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     double* slot_dev(double seq) const { return d_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     // waits until the pass with this sequence number has published; out = {lnL, d1, d2, length, status}
@@ -461,8 +462,10 @@ bool newton_branch(pml_tree* t, int e, const int32_t* dw, int maxiter, double& z
         } else if (!core_at(t, dw, -std::log(z), r)) return false;
         first = false;
         const double d1 = -r[1], d2 = r[2];  // derivatives in lz = log z = -t
-        if (d2 >= 0.0 && z < kZmax) zprev = z = 0.37 * z + 0.63;
-        else curvature_ok = true;
+        if (d2 >= 0.0 && z < kZmax) {
+            zprev = z = 0.37 * z + 0.63;
+            ++t->nr_retries;
+        } else curvature_ok = true;
         if (curvature_ok) {
             if (d2 < 0.0) {
                 const double step = -d1 / d2;
@@ -493,6 +496,28 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
     smoothed = true;
     pml_ctx* c = t->aln->ctx;
     Topology& T = t->topo;
+    if (c->host_nr) {
+        // reference mode (PEPRML_HOST_NR=1): the same sweep with the NR step on the host and a wait per branch; the tests
+        // hold the pipelined path to it
+        std::vector<std::pair<int, int>> stack;  // (branch, far node)
+        stack.push_back({T.edge[0][0], T.nbr[0][0]});
+        while (!stack.empty()) {
+            const auto [e, far] = stack.back();
+            stack.pop_back();
+            const double z0 = std::min(std::max(std::exp(-T.len[e]), kZmin), kZmax);
+            double z;
+            if (!newton_branch(t, e, dw, 1, z)) return false;
+            if (std::fabs(z - z0) > 1.0e-5) smoothed = false;
+            set_branch(t, e, -std::log(z));
+            t->views.branch_changed(T, e);
+            if (!T.is_tip(far)) {
+                const int near = T.ea[e] == far ? T.eb[e] : T.ea[e];
+                for (int s = 2; s >= 0; --s)
+                    if (T.nbr[far][s] != near) stack.push_back({T.edge[far][s], T.nbr[far][s]});
+            }
+        }
+        return true;
+    }
     std::vector<int> order;
     {
         std::vector<std::pair<int, int>> stack;  // (branch, far node)
@@ -811,6 +836,7 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     if (gpu_id < 0 || gpu_id >= ndev) return fail(nullptr, PML_EINVAL, "gpu_id out of range");
     auto c = std::make_unique<pml_ctx>();
     c->device = gpu_id;
+    c->host_nr = getenv("PEPRML_HOST_NR") != nullptr;
     c->rank = rank;
     c->nranks = nranks;
     if (!c->bind() || !c->cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create"))
@@ -1131,6 +1157,8 @@ int pml_tree_invalidate(pml_tree* t) {
     t->prepared_branch = -1;
     return PML_OK;
 }
+
+int64_t pml_tree_nr_retries(const pml_tree* t) { return t ? t->nr_retries : PML_EINVAL; }
 
 int pml_tree_stats(const pml_tree* t, int64_t site_updates[3], int64_t* launches) {
     if (!t) return PML_EINVAL;

@@ -57,6 +57,8 @@ def lib():
         L.pml_tree_newick.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.pml_tree_invalidate.argtypes = [C.c_void_p]
         L.pml_tree_stats.argtypes = [C.c_void_p, c_i64p, c_i64p]
+        L.pml_tree_nr_retries.argtypes = [C.c_void_p]
+        L.pml_tree_nr_retries.restype = C.c_int64
         L.pml_evaluate.argtypes = [C.c_void_p, C.c_void_p, c_f64p, C.c_void_p]
         L.pml_branch_derivs.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, c_f64p, c_f64p, c_f64p]
         L.pml_optimize.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, c_f64p, c_f64p]
@@ -239,6 +241,10 @@ class Tree:
         ps = np.zeros(self.aln.nsites) if per_site else None
         self.ctx.check(lib().pml_evaluate(self.h, _ptr(w), C.byref(lnl), _ptr(ps)), "pml_evaluate")
         return (lnl.value, ps) if per_site else lnl.value
+
+    @property
+    def nr_retries(self):
+        return int(lib().pml_tree_nr_retries(self.h))
 
     def branch_derivs(self, branch, t, weights=None):
         w = _weights(weights)

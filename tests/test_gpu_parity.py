@@ -160,3 +160,35 @@ def test_ragged_pattern_counts(gpu_ctx, golden):
         want = orc.evaluate(m, orc.Tree(fe["tree"], g.names), pat, w, fe["alpha"])
         assert abs(tree.evaluate() - want) <= 1e-10 * abs(want)
         tree.close(); aln.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["deep", "dup"])
+def test_pipelined_smoothing_equals_host_reference_mode(golden, case):
+    """The device-resident sweep (NR step in the kernel tail, host one branch ahead, poison-flag rollback on raxmlHPC's
+    bad-curvature retry) against the same sweep with the step on the host and a wait per branch (PEPRML_HOST_NR=1).
+    Bad starting lengths provoke the retry path."""
+    import os
+    g = golden(case)
+    results, retries = {}, {}
+    for mode in ("device", "host"):
+        if mode == "host":
+            os.environ["PEPRML_HOST_NR"] = "1"
+        else:
+            os.environ.pop("PEPRML_HOST_NR", None)
+        ctx = pb.Context(0)
+        os.environ.pop("PEPRML_HOST_NR", None)
+        aln = pb.Alignment(ctx, g.names, g.seqs, alpha=0.7)
+        out, nret = [], 0
+        for start in (0.1, 2.5, 9.0, 30.0):
+            tree = pb.Tree(aln, g.meta["tree_in"])
+            for e in range(tree.num_branches):
+                tree.set_branch(e, start if e % 3 else 0.001)
+            tree.smooth(3)
+            out.append([tree.branch(e)[2] for e in range(tree.num_branches)] + [tree.evaluate()])
+            nret += tree.nr_retries
+            tree.close()
+        results[mode], retries[mode] = np.array(out), nret
+        aln.close(); ctx.close()
+    assert retries["device"] == retries["host"] and retries["device"] > 0, retries
+    assert np.allclose(results["device"], results["host"], rtol=1e-8, atol=1e-12), np.abs(results["device"] - results["host"]).max()
