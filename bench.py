@@ -33,8 +33,10 @@ UNIT = "site-updates/s"
 NTAX = 100
 SITES_PER_GPU = 100_000
 SEED = 3
-BYTES = {"newview_tip_tip": 642, "newview_tip_inner": 1281, "newview_inner_inner": 1920,
-         "evaluate": 1284, "sumtable": 1920, "core": 644}   # algorithmic bytes per pattern (SURVEY 8d / DESIGN.md)
+BYTES = {"newview_tip_tip": 642, "newview_tip_inner": 1281, "newview_inner_inner": 1920, "evaluate": 660,
+         "branch_inner_inner": 1292, "branch_tip_inner": 652, "core": 648}   # algorithmic bytes per pattern (SURVEY 8d / DESIGN.md)
+# DMMA.8x8x4 issued per 16-pattern tile and MMA warp by the branch kernel (its binding roofline is the FP64 tensor pipe)
+FLOP_PER_PATTERN = {"branch_inner_inner": 4 * 72 * 512 / 16.0, "branch_tip_inner": 4 * 42 * 512 / 16.0}
 WORKMODEL = os.path.join(ROOT, "bench_workmodel.json")
 
 
@@ -345,8 +347,9 @@ def main():
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
     e2e_value = e_s.item() / e_t.item()
-    ncore, neval = prof["core"][1] / args.steps, prof["evaluate"][1] / args.steps
-    d2h = int(24 * ncore + 8 * neval + nwlen)
+    # device -> host: every branch pass publishes five (value, seq) pairs (80 B) through mapped memory; + the result tree
+    npass = sum(prof[k][1] for k in ("evaluate", "branch_inner_inner", "branch_tip_inner", "core")) / args.steps
+    d2h = int(80 * npass + nwlen)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -361,7 +364,10 @@ def main():
         for name, (kms_, kn_, krows_) in prof.items():
             if kn_:
                 kernels[name] = {"launches_per_step": kn_ / args.steps, "ms_per_step": kms_ / args.steps,
-                                 "GBps": BYTES[name] * krows_ / (kms_ * 1e-3) / 1e9}
+                                 "avg_launch_us": 1e3 * kms_ / kn_, "GBps": BYTES[name] * krows_ / (kms_ * 1e-3) / 1e9}
+                if name in FLOP_PER_PATTERN:   # issued FP64 tensor flops (24-wide padding included) against the measured 37.0 TFLOP/s
+                    kernels[name]["dmma_TFLOPs"] = FLOP_PER_PATTERN[name] * krows_ / (kms_ * 1e-3) / 1e12
+                    kernels[name]["dmma_frac_of_37.0"] = kernels[name]["dmma_TFLOPs"] / 37.0
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

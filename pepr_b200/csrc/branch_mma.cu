@@ -346,15 +346,25 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         const long long tk2 = tr ? clock64() : 0;
         // block by block; the whole contraction stays inside this group's turn (issued after the token is passed, its
         // FP64 instructions and the other group's DMMAs slow each other down: measured 1,500 instead of 1,215 clk per tile)
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
+        if (kTipA) {
+            // one side only: both blocks together keep six accumulator chains between two dependent DMMAs
 #pragma unroll
             for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    if (!kTipA) dmma(accA[m][nt][0], accA[m][nt][1], fa[m].v[kt], fragA[nt][kt]);
-                    dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
-                }
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt) dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int kt = 0; kt < 5; ++kt)
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt) {
+                        dmma(accA[m][nt][0], accA[m][nt][1], fa[m].v[kt], fragA[nt][kt]);
+                        dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
+                    }
+        }
         // products of the two sides, then the contraction: four accumulator chains (2 per block) of three DMMAs each
         double fs[2][2][2];
 #pragma unroll

@@ -383,7 +383,7 @@ double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool kee
     const bool in_kernel = c->nranks == 1 || c->peer_ok;
     if (in_kernel) args.pub = pub;
     if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks};
-    const int tk = c->tick(site_lnl ? 3 : 4, a->nloc);
+    const int tk = c->tick(site_lnl ? 3 : (args.a.clv ? 4 : 6), a->nloc);
     launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
