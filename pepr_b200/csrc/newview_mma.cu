@@ -64,7 +64,8 @@ struct SmemPlan {
     static constexpr int kTipDoubles = kCodes * kTipPad;             // exactly one child is a tip in the mixed case
     static constexpr int kMaxInts = kProdSlots * kCats * kTileRows;  // [slot][cat][row]
     static constexpr size_t kBarBytes = 256;
-    static_assert(kProdSlots * kTileDoubles >= pmat::kPDoubles, "the product slots double as the staging area of the P matrices");
+    static_assert(kProdSlots * kTileDoubles >= 8 * pmat::kFragSlotDoubles && kProdSlots * kTileDoubles >= 4 * pmat::kFragSlotDoubles + kCats * pmat::kMat,
+                  "the product slots double as the staging area of the P matrices");
     static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(pmat::kModelDoubles + (kInner == 2 ? 0 : kTipDoubles)) +
                                      sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
                                      sizeof(double) * (size_t)(kProdSlots * kTileDoubles + kMmaGroups * kDepth * kStageDoubles);
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     int* s_sc = s_max + Plan::kMaxInts;                            // [kProdSlots][16] summed scaling counts of the children
     double* s_prod = reinterpret_cast<double*>(s_sc + kProdSlots * kTileRows);
     double* s_stage = s_prod + kProdSlots * kTileDoubles;
-    double* s_P = s_prod;                                          // prologue only: P[child][c][i][j]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long t_entry = 0;
@@ -95,6 +95,11 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     pmat::ModelRegs regs{};
     pdl_launch_dependents();
     if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, stid);
+    // MMA warp w builds the matrix of (category w & 3, left branch for group 0 / right branch for group 1): lane k < 20 holds
+    // lambda_k * r_c now and exp(lambda_k r_c t) once the branch length may be read
+    const int c_p = warp & 3, child_p = warp >> 2;
+    double lr = 0.0;
+    if (warp < kMmaWarps && lane < kStates) lr = op.dm->lambda[lane] * op.dm->rates[c_p];
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMmaGroups * kDepth; ++i) {
             mbar_init(in_full + i, 1);
@@ -106,9 +111,11 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp != kProducerWarp) pmat::matrices_to_smem<kStagers>(regs, stid, s_model);  // static: V and Vinv
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
-    if (warp != kProducerWarp) pmat::length_prefetch(regs, op.len_left, op.len_right);
+    double my_len = 0.0;
+    if (warp < kMmaWarps) my_len = child_p == 0 ? *op.len_left : *op.len_right;
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
@@ -148,20 +155,31 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     // every other warp: P matrices of both branches in shared memory (product slots, free until the first tile is done)
     const bool trp = op.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     if (trp) op.trace[90] += clock64() - t_entry;
-    pmat::model_to_smem<kStagers>(regs, stid, s_model);
-    named_barrier(kStageBarrier, kStagers);
-    if (trp) op.trace[91] += clock64() - t_entry;
-    pmat::build_p<kStagers>(s_model, stid, s_P);
-    named_barrier(kStageBarrier, kStagers);
-    if (trp) op.trace[92] += clock64() - t_entry;
-    if (kMixed) pmat::build_tip_lookup<kStagers>(s_P + (kTipL ? 0 : kCats * pmat::kMat), stid, s_tip, kTipPad);
+    // Each MMA warp builds ONE of the eight matrices on the tensor pipe.  An inner child's matrix is turned into B fragments
+    // and shared with the partner warp of the other group through shared memory; a tip child's matrix goes to shared memory
+    // for the lookup table.
     double fragL[3][5], fragR[3][5];
+    double* s_x = s_prod;                                          // fragment exchange: [slot][15][32]
+    double* s_Ptip = s_prod + 4 * pmat::kFragSlotDoubles;          // mixed case: P[c][i][j] of the tip child
     if (warp < kMmaWarps) {
-        const int c = warp & 3, g = lane >> 2, t = lane & 3;
-        if (!kTipL) load_p_fragments(s_P + c * pmat::kMat, g, t, fragL);
-        if (!kTipR) load_p_fragments(s_P + (kCats + c) * pmat::kMat, g, t, fragR);
+        double acc[3][3][2];
+        pmat::build_p_tiles(s_model, exp(lr * my_len), lane, acc);
+        const bool tip_child = child_p == 0 ? kTipL : kTipR;
+        if (tip_child) pmat::tiles_to_smem(acc, lane, s_Ptip + c_p * pmat::kMat);
+        else {
+            if (child_p == 0) pmat::tiles_to_fragments(acc, lane, fragL);
+            else pmat::tiles_to_fragments(acc, lane, fragR);
+            pmat::fragments_to_smem(child_p == 0 ? fragL : fragR, lane, s_x + (kMixed ? c_p : warp) * pmat::kFragSlotDoubles);
+        }
     }
     named_barrier(kStageBarrier, kStagers);
+    if (trp) op.trace[92] += clock64() - t_entry;
+    if (kMixed) pmat::build_tip_lookup<kStagers>(s_Ptip, stid, s_tip, kTipPad);
+    if (warp < kMmaWarps) {  // the other child's fragments were built by the partner warp
+        if (!kTipL && child_p == 1) pmat::fragments_from_smem(fragL, lane, s_x + c_p * pmat::kFragSlotDoubles);
+        if (!kTipR && child_p == 0) pmat::fragments_from_smem(fragR, lane, s_x + (kMixed ? c_p : kCats + c_p) * pmat::kFragSlotDoubles);
+    }
+    named_barrier(kStageBarrier, kStagers);  // the product slots are free for their real purpose
     if (warp > kProducerWarp) return;
 
     if (warp >= kMmaWarps) {

@@ -52,6 +52,19 @@ __device__ __forceinline__ void length_prefetch(ModelRegs& r, const double* len_
     r.len[1] = *len_r;
 }
 
+// V and Vinv only (static: may be staged before pdl_wait)
+template <int kThreads>
+__device__ __forceinline__ void matrices_to_smem(const ModelRegs& r, int tid, double* s_model) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int idx = tid + q * kThreads;
+        if (idx < kMat) {
+            s_model[idx] = r.v[q];
+            s_model[kMat + idx] = r.vinv[q];
+        }
+    }
+}
+
 // s_model: [V 400][Vinv 400][exp child 0: 80][exp child 1: 80]
 template <int kThreads>
 __device__ __forceinline__ void model_to_smem(const ModelRegs& r, int tid, double* s_model) {
@@ -93,6 +106,78 @@ __device__ __forceinline__ void build_p(const double* s_model, int tid, double* 
         for (int j = 0; j < 5; ++j) out[j] = make_double2(acc[2 * j], acc[2 * j + 1]);
     }
 }
+
+// ---- the same product on the FP64 tensor path, one warp per (branch, category) ---------------------------------------
+// P_c = W * Vinv with W[i][k] = V[i][k] e_c[k] as 3 x 3 tiles of m8n8k4 (45 DMMA, nine independent accumulator chains):
+// the eight MMA warps of a CLV kernel build the eight matrices of a launch in ~1,500 cycles (FMA version above: ~3,200),
+// and an inner child's matrix comes out of the accumulators directly in the B-fragment layout the CLV loop wants.
+// Summation order over k differs from the host code in the last bit; the engine's results are compared with the oracle at
+// 1e-10 relative.
+__device__ __forceinline__ void dmma_p(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// acc[nt][jt] = P_c[nt*8 + g][jt*8 + 2t + {0,1}] for lane = 4g + t.  e_lane = exp(lambda_k r_c t) held by lane k (< 20):
+// the warp computes its own twenty exponentials, so nothing but V and Vinv (static, staged before the dependency wait) has to
+// be in shared memory.
+__device__ __forceinline__ void build_p_tiles(const double* s_model, double e_lane, int lane, double (&acc)[3][3][2]) {
+    const double* s_V = s_model;
+    const double* s_Vinv = s_model + kMat;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) acc[nt][jt][0] = acc[nt][jt][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+        const int k = 4 * ks + t;
+        const double e = __shfl_sync(0xffffffffu, e_lane, k);
+        double a[3], b[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int ij = q * 8 + g;
+            a[q] = ij < kStates ? s_V[ij * kStates + k] * e : 0.0;
+            b[q] = ij < kStates ? s_Vinv[k * kStates + ij] : 0.0;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int jt = 0; jt < 3; ++jt) dmma_p(acc[nt][jt][0], acc[nt][jt][1], a[nt], b[jt]);
+    }
+}
+// accumulators -> B fragments of the CLV loop: frag[nt][kt] = P_c[nt*8 + g][kmap(kt, t)], kmap = 2t, 2t+1, 8+2t, 9+2t, 16+t
+__device__ __forceinline__ void tiles_to_fragments(const double (&acc)[3][3][2], int lane, double (&frag)[3][5]) {
+    const int t = lane & 3, src = (lane & ~3) | (t >> 1);
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+        frag[nt][0] = acc[nt][0][0];
+        frag[nt][1] = acc[nt][0][1];
+        frag[nt][2] = acc[nt][1][0];
+        frag[nt][3] = acc[nt][1][1];
+        const double v0 = __shfl_sync(0xffffffffu, acc[nt][2][0], src), v1 = __shfl_sync(0xffffffffu, acc[nt][2][1], src);
+        frag[nt][4] = (t & 1) ? v1 : v0;
+    }
+}
+// accumulators -> P_c[i][j] row-major in shared memory (a tip child's matrix feeds the lookup table)
+__device__ __forceinline__ void tiles_to_smem(const double (&acc)[3][3][2], int lane, double* Pc) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt) {
+            const int i = nt * 8 + g, j = jt * 8 + 2 * t;
+            if (i < kStates && j < kStates) *reinterpret_cast<double2*>(Pc + i * kStates + j) = make_double2(acc[nt][jt][0], acc[nt][jt][1]);
+        }
+}
+// fragment exchange between the two MMA groups: [warp slot][fragment][lane]
+__device__ __forceinline__ void fragments_to_smem(const double (&frag)[3][5], int lane, double* slot) {
+#pragma unroll
+    for (int q = 0; q < 15; ++q) slot[q * 32 + lane] = frag[q / 5][q % 5];
+}
+__device__ __forceinline__ void fragments_from_smem(double (&frag)[3][5], int lane, const double* slot) {
+#pragma unroll
+    for (int q = 0; q < 15; ++q) frag[q / 5][q % 5] = slot[q * 32 + lane];
+}
+constexpr int kFragSlotDoubles = 15 * 32;
 
 // tip[code][c*20+i] = sum_j P_c[i][j] * indicator(code)[j]; rows padded to `pad` doubles
 template <int kThreads>
