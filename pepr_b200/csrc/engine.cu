@@ -10,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <limits>
 #include <memory>
 #include <sstream>
 #include <string>
@@ -690,6 +691,38 @@ bool polish_branch(pml_tree* t, int e, const int32_t* dw, int iters) {
     return true;
 }
 
+// Lazy scores of a list of regraft targets for the pruned (p, s): every candidate is applied, queued (CLV updates + one branch
+// pass at the subtree's branch) and undone on the host WITHOUT waiting for its lnL; the outcomes are collected from the result
+// ring a few candidates later, so the device never idles between candidates.  out[i] = lnL (or -inf when the move is illegal).
+bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets, const int32_t* dw, std::vector<double>& out) {
+    pml_ctx* c = t->aln->ctx;
+    Topology& T = t->topo;
+    out.assign(targets.size(), -std::numeric_limits<double>::infinity());
+    constexpr size_t kLag = pml_ctx::kRing - 2;
+    std::vector<std::pair<double, size_t>> queued;  // (sequence number, candidate index)
+    size_t head = 0;
+    auto collect = [&](size_t upto) {
+        for (; head < upto; ++head) {
+            double r[5];
+            if (!c->wait_slot(queued[head].first, r)) return false;
+            out[queued[head].second] = r[0];
+        }
+        return true;
+    };
+    for (size_t i = 0; i < targets.size(); ++i) {
+        SprMove mv;
+        if (!spr_apply(T, t->views, p, s, targets[i], mv)) continue;
+        t->prepared_branch = -1;
+        const double seq = branch_launch(t, mv.e_s, dw, T.len[mv.e_s], false, false, kWantLnl, false);
+        spr_undo(T, t->views, mv);
+        t->prepared_branch = -1;
+        if (seq == 0.0) return false;
+        queued.push_back({seq, i});
+        if (queued.size() - head > kLag && !collect(queued.size() - kLag)) return false;
+    }
+    return collect(queued.size());
+}
+
 struct SearchStats {
     int64_t candidates = 0;
     int accepted = 0;
@@ -706,18 +739,14 @@ bool spr_round(pml_tree* t, const int32_t* dw, int radius, double& best, SearchS
             if (targets.empty()) continue;
             int best_target = -1;
             double best_lazy = -1e300;
-            for (int tgt : targets) {
-                SprMove mv;
-                if (!spr_apply(T, t->views, p, s, tgt, mv)) continue;
-                t->prepared_branch = -1;
-                double l;
-                const bool ok = lnl_at(t, mv.e_s, dw, l);
-                spr_undo(T, t->views, mv);
-                if (!ok) return false;
+            std::vector<double> lazy;
+            if (!score_candidates(t, p, s, targets, dw, lazy)) return false;
+            for (size_t i = 0; i < targets.size(); ++i) {
+                if (!std::isfinite(lazy[i])) continue;
                 ++st.candidates;
-                if (l > best_lazy) {
-                    best_lazy = l;
-                    best_target = tgt;
+                if (lazy[i] > best_lazy) {
+                    best_lazy = lazy[i];
+                    best_target = targets[i];
                 }
             }
             // the lazy score leaves three branches unoptimised, so a candidate slightly below the current tree may still win
@@ -1341,20 +1370,15 @@ int pml_score_spr_candidates(pml_tree* t, int node, int keep, int radius, const 
     if (!c->bind()) return PML_ENODEVICE;
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
-    const std::vector<int> cand = spr_targets(T, node, keep, radius);
+    std::vector<int> cand = spr_targets(T, node, keep, radius);
+    if ((int)cand.size() > *ncand) cand.resize(*ncand);
+    std::vector<double> lazy;
+    if (!score_candidates(t, node, keep, cand, dw, lazy)) return PML_ENODEVICE;
     int n = 0;
-    for (int tgt : cand) {
-        if (n >= *ncand) break;
-        SprMove mv;
-        if (!spr_apply(T, t->views, node, keep, tgt, mv)) continue;
-        t->prepared_branch = -1;
-        double l;
-        const bool ok = lnl_at(t, mv.e_s, dw, l);
-        spr_undo(T, t->views, mv);
-        t->prepared_branch = -1;
-        if (!ok) return PML_ENODEVICE;
-        targets[n] = tgt;
-        lnl[n] = l;
+    for (size_t i = 0; i < cand.size(); ++i) {
+        if (!std::isfinite(lazy[i])) continue;
+        targets[n] = cand[i];
+        lnl[n] = lazy[i];
         ++n;
     }
     *ncand = n;

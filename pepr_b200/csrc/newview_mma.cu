@@ -11,6 +11,7 @@
 // CLVs live in HBM in the blocked layout described in mma_common.cuh, so a stage is filled by one bulk copy per child.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "kernels.h"
@@ -366,7 +367,7 @@ struct TipTipSmem {
     uint8_t flag[kCodes * kCodes];
     uint8_t pair[2][kTipTipRows][2];
 };
-__global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp op, int nchunks) {
+__global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp op, int64_t np) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TipTipSmem& sm = *reinterpret_cast<TipTipSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -374,11 +375,15 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
     pmat::ModelRegs regs = pmat::model_prefetch<kTipTipThreads>(op.dm, tid);
     pdl_wait();
     pmat::length_prefetch(regs, op.len_left, op.len_right);
+    // every CTA streams one contiguous range of 8-row blocks (equal shares up to one block), in chunks of 128 rows
+    const int64_t nblk = np / kBlockRows, per_cta = (nblk + gridDim.x - 1) / gridDim.x;
+    const int64_t row_lo = min((long long)np, (long long)blockIdx.x * per_cta * kBlockRows);
+    const int64_t row_hi = min((long long)np, (long long)(row_lo + per_cta * kBlockRows));
     // the residue codes of the first chunk are requested right away; the table set-up below hides their latency
     uint8_t my_l = 0, my_r = 0;
-    if (tid < kTipTipRows && (int)blockIdx.x < nchunks) {
-        my_l = __ldg(op.left.codes + (int64_t)blockIdx.x * kTipTipRows + tid);
-        my_r = __ldg(op.right.codes + (int64_t)blockIdx.x * kTipTipRows + tid);
+    if (tid < kTipTipRows && row_lo + tid < row_hi) {
+        my_l = __ldg(op.left.codes + row_lo + tid);
+        my_r = __ldg(op.right.codes + row_lo + tid);
     }
     pmat::model_to_smem<kTipTipThreads>(regs, tid, sm.model);
     __syncthreads();
@@ -432,24 +437,24 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
         sm.flag[pair] = flag;
     }
     int buf = 0;
-    for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, buf ^= 1) {
-        const int64_t row0 = (int64_t)chunk * kTipTipRows;
-        if (tid < kTipTipRows) {
+    for (int64_t row0 = row_lo; row0 < row_hi; row0 += kTipTipRows, buf ^= 1) {
+        const int nrows = (int)min((long long)kTipTipRows, (long long)(row_hi - row0));
+        if (tid < nrows) {
             sm.pair[buf][tid][0] = my_l;
             sm.pair[buf][tid][1] = my_r;
         }
         __syncthreads();  // also covers sm.flag on the first trip; the other pair buffer is free for the next trip
-        if (tid < kTipTipRows) {
+        if (tid < nrows) {
             op.out_scale[row0 + tid] = sm.flag[my_l * kCodes + my_r];
-            const int next = chunk + gridDim.x;
-            if (next < nchunks) {  // the codes of the following chunk travel while this one is written
-                my_l = __ldg(op.left.codes + (int64_t)next * kTipTipRows + tid);
-                my_r = __ldg(op.right.codes + (int64_t)next * kTipTipRows + tid);
+            const int64_t next = row0 + kTipTipRows + tid;
+            if (next < row_hi) {  // the codes of the following chunk travel while this one is written
+                my_l = __ldg(op.left.codes + next);
+                my_r = __ldg(op.right.codes + next);
             }
         }
         double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
 #pragma unroll 4
-        for (int q = tid; q < kTipTipRows * (kRow / 2); q += kTipTipThreads) {
+        for (int q = tid; q < nrows * (kRow / 2); q += kTipTipThreads) {
             // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
             const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
             const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
@@ -496,8 +501,8 @@ void configure_mma_kernels() {
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
     const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr;
     if (tl && tr) {
-        const int nchunks = (int)(np / kTipTipRows);
-        launch_pdl(k_newview_tiptip, nchunks < sms ? nchunks : sms, kTipTipThreads, sizeof(TipTipSmem), stream, op, nchunks);
+        const int64_t nblk = np / kBlockRows;
+        launch_pdl(k_newview_tiptip, (int)(nblk < sms ? nblk : sms), kTipTipThreads, sizeof(TipTipSmem), stream, op, np);
     } else if (tl) launch_one<true, false>(op, np, sms, stream);
     else if (tr) launch_one<false, true>(op, np, sms, stream);
     else launch_one<false, false>(op, np, sms, stream);
