@@ -305,6 +305,7 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
         nv.right = t->side(op.child[1]);
         nv.len_left = t->d_len + op.cedge[0];
         nv.len_right = t->d_len + op.cedge[1];
+        nv.len_scale = 1.0;
         nv.dm = a->d_model;
         nv.out = t->clv(op.node);
         nv.out_scale = t->scale(op.node);
@@ -352,15 +353,23 @@ bool ensure_sumtable(pml_aln* a) {
 //   device_nr = true:  sums at the branch's length in the tree's device array, followed on the device by the guarded
 //               Newton-Raphson step that overwrites it (see Publish in kernels.h); len is ignored
 enum : int { kWantLnl = 1, kWantDerivs = 2, kWantAll = 3 };
+double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool keep_table,
+                           bool site_lnl, int want, bool device_nr);
 double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, int want, bool device_nr) {
-    pml_aln* a = t->aln;
-    pml_ctx* c = a->ctx;
-    if (keep_table && !ensure_sumtable(a)) return 0.0;
+    if (keep_table && !ensure_sumtable(t->aln)) return 0.0;
     int x, y;
     if (!orient_branch(t, e, x, y) || !sync_lengths(t)) return 0.0;
+    return branch_launch_sides(t, t->side(x), t->side(y), e, dw, len, keep_table, site_lnl, want, device_nr);
+}
+
+// the pass itself between two given sides (sb inner; sa inner or tip); e names the branch for device NR and book-keeping
+double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool keep_table,
+                           bool site_lnl, int want, bool device_nr) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
     BranchArgs args{};
-    args.a = t->side(x);
-    args.b = t->side(y);
+    args.a = sa;
+    args.b = sb;
     args.dm = a->d_model;
     args.weights = dw;
     args.t = len;
@@ -691,16 +700,36 @@ bool polish_branch(pml_tree* t, int e, const int32_t* dw, int iters) {
     return true;
 }
 
-// Lazy scores of a list of regraft targets for the pruned (p, s): every candidate is applied, queued (CLV updates + one branch
-// pass at the subtree's branch) and undone on the host WITHOUT waiting for its lnL; the outcomes are collected from the result
-// ring a few candidates later, so the device never idles between candidates.  out[i] = lnL (or -inf when the move is illegal).
+// Lazy scores of a list of regraft targets for the pruned (p, s) (raxmlHPC rearrangeBIG / testInsertBIG without NR).
+// The subtree is pruned ONCE; the remaining tree keeps its topology and its valid views while the regraft points are
+// visited.  A candidate is a *virtual* insertion: orient the target branch (a, b) on the pruned tree (moving to a
+// neighbouring target costs about one CLV update, as in a smoothing sweep), one CLV update for p from the two directed views
+// of that branch with half its length on either side, and one branch pass between p and the subtree's root at the subtree
+// branch's own length.  Nothing waits for a candidate's lnL: outcomes are collected from the result ring a few candidates
+// later.  out[i] = lnL (or -inf when the move is illegal).
 bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets, const int32_t* dw, std::vector<double>& out) {
-    pml_ctx* c = t->aln->ctx;
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
     Topology& T = t->topo;
     out.assign(targets.size(), -std::numeric_limits<double>::infinity());
+    if (targets.empty() || T.is_tip(p)) return true;
+    // the subtree's own view towards p is taken on the intact tree
+    {
+        std::vector<ViewOp> ops;
+        t->views.plan(T, s, p, ops);
+        if (!run_ops(t, ops)) return false;
+    }
+    SprMove mv;
+    if (!spr_prune(T, t->views, p, s, mv)) return true;
+    t->prepared_branch = -1;
+    const double len_s = T.len[mv.e_s];
+    Side side_p{};
+    side_p.clv = t->clv(p);
+    side_p.scale = t->scale(p);
     constexpr size_t kLag = pml_ctx::kRing - 2;
     std::vector<std::pair<double, size_t>> queued;  // (sequence number, candidate index)
     size_t head = 0;
+    bool ok = true;
     auto collect = [&](size_t upto) {
         for (; head < upto; ++head) {
             double r[5];
@@ -709,18 +738,40 @@ bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets
         }
         return true;
     };
-    for (size_t i = 0; i < targets.size(); ++i) {
-        SprMove mv;
-        if (!spr_apply(T, t->views, p, s, targets[i], mv)) continue;
-        t->prepared_branch = -1;
-        const double seq = branch_launch(t, mv.e_s, dw, T.len[mv.e_s], false, false, kWantLnl, false);
-        spr_undo(T, t->views, mv);
-        t->prepared_branch = -1;
-        if (seq == 0.0) return false;
+    for (size_t i = 0; ok && i < targets.size(); ++i) {
+        const int e = targets[i];
+        if (e == mv.e_q || e == mv.e_r || e == mv.e_s) continue;  // would put p back where it was
+        int x, y;
+        if (!orient_branch(t, e, x, y)) {  // both directed views of the target branch, on the pruned tree
+            ok = false;
+            break;
+        }
+        NewviewOp nv{};
+        nv.left = t->side(x);
+        nv.right = t->side(y);
+        nv.len_left = nv.len_right = t->d_len + e;
+        nv.len_scale = 0.5;
+        nv.dm = a->d_model;
+        nv.out = t->clv(p);
+        nv.out_scale = t->scale(p);
+        const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+        const int tk = c->tick(2 - ntip, a->nloc);
+        launch_newview_mma(nv, a->npad, c->sms, c->stream);
+        c->tock(tk);
+        ++t->launches;
+        t->site_updates[2 - ntip] += a->nloc;
+        const double seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, kWantLnl, false);
+        if (seq == 0.0) {
+            ok = false;
+            break;
+        }
         queued.push_back({seq, i});
-        if (queued.size() - head > kLag && !collect(queued.size() - kLag)) return false;
+        if (queued.size() - head > kLag && !collect(queued.size() - kLag)) ok = false;
     }
-    return collect(queued.size());
+    ok = collect(queued.size()) && ok;
+    spr_unprune(T, t->views, mv);
+    t->prepared_branch = -1;
+    return ok;
 }
 
 struct SearchStats {

@@ -754,6 +754,59 @@ bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv)
     return true;
 }
 
+bool spr_prune(Topology& T, ViewState& V, int p, int s, SprMove& mv) {
+    if (T.is_tip(p)) return false;
+    mv = SprMove();
+    mv.p = p;
+    mv.s = s;
+    for (int k = 0; k < 3; ++k) {
+        const int nb = T.nbr[p][k];
+        if (nb == s) mv.e_s = T.edge[p][k];
+        else if (mv.q < 0) {
+            mv.q = nb;
+            mv.e_q = T.edge[p][k];
+            mv.slot_q = k;
+        } else {
+            mv.r = nb;
+            mv.e_r = T.edge[p][k];
+            mv.slot_r = k;
+        }
+    }
+    if (mv.e_s < 0 || mv.r < 0) return false;
+    mv.len_q = T.len[mv.e_q];
+    mv.len_r = T.len[mv.e_r];
+    // q -- r through branch e_q; p keeps only its link to s, branch e_r is parked
+    set_link(T, mv.q, p, mv.r, mv.e_q);
+    set_link(T, mv.r, p, mv.q, mv.e_q);
+    T.ea[mv.e_q] = mv.q;
+    T.eb[mv.e_q] = mv.r;
+    T.len[mv.e_q] = mv.len_q + mv.len_r;
+    T.nbr[p][mv.slot_q] = T.nbr[p][mv.slot_r] = -1;
+    V.orient[p - T.ntax] = -1;
+    V.branch_changed(T, mv.e_q);
+    return true;
+}
+
+void spr_unprune(Topology& T, ViewState& V, const SprMove& mv) {
+    const int p = mv.p;
+    set_link(T, mv.q, mv.r, p, mv.e_q);
+    set_link(T, mv.r, mv.q, p, mv.e_r);
+    T.nbr[p][mv.slot_q] = mv.q;
+    T.edge[p][mv.slot_q] = mv.e_q;
+    T.nbr[p][mv.slot_r] = mv.r;
+    T.edge[p][mv.slot_r] = mv.e_r;
+    T.ea[mv.e_q] = p;
+    T.eb[mv.e_q] = mv.q;
+    T.ea[mv.e_r] = p;
+    T.eb[mv.e_r] = mv.r;
+    T.len[mv.e_q] = mv.len_q;
+    T.len[mv.e_r] = mv.len_r;
+    V.orient[p - T.ntax] = -1;
+    // views computed on the pruned tree that look across the place where p belongs lack the subtree behind s
+    V.branch_changed(T, mv.e_q);
+    V.branch_changed(T, mv.e_r);
+}
+
 void spr_undo(Topology& T, ViewState& V, const SprMove& mv) {
     const int p = mv.p;
     // detach from a, b

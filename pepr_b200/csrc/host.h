@@ -88,6 +88,11 @@ struct SprMove {
 };
 bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv);
 void spr_undo(Topology& T, ViewState& V, const SprMove& mv);
+// Pruned state for a scan over regraft points: p (with the subtree behind s) is detached, q -- r joined (lengths added), and
+// the remaining tree stays put while candidates are scored by a virtual insertion (engine.cu: score_candidates).  Only
+// traversal planning and branch orientation may be used on the tree until spr_unprune has restored it.
+bool spr_prune(Topology& T, ViewState& V, int p, int s, SprMove& mv);
+void spr_unprune(Topology& T, ViewState& V, const SprMove& mv);
 // branches of the tree that remains after pruning (p, s), at 1..radius steps from the pruning point, excluding the subtree
 // behind s and the two branches next to p (re-inserting there gives the same topology)
 std::vector<int> spr_targets(const Topology& T, int p, int s, int radius);

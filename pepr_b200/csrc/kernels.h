@@ -31,6 +31,7 @@ struct NewviewOp {
     Side left, right;
     const double* len_left;   // the two branch lengths, read on the device (tree's length array)
     const double* len_right;
+    double len_scale;         // both lengths are multiplied by this (1; 0.5 for the halves of a branch a subtree is inserted into)
     const DeviceModel* dm;
     double* out;
     int32_t* out_scale;
