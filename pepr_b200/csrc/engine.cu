@@ -108,6 +108,7 @@ struct pml_ctx {
     long long* d_trace_buf = nullptr;
     long long* d_trace_branch = nullptr;
     bool trace_branch_tip = false;
+    int trace_newview_tips = -1;  // -1: every CLV kernel, 0 / 1: only those with that many tip children
     bool profiling = false;
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> spare_events;
@@ -309,8 +310,8 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
         nv.dm = a->d_model;
         nv.out = t->clv(op.node);
         nv.out_scale = t->scale(op.node);
-        nv.trace = c->d_trace;
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+        nv.trace = (c->trace_newview_tips < 0 || c->trace_newview_tips == ntip) ? c->d_trace : nullptr;
         const int tk = c->tick(2 - ntip, a->nloc);
         launch_newview_mma(nv, a->npad, c->sms, c->stream);
         c->tock(tk);
@@ -983,7 +984,8 @@ int pml_trace_enable(pml_ctx* c, int on) {
         if (!c->cuda(cudaMalloc(&c->d_trace_buf, 96 * sizeof(long long)), "trace alloc")) return PML_ENOMEM;
     }
     if (c->d_trace_buf) cudaMemset(c->d_trace_buf, 0, 96 * sizeof(long long));
-    c->d_trace = on == 1 ? c->d_trace_buf : nullptr;
+    c->d_trace = (on == 1 || on == 4 || on == 5) ? c->d_trace_buf : nullptr;
+    c->trace_newview_tips = on == 4 ? 1 : (on == 5 ? 0 : -1);
     c->d_trace_branch = on >= 2 ? c->d_trace_buf : nullptr;
     c->trace_branch_tip = on == 3;
     return PML_OK;
@@ -1048,7 +1050,7 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
     if (!c->bind()) return PML_ENODEVICE;
     auto a = std::make_unique<pml_aln>();
     a->ctx = c;
-    crunch_patterns(ntax, nsites, chars, site_weights, a->pat);
+    crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks);  // codes of this rank's block only
     for (int i = 0; i < ntax; ++i) a->pat.names.emplace_back(names[i]);
     if (a->pat.npat == 0) return fail(c, PML_EINVAL, "alignment has no column with positive weight");
     const int64_t np = a->pat.npat;
@@ -1058,7 +1060,7 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
     // device copies of this rank's slice; padded rows are "undetermined" with weight 0
     std::vector<uint8_t> hc((size_t)ntax * a->npad, 22);
     for (int t = 0; t < ntax; ++t)
-        std::memcpy(hc.data() + (size_t)t * a->npad, a->pat.codes.data() + (size_t)t * np + a->p0, a->nloc);
+        std::memcpy(hc.data() + (size_t)t * a->npad, a->pat.codes.data() + (size_t)t * a->pat.codes_n, a->nloc);
     std::vector<int32_t> hw(a->npad, 0);
     std::copy(a->pat.weight.begin() + a->p0, a->pat.weight.begin() + a->p0 + a->nloc, hw.begin());
     bool ok = c->cuda(c->dev_alloc(&a->d_codes, hc.size()), "codes alloc") &&

@@ -112,7 +112,7 @@ struct ColumnSorter {
 
 }  // namespace
 
-void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out) {
+void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank, int nranks) {
     out.ntax = ntax;
     out.nsites = nsites;
     ColumnSorter cs{ntax, nsites, chars, {}};
@@ -181,20 +181,21 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
     });
     out.npat = (int64_t)first.size();
     lap("weights");
-    out.codes.assign((size_t)ntax * out.npat, 22);
-    // gather of the representatives' codes, two taxon rows per pass over the (32-bit) column list: the pass is bound by
-    // streaming that list, the rows themselves stay cache resident
+    out.codes_p0 = out.npat * rank / nranks;
+    out.codes_n = out.npat * (rank + 1) / nranks - out.codes_p0;
+    out.codes.assign((size_t)ntax * out.codes_n, 22);
+    // gather of the representatives' codes, two taxon rows per pass over the (32-bit) column list
     std::vector<uint32_t> first32;
     const bool narrow = nsites < (int64_t)1 << 32;
-    if (narrow) first32.assign(first.begin(), first.end());
+    if (narrow) first32.assign(first.begin() + out.codes_p0, first.begin() + out.codes_p0 + out.codes_n);
     parallel_for((ntax + 1) / 2, threads, [&](int64_t pair) {
         const int t0r = (int)(2 * pair), t1r = std::min(ntax - 1, t0r + 1);
         const uint8_t* row0 = chars + (size_t)t0r * nsites;
         const uint8_t* row1 = chars + (size_t)t1r * nsites;
-        uint8_t* dst0 = out.codes.data() + (size_t)t0r * out.npat;
-        uint8_t* dst1 = out.codes.data() + (size_t)t1r * out.npat;
-        for (int64_t p = 0; p < out.npat; ++p) {
-            const size_t s = narrow ? (size_t)first32[p] : (size_t)first[p];
+        uint8_t* dst0 = out.codes.data() + (size_t)t0r * out.codes_n;
+        uint8_t* dst1 = out.codes.data() + (size_t)t1r * out.codes_n;
+        for (int64_t p = 0; p < out.codes_n; ++p) {
+            const size_t s = narrow ? (size_t)first32[p] : (size_t)first[out.codes_p0 + p];
             dst0[p] = cs.lut[row0[s]];
             dst1[p] = cs.lut[row1[s]];
         }
@@ -867,7 +868,7 @@ namespace {
 struct HostParsimony {
     const Patterns& pat;
     std::vector<std::vector<uint32_t>> tipmask, down, up;
-    explicit HostParsimony(const Patterns& p) : pat(p), tipmask(p.ntax, std::vector<uint32_t>((size_t)p.npat)) {
+    explicit HostParsimony(const Patterns& p) : pat(p), tipmask(p.ntax, std::vector<uint32_t>((size_t)p.npat)) {  // needs all codes
         for (int t = 0; t < pat.ntax; ++t)
             for (int64_t s = 0; s < pat.npat; ++s) tipmask[t][s] = parsimony_code_mask(pat.codes[(size_t)t * pat.npat + s]);
     }

@@ -15,12 +15,15 @@ struct Patterns {
     int ntax = 0;
     int64_t nsites = 0, npat = 0;
     std::vector<std::string> names;
-    std::vector<uint8_t> codes;        // ntax x npat, row-major: residue codes of each pattern
+    std::vector<uint8_t> codes;        // ntax x codes_n, row-major: residue codes of patterns [codes_p0, codes_p0 + codes_n)
+    int64_t codes_p0 = 0, codes_n = 0; // (all patterns unless a rank asked for its own block only)
     std::vector<int32_t> weight;       // npat
     std::vector<int64_t> site_to_pat;  // nsites, -1 for dropped columns
 };
 // column sort + duplicate merge in the reference's order (raxmlHPC sitesort/sitecombcrunch: lexicographic by taxon row)
-void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out);
+// rank / nranks: keep the residue codes of that rank's contiguous pattern block only (the sort itself is always global)
+void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank = 0,
+                     int nranks = 1);
 bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,
                  std::string& err);
 

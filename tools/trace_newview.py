@@ -18,7 +18,7 @@ tree.evaluate()
 L = pb.lib()
 L.pml_trace_enable.argtypes = [C.c_void_p, C.c_int]
 L.pml_trace_read.argtypes = [C.c_void_p, C.c_void_p]
-L.pml_trace_enable(ctx.h, 1)
+L.pml_trace_enable(ctx.h, int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 for _ in range(3):
     tree.invalidate()
     tree.evaluate()
