@@ -216,7 +216,6 @@ struct pml_aln {
     double* d_site_lnl = nullptr;
     double* d_partials = nullptr;
     double* d_result = nullptr;  // 16 doubles
-    double* d_scalar = nullptr;  // branch length handed to the NR core
     unsigned int* d_ticket = nullptr;
     double* d_sumtable = nullptr;
     int32_t* d_sumscale = nullptr;
@@ -1070,7 +1069,6 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
               c->cuda(c->dev_alloc(&a->d_site_lnl, sizeof(double) * a->npad), "site lnl alloc") &&
               c->cuda(c->dev_alloc(&a->d_partials, sizeof(double) * reduce_partials_capacity(a->npad)), "partials alloc") &&
               c->cuda(c->dev_alloc(&a->d_result, sizeof(double) * 16), "result alloc") &&
-              c->cuda(c->dev_alloc(&a->d_scalar, sizeof(double) * 8), "scalar alloc") &&
               c->cuda(c->dev_alloc(&a->d_ticket, 64), "ticket alloc") &&
               c->cuda(cudaMemset(a->d_ticket, 0, 64), "ticket clear") &&
               c->cuda(cudaMemcpy(a->d_codes, hc.data(), hc.size(), cudaMemcpyHostToDevice), "codes upload") &&
@@ -1114,7 +1112,6 @@ void pml_aln_free(pml_aln* a) {
     a->ctx->dev_free(a->d_site_lnl);
     a->ctx->dev_free(a->d_partials);
     a->ctx->dev_free(a->d_result);
-    a->ctx->dev_free(a->d_scalar);
     a->ctx->dev_free(a->d_ticket);
     a->ctx->dev_free(a->d_sumtable);
     a->ctx->dev_free(a->d_sumscale);

@@ -129,10 +129,6 @@ void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* s
     k_reduce<<<1, 1024, 0, stream>>>(partials, grid, 3, result);
 }
 
-void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream) {
-    k_reduce<<<1, 1024, 0, stream>>>(partials, nblocks, nvals, result);
-}
-
 void launch_replicate_lnl(const int32_t* W, int nrep, int64_t np, int64_t ldw, const double* site_lnl, double* lnl,
                           cudaStream_t stream) {
     if (nrep > 0) k_replicate_lnl<<<nrep, 256, 0, stream>>>(W, np, ldw, site_lnl, lnl);

@@ -185,8 +185,6 @@ void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t
 void configure_branch_kernels();
 // NR step + publication from result[0..3] (after the allreduce of result[0..2] when ranks > 1)
 void launch_publish(const double* result, const Publish& pub, cudaStream_t stream);
-// fixed-order sum of `nblocks` partials for each of `nvals` values
-void launch_reduce(const double* partials, int nblocks, int nvals, double* result, cudaStream_t stream);
 
 // result[0..2] = lnL, dlnL/dt, d2lnL/dt2 at branch length *d_t (device scalar) from a sumtable
 void launch_core(const DeviceModel* dm, const double* sumtable, const int32_t* sum_scale, const int32_t* weights, int64_t np, double t,
