@@ -2,7 +2,7 @@
 
 It keeps the method names, argument meaning and error behaviour of
   edu.vt.vbi.ci.pepr.tree.RAxMLRunner           (src/edu/vt/vbi/ci/pepr/tree/RAxMLRunner.java)
-  edu.vt.vbi.ci.pepr.tree.FastTreeRunner        (.../FastTreeRunner.java:142-199, getRaxmlBranchLengths)
+  edu.vt.vbi.ci.pepr.tree.FastTreeRunner        (.../FastTreeRunner.java:38-135 run, :142-199 getRaxmlBranchLengths)
   edu.vt.vbi.ci.pepr.tree.TreeSupportDecorator  (.../TreeSupportDecorator.java:86-163)
 so that the parity tests read like calls PEPR itself makes.  The Java twin (`B200MLRunner`) binds the
 same C entry points through JNI / Panama; no JDK exists in this image, so this Python class is the executable mirror.
@@ -228,6 +228,68 @@ class B200MLRunner:
         if self._own_ctx and self.ctx is not None:
             self.ctx.close()
             self.ctx = None
+
+
+class B200FastTreeRunner:
+    """drop-in for FastTreeRunner (FastTreeRunner.java:38-135), the tool PEPR calls ~100 times per refinement round for
+    its support trees: `FastTree_WAG -gamma -nosupport X.faa` (newick on stdout), `-gamma` with local supports x 100
+    truncated to integers when bootstrapReps > 0, optionally followed by raxmlHPC `-f e` branch lengths
+    (getRaxmlBranchLengths, :142-199).  Here the tree comes from the engine's own ML search (parsimony start tree, lazy
+    SPR, WAG+G4 branch lengths -- so it always carries `-f e` quality lengths), supports are replicate percentages.
+    FastTree's CAT/ME heuristics are not reproduced: trees are compared by their splits (tests/test_gpu_search.py).
+    Refused loudly, not ignored: topological constraints (`-constraints`) and nucleotide alignments (`-gtr -nt`)."""
+
+    def __init__(self, gpu=0, ctx=None, strict=False):
+        self._ml = B200MLRunner(gpu=gpu, ctx=ctx, strict=strict)
+        self.alignment, self.constraints, self.bootstrap_reps = None, None, 0
+        self.use_raxml_branch_lengths, self.thread_count, self.nucleotide = False, 1, False
+        self.result, self.last_error, self.strict = None, None, strict
+
+    def setAlignment(self, alignment):
+        self.alignment = alignment
+
+    def setConstraints(self, constraints):
+        self.constraints = constraints
+
+    def setBootstrapReps(self, n):
+        self.bootstrap_reps = int(n)
+
+    def setUseRaxmlBranchLengths(self, flag):
+        self.use_raxml_branch_lengths = bool(flag)
+
+    def setThreadCount(self, n):
+        self.thread_count = int(n)
+
+    def setNucleotide(self, flag):
+        self.nucleotide = bool(flag)
+
+    def run(self):
+        self.result, self.last_error = None, None
+        if self.constraints is not None or self.nucleotide:
+            self.last_error = "B200FastTreeRunner: constraints / nucleotide alignments are not supported by the engine"
+            logger.error(self.last_error)
+            if self.strict:
+                raise _e.EngineError(self.last_error)
+            return
+        self._ml.setAlignment(self.alignment)
+        self._ml.setBootstrapReps(self.bootstrap_reps)
+        self._ml.algorithm = ML_ALGORITHM
+        self._ml.start_tree = None
+        self._ml.run()
+        if self._ml.last_error is not None:
+            self.last_error = self._ml.last_error   # reference convention: logged, result stays null
+            return
+        self.tree_options = "peprml search -m PROTGAMMAWAG" + ("" if self.bootstrap_reps else " -nosupport")
+        self.result = self._ml.getBestTreeWithSupports() if self.bootstrap_reps > 0 else self._ml.getBestTree()
+
+    def getResult(self):
+        return self.result
+
+    def getLikelihood(self):
+        return self._ml.getLikelihood()
+
+    def close(self):
+        self._ml.close()
 
 
 class TreeSupportDecorator:

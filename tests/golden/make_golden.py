@@ -212,6 +212,34 @@ def case_search(d):
 
 CASES["search"] = case_search
 
+FASTTREE = "/root/reference/pepr-bin_linux/FastTree_WAG"
+
+
+def case_search_fasttree(d):
+    """adds FastTree_WAG's trees for the `search` alignment (FastTreeRunner.run: `-gamma -nosupport`, and `-gamma` when
+    bootstrapReps > 0; FastTreeRunner.java:66-94) to search.json without touching the raxmlHPC entries"""
+    toks = gzip.open(os.path.join(d, "search.phy.gz"), "rt").read().split()
+    n = int(toks[0])
+    names, seqs = toks[2::2][:n], toks[3::2][:n]
+    tmp = tempfile.mkdtemp()
+    with open(os.path.join(tmp, "s.faa"), "w") as f:
+        for a, b in zip(names, seqs):
+            f.write(">%s\n%s\n" % (a, b))
+    g = json.load(open(os.path.join(d, "search.json")))
+    out = {}
+    for key, extra in (("tree", ["-nosupport"]), ("tree_support", [])):
+        r = subprocess.run([FASTTREE, "-gamma"] + extra + ["s.faa"], cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        out[key] = r.stdout.strip().splitlines()[0]
+        m = re.search(r"Gamma\(20\) LogLk = (\S+) alpha = (\S+)", r.stderr)
+        out["gamma20_loglk"], out["alpha"] = float(m.group(1)), float(m.group(2))
+    g["fasttree"] = out
+    json.dump(g, open(os.path.join(d, "search.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+
+
+CASES["search_fasttree"] = case_search_fasttree
+
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)

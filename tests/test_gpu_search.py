@@ -120,3 +120,23 @@ def test_runner_f_d_and_f_a(gpu_ctx, golden):
     # the data carry strong signal: raxmlHPC's own rapid bootstrap gives (nearly) full support, so must the replicates here
     ref = [int(x) for x in re.findall(r"\)(\d+)", g.meta["fa"]["bipartitions"])]
     assert np.mean(labels) >= np.mean(ref) - 15
+
+
+def test_fasttree_runner_mirror_gives_fasttrees_tree(gpu_ctx, golden):
+    """FastTreeRunner.run (FastTreeRunner.java:38-135) served by the engine: same splits as the bundled FastTree_WAG found
+    (golden made by running the reference binary), supports as integer percentages, unsupported options refused loudly"""
+    g = golden("search")
+    ft = g.meta["fasttree"]
+    r = R.B200FastTreeRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r.run()
+    assert r.last_error is None and r.getResult()
+    assert _splits(_strip(r.getResult())) == _splits(_strip(re.sub(r"\)[0-9.]+", ")", ft["tree"])))
+    r.setBootstrapReps(4)
+    r.setUseRaxmlBranchLengths(True)
+    r.run()
+    labels = [int(x) for x in re.findall(r"\)(\d+)", r.getResult())]
+    assert len(labels) == len(g.names) - 3 and all(0 <= v <= 100 for v in labels)
+    r.setConstraints("((T0000,T0001),T0002);")
+    r.run()
+    assert r.getResult() is None and "not supported" in r.last_error
