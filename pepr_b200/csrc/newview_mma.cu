@@ -375,6 +375,8 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
     pmat::ModelRegs regs = pmat::model_prefetch<kTipTipThreads>(op.dm, tid);
     pdl_wait();
     pmat::length_prefetch(regs, op.len_left, op.len_right);
+    regs.len[0] *= op.len_scale;
+    regs.len[1] *= op.len_scale;
     // every CTA streams one contiguous range of 8-row blocks (equal shares up to one block), in chunks of 128 rows
     const int64_t nblk = np / kBlockRows, per_cta = (nblk + gridDim.x - 1) / gridDim.x;
     const int64_t row_lo = min((long long)np, (long long)blockIdx.x * per_cta * kBlockRows);
