@@ -348,7 +348,8 @@ def main():
         dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
     e2e_value = e_s.item() / e_t.item()
     # device -> host: every branch pass publishes five (value, seq) pairs (80 B) through mapped memory; + the result tree
-    npass = sum(prof[k][1] for k in ("evaluate", "branch_inner_inner", "branch_tip_inner", "core")) / args.steps
+    npass = sum(prof[k][1] for k in ("evaluate", "branch_inner_inner", "branch_tip_inner", "core", "fused_update_branch_inner",
+                                     "fused_update_branch_tip")) / args.steps
     d2h = int(80 * npass + nwlen)
 
     if rank == 0:
@@ -363,8 +364,9 @@ def main():
         kernels = {}
         for name, (kms_, kn_, krows_) in prof.items():
             if kn_:
-                kernels[name] = {"launches_per_step": kn_ / args.steps, "ms_per_step": kms_ / args.steps,
-                                 "avg_launch_us": 1e3 * kms_ / kn_, "GBps": BYTES[name] * krows_ / (kms_ * 1e-3) / 1e9}
+                kernels[name] = {"launches_per_step": kn_ / args.steps, "ms_per_step": kms_ / args.steps, "avg_launch_us": 1e3 * kms_ / kn_}
+                if name in BYTES:
+                    kernels[name]["GBps"] = BYTES[name] * krows_ / (kms_ * 1e-3) / 1e9
                 if name in FLOP_PER_PATTERN:   # issued FP64 tensor flops (24-wide padding included) against the measured 37.0 TFLOP/s
                     kernels[name]["dmma_TFLOPs"] = FLOP_PER_PATTERN[name] * krows_ / (kms_ * 1e-3) / 1e12
                     kernels[name]["dmma_frac_of_37.0"] = kernels[name]["dmma_TFLOPs"] / 37.0

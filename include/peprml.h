@@ -112,8 +112,9 @@ int64_t pml_tree_nr_retries(const pml_tree *);
  * Between begin and end every launch of kind k is bracketed by a pair of events; end() synchronises and returns, per
  * kind, the summed device milliseconds, the launch count and the pattern rows processed.
  * kinds: 0 newview tip-tip, 1 newview tip-inner, 2 newview inner-inner, 3 root evaluate (branch pass with per-pattern lnL),
- * 4 branch pass between two inner nodes, 5 NR core on a stored table, 6 branch pass with a tip end. */
-#define PML_NKINDS 7
+ * 4 branch pass between two inner nodes, 5 NR core on a stored table, 6 branch pass with a tip end,
+ * 7 / 8 fused CLV update + branch pass with an inner / a tip far end. */
+#define PML_NKINDS 9
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpeprml.so")
 CLI = os.path.join(HERE, "bin", "peprml")
-SOURCES = ["model.cpp", "host.cpp", "kernels.cu", "newview_mma.cu", "branch_mma.cu", "parsimony.cu", "engine.cu"]
+SOURCES = ["model.cpp", "host.cpp", "kernels.cu", "newview_mma.cu", "branch_mma.cu", "fused_mma.cu", "parsimony.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "-I", os.path.join(HERE, "..", "include")]

@@ -80,6 +80,7 @@ struct pml_ctx {
     double** d_mail_ptrs = nullptr;
     std::vector<void*> peer_opened;
     bool peer_ok = false;
+    bool fuse = true;      // PEPRML_NO_FUSE=1: CLV update and branch pass always as two launches (reference mode for tests)
     bool host_nr = false;  // PEPRML_HOST_NR=1: Newton-Raphson steps on the host, one wait per branch (reference mode for tests)
     volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     double* slot_dev(double seq) const { return d_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
@@ -294,21 +295,26 @@ bool sync_lengths(pml_tree* t) {
     return true;
 }
 
+NewviewOp make_newview_op(pml_tree* t, const ViewOp& op) {
+    NewviewOp nv{};
+    nv.left = t->side(op.child[0]);
+    nv.right = t->side(op.child[1]);
+    nv.len_left = t->d_len + op.cedge[0];
+    nv.len_right = t->d_len + op.cedge[1];
+    nv.len_scale = 1.0;
+    nv.dm = t->aln->d_model;
+    nv.out = t->clv(op.node);
+    nv.out_scale = t->scale(op.node);
+    return nv;
+}
+
 // executes a traversal descriptor: one CLV kernel per entry; each builds its own P matrices from the device lengths
 bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     if (!sync_lengths(t)) return false;
     for (const ViewOp& op : ops) {
-        NewviewOp nv{};
-        nv.left = t->side(op.child[0]);
-        nv.right = t->side(op.child[1]);
-        nv.len_left = t->d_len + op.cedge[0];
-        nv.len_right = t->d_len + op.cedge[1];
-        nv.len_scale = 1.0;
-        nv.dm = a->d_model;
-        nv.out = t->clv(op.node);
-        nv.out_scale = t->scale(op.node);
+        NewviewOp nv = make_newview_op(t, op);
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
         nv.trace = (c->trace_newview_tips < 0 || c->trace_newview_tips == ntip) ? c->d_trace : nullptr;
         const int tk = c->tick(2 - ntip, a->nloc);
@@ -353,18 +359,41 @@ bool ensure_sumtable(pml_aln* a) {
 //   device_nr = true:  sums at the branch's length in the tree's device array, followed on the device by the guarded
 //               Newton-Raphson step that overwrites it (see Publish in kernels.h); len is ignored
 enum : int { kWantLnl = 1, kWantDerivs = 2, kWantAll = 3 };
-double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool keep_table,
-                           bool site_lnl, int want, bool device_nr);
+double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool fused,
+                           bool keep_table, bool site_lnl, int want, bool device_nr, const NewviewOp* nv = nullptr);
 double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, int want, bool device_nr) {
     if (keep_table && !ensure_sumtable(t->aln)) return 0.0;
-    int x, y;
-    if (!orient_branch(t, e, x, y) || !sync_lengths(t)) return 0.0;
-    return branch_launch_sides(t, t->side(x), t->side(y), e, dw, len, keep_table, site_lnl, want, device_nr);
+    pml_ctx* c = t->aln->ctx;
+    int x = t->topo.ea[e], y = t->topo.eb[e];
+    if (t->topo.is_tip(y)) std::swap(x, y);
+    std::vector<ViewOp> ops;
+    t->views.plan(t->topo, x, y, ops);
+    t->views.plan(t->topo, y, x, ops);
+    // The last CLV update of the visit produces one end of this very branch: update and pass go out as ONE launch
+    // (fused_mma.cu) unless the product table is wanted or both children of that node are tips.
+    const bool fuse = c->fuse && !keep_table && !ops.empty() &&
+                      !(t->topo.is_tip(ops.back().child[0]) && t->topo.is_tip(ops.back().child[1]));
+    if (!fuse) {
+        if (!run_ops(t, ops) || !sync_lengths(t)) return 0.0;
+        return branch_launch_sides(t, t->side(x), t->side(y), e, dw, len, false, keep_table, site_lnl, want, device_nr);
+    }
+    const ViewOp last = ops.back();
+    ops.pop_back();
+    if (!run_ops(t, ops) || !sync_lengths(t)) return 0.0;
+    const int far = last.node == x ? y : x;
+    const NewviewOp nv = make_newview_op(t, last);
+    const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+    t->site_updates[2 - ntip] += t->aln->nloc;
+    Side sx{};
+    sx.clv = nv.out;
+    sx.scale = nv.out_scale;
+    return branch_launch_sides(t, t->side(far), sx, e, dw, len, true, false, site_lnl, want, device_nr, &nv);
 }
 
-// the pass itself between two given sides (sb inner; sa inner or tip); e names the branch for device NR and book-keeping
-double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool keep_table,
-                           bool site_lnl, int want, bool device_nr) {
+// the pass itself between two given sides (sb inner; sa inner or tip); e names the branch for device NR and book-keeping;
+// fused: sb is what the CLV update *nv is about to produce, both go out as one launch
+double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool fused,
+                           bool keep_table, bool site_lnl, int want, bool device_nr, const NewviewOp* nv) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     BranchArgs args{};
@@ -393,8 +422,9 @@ double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, c
     const bool in_kernel = c->nranks == 1 || c->peer_ok;
     if (in_kernel) args.pub = pub;
     if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks};
-    const int tk = c->tick(site_lnl ? 3 : (args.a.clv ? 4 : 6), a->nloc);
-    launch_branch_mma(args, a->npad, c->sms, c->stream);
+    const int tk = c->tick(fused ? (args.a.clv ? 7 : 8) : (site_lnl ? 3 : (args.a.clv ? 4 : 6)), a->nloc);
+    if (fused) launch_fused(*nv, args, a->npad, c->sms, c->stream);
+    else launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
@@ -760,7 +790,7 @@ bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets
         c->tock(tk);
         ++t->launches;
         t->site_updates[2 - ntip] += a->nloc;
-        const double seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, kWantLnl, false);
+        const double seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, false, kWantLnl, false);
         if (seq == 0.0) {
             ok = false;
             break;
@@ -917,6 +947,7 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     auto c = std::make_unique<pml_ctx>();
     c->device = gpu_id;
     c->host_nr = getenv("PEPRML_HOST_NR") != nullptr;
+    c->fuse = getenv("PEPRML_NO_FUSE") == nullptr;
     c->rank = rank;
     c->nranks = nranks;
     if (!c->bind() || !c->cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create"))
@@ -924,6 +955,7 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
     cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, gpu_id);
     configure_mma_kernels();
     configure_branch_kernels();
+    configure_fused_kernels();
     c->stage_cap = 1 << 20;
     if (!c->cuda(cudaMallocHost(&c->h_stage, c->stage_cap), "pinned alloc") ||
         !c->cuda(cudaMallocHost(&c->h_result, 4096), "pinned alloc") ||

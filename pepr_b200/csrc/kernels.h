@@ -183,6 +183,10 @@ struct BranchArgs {
 };
 void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
 void configure_branch_kernels();
+// fused_mma.cu: the CLV update `op` (at least one inner child) and the branch pass between its result (the x end) and
+// args.a (the y end, inner or tip) in one launch; args.b is ignored, args.sumtable must be null
+void launch_fused(const NewviewOp& op, const BranchArgs& args, int64_t np, int sms, cudaStream_t stream);
+void configure_fused_kernels();
 // NR step + publication from result[0..3] (after the allreduce of result[0..2] when ranks > 1)
 void launch_publish(const double* result, const Publish& pub, cudaStream_t stream);
 

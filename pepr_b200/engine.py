@@ -135,11 +135,11 @@ class Context:
 
     def profile_end(self):
         """-> dict kind -> (device ms, launches, pattern rows)"""
-        ms = (C.c_double * 7)()
-        n = (C.c_int64 * 7)()
-        rows = (C.c_int64 * 7)()
+        ms = (C.c_double * 9)()
+        n = (C.c_int64 * 9)()
+        rows = (C.c_int64 * 9)()
         self.check(lib().pml_profile_end(self.h, ms, n, rows), "pml_profile_end")
-        kinds = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "branch_inner_inner", "core", "branch_tip_inner"]
+        kinds = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "branch_inner_inner", "core", "branch_tip_inner", "fused_update_branch_inner", "fused_update_branch_tip"]
         return {k: (ms[i], n[i], rows[i]) for i, k in enumerate(kinds)}
 
     def close(self):

@@ -192,3 +192,42 @@ def test_pipelined_smoothing_equals_host_reference_mode(golden, case):
         aln.close(); ctx.close()
     assert retries["device"] == retries["host"] and retries["device"] > 0, retries
     assert np.allclose(results["device"], results["host"], rtol=1e-8, atol=1e-12), np.abs(results["device"] - results["host"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["small", "deep", "wide"])
+def test_fused_update_and_branch_pass_equals_two_launches(golden, case):
+    """fused_mma.cu (last CLV update of a branch visit + the pass over that branch in one launch) against the same work as
+    two launches (PEPRML_NO_FUSE=1): per-site lnL, smoothing sweeps, `-f e`; both against the reference lnL."""
+    import os
+    g = golden(case)
+    fe = g.meta["fe"]
+    res = {}
+    for mode in ("fused", "two"):
+        if mode == "two":
+            os.environ["PEPRML_NO_FUSE"] = "1"
+        else:
+            os.environ.pop("PEPRML_NO_FUSE", None)
+        ctx = pb.Context(0)
+        os.environ.pop("PEPRML_NO_FUSE", None)
+        aln = pb.Alignment(ctx, g.names, g.seqs, alpha=fe["alpha"])
+        tree = pb.Tree(aln, fe["tree"])
+        lnl, ps = tree.evaluate(per_site=True)
+        assert abs(lnl - fe["lnl"]) <= REL_REF * abs(fe["lnl"])
+        su0, ln0 = tree.stats()
+        for e in range(tree.num_branches):
+            tree.set_branch(e, 0.05 + 0.01 * (e % 7))
+        tree.smooth(2)
+        lens = [tree.branch(e)[2] for e in range(tree.num_branches)]
+        l2 = tree.evaluate()
+        su1, ln1 = tree.stats()
+        tree.close()
+        t2 = pb.Tree(aln, g.meta["tree_in"])
+        l3, a3 = t2.optimize(True, 0.1)
+        t2.close(); aln.close(); ctx.close()
+        res[mode] = (lnl, ps, np.array(lens), l2, l3, a3, ln1 - ln0, sum(su1) - sum(su0))
+    f, t = res["fused"], res["two"]
+    assert abs(f[0] - t[0]) <= 1e-12 * abs(t[0]) and np.abs(f[1] - t[1]).max() <= 1e-9
+    assert np.allclose(f[2], t[2], rtol=1e-8, atol=1e-12) and abs(f[3] - t[3]) <= 1e-10 * abs(t[3])
+    assert abs(f[4] - t[4]) <= 1e-3 and abs(f[5] - t[5]) <= 1e-4 * t[5]
+    assert f[7] == t[7] and f[6] < t[6]          # same site-updates, fewer launches
