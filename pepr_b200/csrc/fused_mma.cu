@@ -483,6 +483,38 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     }
 
     // ------------------------------------------------------------------------------------------------ BR group
+    // The contraction of a tile's products with the exponentials (12 DMMA in four chains of three) is issued one turn
+    // LATER, between the transforms of the next tile: issued right behind its own transforms it waits for their results and
+    // then for each link of its chains while the group holds the pipe (measured 1,750 instead of 1,152 clk per turn).
+    double sv[2][3][2];        // products of the previous tile, waiting for their contraction
+    int2 side_prev = make_int2(0, 0);
+    int prev_n = -1;
+    // two links per block and k step; a block's chain advances by two DMMAs that sit a whole k step of transforms apart from
+    // the next pair, so one accumulator per block is enough (no partial sums to add afterwards)
+    auto contraction_step = [&](int nt, double (&fs)[2][2]) {
+#pragma unroll
+        for (int m = 0; m < 2; ++m) dmma(fs[m][0], fs[m][1], sv[m][nt][0], efrag[nt][0]);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) dmma(fs[m][0], fs[m][1], sv[m][nt][1], efrag[nt][1]);
+    };
+    auto emit_row_sums = [&](int n, const double (&fs)[2][2], int2 side) {
+        const int rslot = n % kSlots;
+        mbar_wait(red_empty + rslot, ((n / kSlots) & 1) ^ 1);
+        double* red = s_red + ((size_t)rslot * kCats + c) * kTileRows * 3;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            double* dst = red + (m * 8 + g) * 3;
+            if (t == 0) {
+                dst[0] = fs[m][0];
+                dst[1] = fs[m][1];
+            } else if (t == 1) {
+                dst[2] = fs[m][0];
+            }
+        }
+        if (c == 0 && lane < kTileRows) s_side[rslot * kTileRows + lane] = side;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(red_full + rslot);
+    };
     mma_turn_init(1);
     mma_turn_begin(1);  // one empty turn at the start: the NV group runs one tile ahead
     mma_turn_end(1);
@@ -524,73 +556,38 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             mbar_arrive(prod_read + pslot);
             mbar_arrive(prod_empty + pslot);
         }
+        double fs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         mma_turn_begin(1);
-        if (kTipY) {
 #pragma unroll
-            for (int kt = 0; kt < 5; ++kt)
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < 3; ++nt) dmma(accX[m][nt][0], accX[m][nt][1], fx[m].v[kt], fragR[nt][kt]);
-        } else {
+        for (int kt = 0; kt < 5; ++kt) {
+            if (kt < 3 && prev_n >= 0) contraction_step(kt, fs);  // previous tile: one link of each chain per k step
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
-                for (int kt = 0; kt < 5; ++kt)
-#pragma unroll
-                    for (int nt = 0; nt < 3; ++nt) {
-                        dmma(accY[m][nt][0], accY[m][nt][1], fy[m].v[kt], fragL[nt][kt]);
-                        dmma(accX[m][nt][0], accX[m][nt][1], fx[m].v[kt], fragR[nt][kt]);
-                    }
+                for (int nt = 0; nt < 3; ++nt) {
+                    if (!kTipY) dmma(accY[m][nt][0], accY[m][nt][1], fy[m].v[kt], fragL[nt][kt]);
+                    dmma(accX[m][nt][0], accX[m][nt][1], fx[m].v[kt], fragR[nt][kt]);
+                }
         }
-        double fs[2][2][2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) fs[m][0][0] = fs[m][0][1] = fs[m][1][0] = fs[m][1][1] = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt) {
-            accY[0][nt][0] *= accX[0][nt][0];
-            accY[0][nt][1] *= accX[0][nt][1];
-        }
-        dmma(fs[0][0][0], fs[0][0][1], accY[0][0][0], efrag[0][0]);
-        dmma(fs[0][1][0], fs[0][1][1], accY[0][0][1], efrag[0][1]);
-#pragma unroll
-        for (int nt = 0; nt < 3; ++nt) {
-            accY[1][nt][0] *= accX[1][nt][0];
-            accY[1][nt][1] *= accX[1][nt][1];
-        }
-        dmma(fs[1][0][0], fs[1][0][1], accY[1][0][0], efrag[0][0]);
-        dmma(fs[1][1][0], fs[1][1][1], accY[1][0][1], efrag[0][1]);
-#pragma unroll
-        for (int nt = 1; nt < 3; ++nt)
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                dmma(fs[m][0][0], fs[m][0][1], accY[m][nt][0], efrag[nt][0]);
-                dmma(fs[m][1][0], fs[m][1][1], accY[m][nt][1], efrag[nt][1]);
-            }
         mma_turn_end(1);
         __syncwarp();
         if (lane == 0) mbar_arrive(y_empty + yslot);
+        if (prev_n >= 0) emit_row_sums(prev_n, fs, side_prev);
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            fs[m][0][0] += fs[m][1][0];
-            fs[m][0][1] += fs[m][1][1];
-        }
-        const int rslot = n % kSlots;
-        mbar_wait(red_empty + rslot, ((n / kSlots) & 1) ^ 1);
-        double* red = s_red + ((size_t)rslot * kCats + c) * kTileRows * 3;
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            double* dst = red + (m * 8 + g) * 3;
-            if (t == 0) {
-                dst[0] = fs[m][0][0];
-                dst[1] = fs[m][0][1];
-            } else if (t == 1) {
-                dst[2] = fs[m][0][0];
+            for (int nt = 0; nt < 3; ++nt) {
+                sv[m][nt][0] = accY[m][nt][0] * accX[m][nt][0];
+                sv[m][nt][1] = accY[m][nt][1] * accX[m][nt][1];
             }
-        }
-        if (c == 0 && lane < kTileRows) s_side[rslot * kTileRows + lane] = side;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(red_full + rslot);
+        side_prev = side;
+        prev_n = n;
+    }
+    if (prev_n >= 0) {  // the last tile's contraction: nobody else needs the pipe any more
+        double fs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) contraction_step(nt, fs);
+        emit_row_sums(prev_n, fs, side_prev);
     }
 }
 
