@@ -785,12 +785,17 @@ bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets
         nv.out = t->clv(p);
         nv.out_scale = t->scale(p);
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-        const int tk = c->tick(2 - ntip, a->nloc);
-        launch_newview_mma(nv, a->npad, c->sms, c->stream);
-        c->tock(tk);
-        ++t->launches;
         t->site_updates[2 - ntip] += a->nloc;
-        const double seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, false, kWantLnl, false);
+        double seq;
+        if (c->fuse && ntip < 2) {  // the insertion update and the pass over the subtree's branch as one launch
+            seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, true, false, false, kWantLnl, false, &nv);
+        } else {
+            const int tk = c->tick(2 - ntip, a->nloc);
+            launch_newview_mma(nv, a->npad, c->sms, c->stream);
+            c->tock(tk);
+            ++t->launches;
+            seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, false, kWantLnl, false);
+        }
         if (seq == 0.0) {
             ok = false;
             break;
