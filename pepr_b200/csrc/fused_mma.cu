@@ -145,6 +145,11 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
+    // lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
+    double my_len = 0.0;
+    if (warp < kMmaWarps) my_len = (child_p == 0 ? *op.len_left : *op.len_right) * op.len_scale;
+    const double t_raw = args.t_ptr ? *args.t_ptr : args.t;
     if (warp != kProducerWarp) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -156,11 +161,8 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             }
         }
     }
-    pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
-    double my_len = 0.0;
-    if (warp < kMmaWarps) my_len = (child_p == 0 ? *op.len_left : *op.len_right) * op.len_scale;
     // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
-    const double tt = args.t_ptr ? nr_clamp_length(*args.t_ptr) : args.t;
+    const double tt = args.t_ptr ? nr_clamp_length(t_raw) : t_raw;
     __syncthreads();
 
     const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;

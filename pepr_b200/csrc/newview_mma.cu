@@ -112,11 +112,12 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp != kProducerWarp) pmat::matrices_to_smem<kStagers>(regs, stid, s_model);  // static: V and Vinv
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
+    // the length is requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
     double my_len = 0.0;
     if (warp < kMmaWarps) my_len = (child_p == 0 ? *op.len_left : *op.len_right) * op.len_scale;
+    if (warp != kProducerWarp) pmat::matrices_to_smem<kStagers>(regs, stid, s_model);  // V and Vinv
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
