@@ -118,7 +118,7 @@ int64_t pml_tree_nr_retries(const pml_tree *);
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 
-/* profiling aid: while enabled (on = 1: CLV kernel, 4 / 5: CLV kernel with one / no tip child only, 2 / 3: branch kernel with two inner ends / a tip end, 0: off), the kernel accumulates per warp of its
+/* profiling aid: while enabled (on = 1: CLV kernel, 4 / 5: CLV kernel with one / no tip child only, 2 / 3: branch kernel with two inner ends / a tip end, 6: fused kernel (inner children, inner far end), 0: off), the kernel accumulates per warp of its
  * first CTA the clock cycles spent in each pipeline phase (12 warps x 8 counters: wait data, fragments + wait turn, MMAs,
  * products, wait slot, store, tiles, prologue) */
 int pml_trace_enable(pml_ctx *, int on);

@@ -109,6 +109,7 @@ struct pml_ctx {
     long long* d_trace_buf = nullptr;
     long long* d_trace_branch = nullptr;
     bool trace_branch_tip = false;
+    bool trace_fused = false;
     int trace_newview_tips = -1;  // -1: every CLV kernel, 0 / 1: only those with that many tip children
     bool profiling = false;
     std::vector<Timed> timed;
@@ -381,8 +382,9 @@ double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool kee
     ops.pop_back();
     if (!run_ops(t, ops) || !sync_lengths(t)) return 0.0;
     const int far = last.node == x ? y : x;
-    const NewviewOp nv = make_newview_op(t, last);
+    NewviewOp nv = make_newview_op(t, last);
     const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+    if (c->trace_fused && ntip == 0 && !t->topo.is_tip(far)) nv.trace = c->d_trace_buf;  // inner-inner update, inner far end
     t->site_updates[2 - ntip] += t->aln->nloc;
     Side sx{};
     sx.clv = nv.out;
@@ -1022,6 +1024,7 @@ int pml_trace_enable(pml_ctx* c, int on) {
     if (c->d_trace_buf) cudaMemset(c->d_trace_buf, 0, 96 * sizeof(long long));
     c->d_trace = (on == 1 || on == 4 || on == 5) ? c->d_trace_buf : nullptr;
     c->trace_newview_tips = on == 4 ? 1 : (on == 5 ? 0 : -1);
+    c->trace_fused = on == 6;
     c->d_trace_branch = on >= 2 ? c->d_trace_buf : nullptr;
     c->trace_branch_tip = on == 3;
     return PML_OK;

@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     const int c = warp & 3, g = lane >> 2, t = lane & 3;
     if (warp < 4) {
         // -------------------------------------------------------------------------------------------- NV group
+        const bool tr = op.trace != nullptr && blockIdx.x == 0 && lane == 0;
         mma_turn_init(0);
         for (int n = 0; n <= cta_tiles; ++n) {
             if (n == cta_tiles) {  // one empty turn at the end: the BR group is one tile behind
@@ -413,7 +414,9 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 break;
             }
             const int slot = n % kFDepth;
+            const long long k0 = tr ? clock64() : 0;
             mbar_wait(nv_full + slot, (n / kFDepth) & 1);
+            const long long k1 = tr ? clock64() : 0;
             const double* stage = s_nvstage + (size_t)slot * Plan::kNvStageDoubles;
             const unsigned char* aux = reinterpret_cast<const unsigned char*>(stage + Plan::kInner * kTileDoubles);
             int code[2] = {0, 0};
@@ -443,6 +446,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                     if (!kTipR) accR[m][nt][0] = accR[m][nt][1] = 0.0;
                 }
             mma_turn_begin(0);
+            const long long k2 = tr ? clock64() : 0;
 #pragma unroll
             for (int kt = 0; kt < 5; ++kt)
 #pragma unroll
@@ -452,6 +456,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                         if (!kTipL) dmma(accL[m][nt][0], accL[m][nt][1], aL[m].v[kt], fragL[nt][kt]);
                         if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
                     }
+            const long long k3 = tr ? clock64() : 0;
             mma_turn_end(0);
             __syncwarp();
             if (lane == 0) mbar_arrive(nv_empty + slot);
@@ -469,7 +474,9 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 1));
                 big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 2));
             }
+            const long long k4 = tr ? clock64() : 0;
             mbar_wait(prod_empty + pslot, ((n / kSlots) & 1) ^ 1);
+            const long long k5 = tr ? clock64() : 0;
             double* prod = s_prod + (size_t)pslot * kTileDoubles;
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -480,6 +487,17 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             fence_async_smem();  // the tile leaves through the async proxy (bulk store)
             __syncwarp();
             if (lane == 0) mbar_arrive(prod_full + pslot);
+            if (tr) {  // wait data | fragments + wait turn | MMAs | products | wait slot | store | tiles
+                long long* row = op.trace + warp * 8;
+                const long long k6 = clock64();
+                row[0] += k1 - k0;
+                row[1] += k2 - k1;
+                row[2] += k3 - k2;
+                row[3] += k4 - k3;
+                row[4] += k5 - k4;
+                row[5] += k6 - k5;
+                row[6] += 1;
+            }
         }
         return;
     }
@@ -520,10 +538,14 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     mma_turn_init(1);
     mma_turn_begin(1);  // one empty turn at the start: the NV group runs one tile ahead
     mma_turn_end(1);
+    const bool trb = op.trace != nullptr && blockIdx.x == 0 && lane == 0;
     for (int n = 0; n < cta_tiles; ++n) {
         const int pslot = n % kSlots, yslot = n % kFDepth;
+        const long long b0 = trb ? clock64() : 0;
         mbar_wait(prod_full + pslot, (n / kSlots) & 1);
+        const long long b1 = trb ? clock64() : 0;
         mbar_wait(y_full + yslot, (n / kFDepth) & 1);
+        const long long b2 = trb ? clock64() : 0;
         const double* prod = s_prod + (size_t)pslot * kTileDoubles;
         const double* ystage = s_ystage + (size_t)yslot * Plan::kYStageDoubles;
         const unsigned char* yaux = reinterpret_cast<const unsigned char*>(ystage + (kTipY ? 0 : kTileDoubles));
@@ -559,7 +581,9 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             mbar_arrive(prod_empty + pslot);
         }
         double fs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const long long b3 = trb ? clock64() : 0;
         mma_turn_begin(1);
+        const long long b4 = trb ? clock64() : 0;
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt) {
             if (kt < 3 && prev_n >= 0) contraction_step(kt, fs);  // previous tile: one link of each chain per k step
@@ -571,6 +595,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                     dmma(accX[m][nt][0], accX[m][nt][1], fx[m].v[kt], fragR[nt][kt]);
                 }
         }
+        const long long b5 = trb ? clock64() : 0;
         mma_turn_end(1);
         __syncwarp();
         if (lane == 0) mbar_arrive(y_empty + yslot);
@@ -584,6 +609,17 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             }
         side_prev = side;
         prev_n = n;
+        if (trb) {  // wait products | wait far-end tile | fragments | wait turn | MMAs | row sums + products | tiles
+            long long* row = op.trace + warp * 8;
+            const long long b6 = clock64();
+            row[0] += b1 - b0;
+            row[1] += b2 - b1;
+            row[2] += b3 - b2;
+            row[3] += b4 - b3;
+            row[4] += b5 - b4;
+            row[5] += b6 - b5;
+            row[6] += 1;
+        }
     }
     if (prev_n >= 0) {  // the last tile's contraction: nobody else needs the pipe any more
         double fs[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
