@@ -69,6 +69,27 @@ def test_pattern_crunch_with_column_weights(golden):
     assert (s2p[sw == 0] == -1).all()
 
 
+def test_pattern_crunch_threaded_radix_path_matches_oracle():
+    """>= 20,000 columns take the multi-threaded MSD-radix path (level-0 buckets sorted by different threads, pattern
+    boundaries from the radix pass, chunked weight accumulation): same patterns, weights and site map as the oracle's
+    comparison sort, on a duplicate-rich alignment with gaps, B/Z codes, zero-weight columns and patterns that straddle
+    the 32 k-column chunks of the weight pass"""
+    rng = np.random.default_rng(11)
+    ntax, nbase = 9, 900
+    letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV-?XBZ", np.uint8)
+    base = letters[rng.integers(0, len(letters), size=(ntax, nbase))]
+    cols = rng.integers(0, nbase, size=70_000)
+    cols[5_000:45_000] = 7                                        # one pattern 40,000 columns long: crosses chunk boundaries
+    chars = np.ascontiguousarray(base[:, cols])
+    seqs = [bytes(r).decode() for r in chars]
+    sw = rng.integers(0, 3, size=chars.shape[1]).astype(np.int32)
+    for weights in (None, sw):
+        codes, w, s2p = pb.crunch_patterns(seqs, weights)
+        oc, ow, os_ = orc.compress(orc.encode(seqs), weights)
+        assert codes.shape == oc.shape and (codes == oc).all() and (w == ow).all() and (s2p == os_).all()
+        assert w.sum() == (chars.shape[1] if weights is None else int(sw.sum()))
+
+
 def test_bootstrap_weights_bit_exact_with_reference(golden):
     g = golden("small")
     fj = g.meta["fj"]
