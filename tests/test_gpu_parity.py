@@ -17,7 +17,7 @@ def _load(gpu_ctx, g, alpha, newick, site_weights=None):
     return aln, pb.Tree(aln, newick)
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales"])
 def test_lnl_matches_reference_and_oracle(gpu_ctx, golden, case):
     g = golden(case)
     fe = g.meta["fe"]
@@ -108,7 +108,7 @@ def test_branch_derivatives_match_oracle(gpu_ctx, golden, case, edges):
     tree.close(); aln.close()
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "aquificales"])
 def test_optimize_reaches_reference_optimum(gpu_ctx, golden, case):
     """`-f e` from the unoptimised input tree: raxmlHPC stops at dlnL <= 0.1, so that is the comparison tolerance."""
     g = golden(case)
@@ -231,3 +231,23 @@ def test_fused_update_and_branch_pass_equals_two_launches(golden, case):
     assert np.allclose(f[2], t[2], rtol=1e-8, atol=1e-12) and abs(f[3] - t[3]) <= 1e-10 * abs(t[3])
     assert abs(f[4] - t[4]) <= 1e-3 and abs(f[5] - t[5]) <= 1e-4 * t[5]
     assert f[7] == t[7] and f[6] < t[6]          # same site-updates, fewer launches
+
+
+def test_real_data_per_site_lnl_and_search(gpu_ctx, golden):
+    """the reference's own example genomes (tests/golden/make_real.py): per-site lnL against raxmlHPC -f g, and the engine's
+    search from a parsimony start tree ends at least as high as raxmlHPC -f d did (two strains are identical: branches at
+    the zmax bound)"""
+    import re
+    g = golden("aquificales")
+    fe = g.meta["fe"]
+    aln, tree = _load(gpu_ctx, g, fe["alpha"], fe["tree"])
+    lnl, ps = tree.evaluate(per_site=True)
+    ref = np.array(g.meta["fg"]["per_site"])
+    assert np.abs(ps - ref).max() < 2e-6 and abs(lnl - fe["lnl"]) <= REL_REF * abs(fe["lnl"])
+    tree.close()
+    t2 = pb.Tree(aln, parsimony_seed=12345)
+    t2.optimize(True, 5.0)
+    t2.search(radius=5, max_rounds=10, eps=0.1)
+    l2, a2 = t2.optimize(True, 0.1)
+    assert l2 >= g.meta["fd"]["lnl"] - 0.5, (l2, g.meta["fd"]["lnl"])
+    t2.close(); aln.close()

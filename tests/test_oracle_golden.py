@@ -7,7 +7,7 @@ import pytest
 from oracle import oracle as orc
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales"])
 def test_fixed_parameter_lnl_matches_reference(golden, case):
     g = golden(case)
     fe = g.meta["fe"]
@@ -26,8 +26,9 @@ def test_lnl_is_the_same_on_every_branch(golden):
     assert max(vals) - min(vals) < 1e-9
 
 
-def test_per_site_lnl_matches_reference(golden):
-    g = golden("small")
+@pytest.mark.parametrize("case", ["small", "aquificales"])
+def test_per_site_lnl_matches_reference(golden, case):
+    g = golden(case)
     fg = g.meta["fg"]
     t = orc.Tree(g.meta["fe"]["tree"], g.names)
     lnl, pp = orc.evaluate(orc.Model(), t, g.pat, g.w, g.meta["fe"]["alpha"], per_pattern=True)
