@@ -8,7 +8,7 @@ the first genome, columns are that protein's positions (insertions relative to i
 columns with more than half gaps are trimmed (the role Gblocks plays, MSATrimmer.java:94-102).  A star alignment is cruder
 than muscle, but the point here is real data for the likelihood engine: unequal residue composition, indel-derived gaps,
 strong among-site rate variation, invariant columns, duplicate patterns.
-Writes tests/golden/aquificales.phy.gz and aquificales.json.  Needs /root/reference (run once; the outputs are committed)."""
+Writes tests/golden/<example>.phy.gz and <example>.json (aquificales, erysipelotrichales).  Needs /root/reference (run once; the outputs are committed)."""
 import glob
 import gzip
 import json
@@ -77,9 +77,9 @@ def star_align(center, seq, M, gap=6):
     return "".join(reversed(out))
 
 
-def main():
-    files = sorted(glob.glob(os.path.join(REF, "examples", "Aquificales", "*.faa"))) + \
-        sorted(glob.glob(os.path.join(REF, "examples", "Aquificales", "outgroup", "*.faa")))
+def main(example="Aquificales"):
+    files = sorted(glob.glob(os.path.join(REF, "examples", example, "*.faa"))) + \
+        sorted(glob.glob(os.path.join(REF, "examples", example, "outgroup", "*.faa")))
     genomes = []
     for f in files:
         taxon = re.sub(r"\W+", "_", os.path.basename(f).replace(".PATRIC.faa", ""))[:40]
@@ -89,7 +89,9 @@ def main():
             product = parts[4].strip().split("[")[0].strip() if len(parts) > 4 else ""
             if not product or "hypothetical" in product.lower() or len(seq) < 80:
                 continue
-            fam.setdefault(product, []).append(seq.replace("*", ""))
+            seq = seq.replace("*", "")
+            if seq not in fam.setdefault(product, []):   # one example file lists every protein twice
+                fam[product].append(seq)
         genomes.append((taxon, fam))
     shared = set(genomes[0][1])
     for _, fam in genomes:
@@ -130,11 +132,12 @@ def main():
     lines = open(os.path.join(tmp, "RAxML_perSiteLLs.fg")).read().split("\n")
     g["fg"] = {"per_site": [float(x) for x in lines[1].split("\t")[1].split()]}
     g["tree_in"] = re.sub(r":[0-9.eE+-]+", "", g["fd"]["tree"])
-    with open(os.path.join(tmp, "t.phy"), "rb") as f, gzip.GzipFile(os.path.join(HERE, "aquificales.phy.gz"), "wb", mtime=0) as o:
+    with open(os.path.join(tmp, "t.phy"), "rb") as f, gzip.GzipFile(os.path.join(HERE, example.lower() + ".phy.gz"), "wb", mtime=0) as o:
         o.write(f.read())
-    json.dump(g, open(os.path.join(HERE, "aquificales.json"), "w"), indent=1)
+    json.dump(g, open(os.path.join(HERE, example.lower() + ".json"), "w"), indent=1)
     shutil.rmtree(tmp)
 
 
 if __name__ == "__main__":
-    main()
+    for ex in sys.argv[1:] or ["Aquificales", "Erysipelotrichales"]:
+        main(ex)

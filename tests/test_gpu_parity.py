@@ -17,7 +17,7 @@ def _load(gpu_ctx, g, alpha, newick, site_weights=None):
     return aln, pb.Tree(aln, newick)
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales", "erysipelotrichales"])
 def test_lnl_matches_reference_and_oracle(gpu_ctx, golden, case):
     g = golden(case)
     fe = g.meta["fe"]
@@ -108,7 +108,7 @@ def test_branch_derivatives_match_oracle(gpu_ctx, golden, case, edges):
     tree.close(); aln.close()
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep", "aquificales"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "aquificales", "erysipelotrichales"])
 def test_optimize_reaches_reference_optimum(gpu_ctx, golden, case):
     """`-f e` from the unoptimised input tree: raxmlHPC stops at dlnL <= 0.1, so that is the comparison tolerance."""
     g = golden(case)

@@ -7,7 +7,7 @@ import pytest
 from oracle import oracle as orc
 
 
-@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales"])
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide", "aquificales", "erysipelotrichales"])
 def test_fixed_parameter_lnl_matches_reference(golden, case):
     g = golden(case)
     fe = g.meta["fe"]
@@ -26,7 +26,7 @@ def test_lnl_is_the_same_on_every_branch(golden):
     assert max(vals) - min(vals) < 1e-9
 
 
-@pytest.mark.parametrize("case", ["small", "aquificales"])
+@pytest.mark.parametrize("case", ["small", "aquificales", "erysipelotrichales"])
 def test_per_site_lnl_matches_reference(golden, case):
     g = golden(case)
     fg = g.meta["fg"]
