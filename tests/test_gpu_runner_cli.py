@@ -148,3 +148,36 @@ def test_cli_f_d_and_f_a_tree_search(tmp_path, golden):
     assert len(labels) == len(g.names) - 3 and min(labels) >= 0 and max(labels) <= 100
     r = _run_cli(["-f", "d", "-y", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "p1"], tmp_path)     # parsimony tree only
     assert r.returncode == 0 and (tmp_path / "RAxML_parsimonyTree.p1").exists()
+
+
+def test_concurrent_contexts_from_threads(golden):
+    """PEPR runs up to `tree_threads` runners concurrently in one JVM (PhylogenomicPipeline2.java:1233-1254): distinct contexts
+    on the same GPU used from distinct host threads at the same time must give the single-threaded answers"""
+    import threading
+    cases = ["small", "dup", "deep", "aquificales"]
+    want, got, errs = {}, {}, []
+
+    def work(case, out):
+        try:
+            g = golden_get(case)
+            ctx = pb.Context(0)
+            aln = pb.Alignment(ctx, g.names, g.seqs, alpha=1.0)
+            tree = pb.Tree(aln, g.meta["tree_in"])
+            out[case] = tree.optimize(True, 0.1) + (tree.newick(),)
+            tree.close(); aln.close(); ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((case, repr(e)))
+
+    from tests.conftest import Golden
+    cache = {c: Golden(c) for c in cases}
+    golden_get = cache.__getitem__
+    for c in cases:
+        work(c, want)
+    threads = [threading.Thread(target=work, args=(c, got)) for c in cases]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for c in cases:
+        assert got[c] == want[c], c       # bit-identical: same kernels, same fixed-order reductions
