@@ -215,6 +215,7 @@ struct pml_aln {
     DeviceModel* d_model = nullptr;
     bool model_set = false;
     double alpha = 1.0, rates[kCats] = {1, 1, 1, 1};
+    double alpha_step = 0.1;             // first probe distance (in log alpha) of the next alpha optimisation
     double* d_site_lnl = nullptr;
     double* d_partials = nullptr;
     double* d_result = nullptr;  // 16 doubles
@@ -650,14 +651,23 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
     pml_aln* a = t->aln;
     const int root_branch = t->topo.edge[0][0];
     bool ok = true;
+    static const bool debug = getenv("PEPRML_DEBUG_ALPHA") != nullptr;
+    int nevals = 0;
     auto f = [&](double la) {
         double l = 0.0;
         if (!set_alpha(t, std::exp(la)) || evaluate_branch(t, root_branch, weights, &l) != PML_OK) ok = false;
+        ++nevals;
+        if (debug) fprintf(stderr, "  alpha trial %d: log alpha %.6f lnL %.4f\n", nevals, la, l);
         return -l;
     };
     const double lmin = std::log(kAlphaMin), lmax = std::log(kAlphaMax), gold = 1.6180339887498949, cgold = 0.3819660112501051;
     auto clamp = [&](double v) { return std::min(std::max(v, lmin), lmax); };
-    double xa = std::log(a->alpha), xb = clamp(xa + 0.1), fa = f(xa), fb = f(xb);
+    // the caller has just evaluated the tree at the current alpha (*best_lnl): no trial is spent on it.  The first probe sits
+    // as far away as alpha moved in the previous call (three times that, between 4 tol and 0.1): late modOpt rounds, where
+    // alpha moves in the third decimal, bracket the optimum tightly at once
+    const double x0 = std::log(a->alpha);
+    double xa = x0, xb = clamp(xa + a->alpha_step), fa = -*best_lnl, fb = f(xb);
+    if (xb == xa) xb = clamp(xa - a->alpha_step), fb = f(xb);
     if (fb > fa) {
         std::swap(xa, xb);
         std::swap(fa, fb);
@@ -712,6 +722,7 @@ bool optimise_alpha(pml_tree* t, const int32_t* weights, double tol, double* bes
     }
     if (!ok) return false;
     if (!set_alpha(t, std::exp(x))) return false;
+    a->alpha_step = std::min(0.1, std::max(4.0 * tol, 3.0 * std::fabs(x - x0)));
     *best_lnl = -fx;
     return true;
 }
@@ -1341,6 +1352,7 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
     const int32_t* dw = device_weights(a, weights);
     if (!dw) return PML_ENODEVICE;
     // modOpt: { smooth (2 sweeps max), Brent on alpha, smooth (3 sweeps max) } until a round gains <= eps
+    a->alpha_step = 0.1;  // every call brackets alpha from the same first probe: results do not depend on earlier calls
     double cur, best = 0.0;
     if (evaluate_branch(t, t->topo.edge[0][0], weights, &best) != PML_OK) return PML_ENODEVICE;
     int rounds = 0;
