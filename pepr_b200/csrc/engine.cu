@@ -234,6 +234,7 @@ struct pml_tree {
     double* d_len = nullptr;      // branch lengths as the kernels read them (one double per branch id)
     std::vector<double> len_dev;  // what d_len holds (mirror), so that host-side edits of topo.len are uploaded lazily
     int64_t nr_retries = 0;       // Newton-Raphson passes that ended in the bad-curvature retry
+    int last_swept = -1;          // branch the last smoothing sweep ended on
     int prepared_branch = -1;     // branch whose sumtable is resident
     int64_t site_updates[3] = {0, 0, 0};
     int64_t launches = 0;
@@ -553,6 +554,7 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
             if (std::fabs(z - z0) > 1.0e-5) smoothed = false;
             set_branch(t, e, -std::log(z));
             t->views.branch_changed(T, e);
+            t->last_swept = e;
             if (!T.is_tip(far)) {
                 const int near = T.ea[e] == far ? T.eb[e] : T.ea[e];
                 for (int s = 2; s >= 0; --s)
@@ -576,6 +578,7 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
             }
         }
     }
+    t->last_swept = order.empty() ? -1 : order.back();
     struct Pending { int e; double seq; };
     // adopts the outcome of a queued step: host mirror of the length, convergence flag; false = retry needed / error
     auto adopt = [&](const Pending& p, double r[5]) {
@@ -626,14 +629,19 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
     return true;
 }
 
-bool tree_evaluate(pml_tree* t, const int32_t* weights, const int32_t* dw, double factor, double* lnl) {
+// raxmlHPC treeEvaluate: smoothing sweeps until no branch moves, then the tree's lnL.  The lnL is the same at every branch;
+// where_last takes it at the branch the last sweep ended on -- both views are in place there, so it costs one branch pass
+// instead of re-orienting the whole tree towards taxon 0 (worth it when the caller is about to change alpha, which
+// invalidates every view anyway)
+bool tree_evaluate(pml_tree* t, const int32_t* weights, const int32_t* dw, double factor, double* lnl, bool where_last = false) {
     int sweeps = (int)(32 * factor);
     while (--sweeps >= 0) {
         bool smoothed;
         if (!smooth_sweep(t, dw, smoothed)) return false;
         if (smoothed) break;
     }
-    return evaluate_branch(t, t->topo.edge[0][0], weights, lnl) == PML_OK;
+    const int e = where_last && t->last_swept >= 0 ? t->last_swept : t->topo.edge[0][0];
+    return evaluate_branch(t, e, weights, lnl) == PML_OK;
 }
 
 bool set_alpha(pml_tree* t, double alpha) {
@@ -1358,7 +1366,7 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
     int rounds = 0;
     do {
         cur = best;
-        if (!tree_evaluate(t, weights, dw, 0.0625, &best)) return PML_ENODEVICE;
+        if (!tree_evaluate(t, weights, dw, 0.0625, &best, opt_alpha != 0)) return PML_ENODEVICE;
         if (opt_alpha) {
             if (!optimise_alpha(t, weights, 1.0e-3, &best)) return PML_ENODEVICE;
         }
