@@ -455,30 +455,30 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
                 my_r = __ldg(op.right.codes + next);
             }
         }
+        // A warp takes four rows at a time and walks them in row order, 16 bytes per lane: the 32 lanes of one step read
+        // CONSECUTIVE entries of (at most two) lookup rows -- conflict-free shared-memory reads; gathering in the order of
+        // the blocked layout instead made 8 lookup rows collide on the same banks and held the kernel at 16 B/clk per SM.
+        // The stores land in 64-byte runs of the blocked layout (mma_common.cuh).
         double2* out = reinterpret_cast<double2*>(op.out + row0 * kRow);
-#pragma unroll 4
-        for (int q = tid; q < nrows * (kRow / 2); q += kTipTipThreads) {
-            // q walks the blocked layout in 16-byte steps: block, category, chunk (see mma_common.cuh)
-            const int blk = q / (kBlockDoubles / 2), rem = q % (kBlockDoubles / 2);
-            const int cat = rem / (kCatDoubles / 2), u = rem % (kCatDoubles / 2);
-            int g, st;
-            if (u < 64) {
-                g = (u & 31) >> 2;
-                st = (u >> 5) * 8 + (u & 3) * 2;
-            } else {
-                g = (u - 64) >> 1;
-                st = 16 + ((u - 64) & 1) * 2;
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int grp = wid; grp < nrows / 4; grp += kTipTipThreads / 32) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int idx = lane + 32 * j;               // 0 .. 159 = 4 rows x 40 double2
+                const int r = grp * 4 + idx / (kRow / 2), k = idx % (kRow / 2);
+                const int cl = sm.pair[buf][r][0], cr = sm.pair[buf][r][1];
+                const double2 a = reinterpret_cast<const double2*>(sm.l + cl * kTipPad)[k];
+                const double2 b = reinterpret_cast<const double2*>(sm.r + cr * kTipPad)[k];
+                double2 v = make_double2(a.x * b.x, a.y * b.y);
+                if (sm.flag[cl * kCodes + cr]) {
+                    v.x *= kTwo256;
+                    v.y *= kTwo256;
+                }
+                // (row, category, state pair) -> 16-byte slot of the blocked layout
+                const int cat = k / (kStates / 2), sp = k % (kStates / 2), g = r & 7;
+                const int slot = sp < 4 ? g * 4 + sp : (sp < 8 ? 32 + g * 4 + (sp - 4) : 64 + g * 2 + (sp - 8));
+                out[(r >> 3) * (kBlockDoubles / 2) + cat * (kCatDoubles / 2) + slot] = v;
             }
-            const int r = blk * kBlockRows + g, k = (cat * kStates + st) >> 1;
-            const int cl = sm.pair[buf][r][0], cr = sm.pair[buf][r][1];
-            const double2 a = reinterpret_cast<const double2*>(sm.l + cl * kTipPad)[k];
-            const double2 b = reinterpret_cast<const double2*>(sm.r + cr * kTipPad)[k];
-            double2 v = make_double2(a.x * b.x, a.y * b.y);
-            if (sm.flag[cl * kCodes + cr]) {
-                v.x *= kTwo256;
-                v.y *= kTwo256;
-            }
-            out[q] = v;
         }
     }
 }
