@@ -181,3 +181,28 @@ def test_concurrent_contexts_from_threads(golden):
     assert not errs, errs
     for c in cases:
         assert got[c] == want[c], c       # bit-identical: same kernels, same fixed-order reductions
+
+
+def test_cli_on_the_reference_example_genomes(tmp_path, golden):
+    """the executable on the real-data supermatrix (examples/Aquificales, tests/golden/make_real.py): the files PEPR reads
+    back after `-f e` and `-f g` carry raxmlHPC's numbers; long taxon names survive the relaxed phylip round trip"""
+    g = golden("aquificales")
+    from pepr_b200 import synth
+    synth.write_phylip(str(tmp_path / "a.phy"), g.names, g.seqs)
+    (tmp_path / "a.nwk").write_text(g.meta["tree_in"] + "\n")
+    r = _run_cli(["-f", "e", "-m", "PROTGAMMAWAG", "-s", "a.phy", "-n", "fe", "-t", "a.nwk"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    info = (tmp_path / "RAxML_info.fe").read_text()
+    lnl = float(re.search(r"Final GAMMA\s+likelihood: (\S+)", info).group(1))
+    assert abs(lnl - g.meta["fe"]["lnl"]) < 0.1
+    assert "Alignment has %d distinct alignment patterns" % g.meta["fe"]["patterns"] in info
+    tree = (tmp_path / "RAxML_result.fe").read_text().strip()
+    assert all(n in tree for n in g.names)
+    (tmp_path / "ref.nwk").write_text(g.meta["fe"]["tree"] + "\n")
+    r = _run_cli(["-f", "g", "-m", "PROTGAMMAWAG", "-s", "a.phy", "-n", "fg", "-z", "ref.nwk"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    lines = (tmp_path / "RAxML_perSiteLLs.fg").read_text().split("\n")
+    got = np.array([float(x) for x in lines[1].split("\t")[1].split()])
+    ref = np.array(g.meta["fg"]["per_site"])
+    # `-f g` re-optimises the model on the given tree like raxmlHPC does, so alpha (hence every site) moves in the 4th decimal
+    assert got.shape == ref.shape and abs(got.sum() - ref.sum()) < 0.1 and np.abs(got - ref).max() < 5e-3
