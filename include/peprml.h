@@ -27,7 +27,7 @@ extern "C" {
 #define PML_EINVAL (-1)    /* bad argument / malformed newick / unknown taxon */
 #define PML_ENODEVICE (-2) /* no CUDA device, or CUDA runtime error (see pml_last_error) */
 #define PML_ENOMEM (-3)
-#define PML_ECOMM (-4)     /* NCCL error */
+#define PML_ECOMM (-4)     /* NCCL error, or a rank of the group did not deliver its sums in time */
 #define PML_ESTATE (-5)    /* call order (e.g. evaluate before model_set) */
 
 #define PML_UNIQUE_ID_BYTES 128
@@ -45,6 +45,14 @@ const char *pml_version(void);
  * on one rank (distributed by the host: a Java array shared by threads, torch.distributed broadcast, a file ...). */
 int pml_comm_unique_id(unsigned char id[PML_UNIQUE_ID_BYTES]);
 int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char *unique_id, pml_ctx **out);
+/* All ranks of a site-sharded group inside ONE process: what `-T n` is to raxmlHPC-PTHREADS when PEPR's single JVM starts it
+ * (RAxMLRunner.java:130-132).  out receives ngpu contexts, rank i on gpu_ids[i] (distinct GPUs).  The in-kernel reduction
+ * reaches the peers' mailboxes through cudaDeviceEnablePeerAccess (no CUDA IPC, which cannot map a handle inside the process
+ * that exported it), so pml_ctx_collective() is 2 here exactly as it is for one process per GPU.  Each context is driven
+ * by its own host thread and all threads make the same calls in the same order (a branch pass waits for its peers' sums --
+ * for at most PEPRML_PEER_TIMEOUT_MS, default 10 s, then the call fails with PML_ECOMM; nothing hangs).  pml_aln_load on
+ * such contexts sorts the alignment once for the whole group.  Destroy every context with pml_ctx_destroy when all are idle. */
+int pml_group_create(const int *gpu_ids, int ngpu, pml_ctx **out);
 void pml_ctx_destroy(pml_ctx *);
 const char *pml_last_error(const pml_ctx *); /* ctx may be NULL: last creation error of this thread */
 int pml_ctx_sync(pml_ctx *);
@@ -72,6 +80,12 @@ const char *pml_aln_name(const pml_aln *, int taxon);
  * capacity, filled as ntax x *npatterns row-major; weights_out / site_to_pattern as above. */
 int pml_crunch_patterns(int ntax, int64_t nsites, const uint8_t *chars, const int32_t *site_weights, uint8_t *codes_out,
                         int32_t *weights_out, int64_t *site_to_pattern, int64_t *npatterns);
+
+/* host-only: the same crunch as `nranks` ranks of a multi-process group perform it -- the radix sort split by first-residue
+ * bucket, the sorted column order exchanged by an element-wise sum (an NCCL allreduce inside pml_aln_load; threads and a
+ * barrier here) -- with every rank's code block put side by side.  Must equal pml_crunch_patterns bit for bit. */
+int pml_crunch_patterns_sharded(int nranks, int ntax, int64_t nsites, const uint8_t *chars, const int32_t *site_weights,
+                                uint8_t *codes_out, int32_t *weights_out, int64_t *site_to_pattern, int64_t *npatterns);
 
 /* ---- model: `-m PROTGAMMAWAG` (PhylogenomicPipeline2.java:248-250) -----------------------------------------
  * WAG exchangeabilities + fixed WAG frequencies, 4 mean-Gamma categories with shape alpha. */
@@ -113,8 +127,9 @@ int64_t pml_tree_nr_retries(const pml_tree *);
  * kind, the summed device milliseconds, the launch count and the pattern rows processed.
  * kinds: 0 newview tip-tip, 1 newview tip-inner, 2 newview inner-inner, 3 root evaluate (branch pass with per-pattern lnL),
  * 4 branch pass between two inner nodes, 5 NR core on a stored table, 6 branch pass with a tip end,
- * 7 / 8 fused CLV update + branch pass with an inner / a tip far end. */
-#define PML_NKINDS 9
+ * 7-10 fused CLV update + branch pass: 7 inner children / inner far end, 8 inner children / tip far end, 9 one tip child /
+ * inner far end, 10 one tip child / tip far end. */
+#define PML_NKINDS 11
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 
@@ -173,6 +188,19 @@ int pml_bootstrap_weights(const pml_aln *, int64_t *seed, int nrep, int32_t *out
 int pml_bootstrap_weights_host(const int32_t *pattern_weights, int64_t npatterns, int64_t *seed, int nrep, int32_t *out);
 /* lnL of `nrep` weight vectors on the current tree/parameters in one pass (W: nrep x npatterns, global order) */
 int pml_evaluate_replicates(pml_tree *, const int32_t *W, int nrep, double *lnl);
+
+/* ---- replicate trees, sharded by REPLICATE ---------------------------------------------------------
+ * Replaces PEPR's support-tree workers (PhylogenomicPipeline2.java:1227-1275: one runner thread per support tree, results
+ * collected on the host) and the replicate searches of `-f a -x seed -N nrep` (RAxMLRunner.java:112-124).
+ * Runs the replicates first, first + stride, ... (< nrep) on THIS context: weights of replicate r from raxmlHPC's stream
+ * (the whole stream is drawn, so r carries the same vector whatever the sharding) -> parsimony start tree on the replicate
+ * (seed parsimony_seed + 1 + r) -> alpha + branch lengths (eps 5) -> `rounds` lazy-SPR rounds of `radius` with smoothing.
+ * With one single-rank context per GPU holding the FULL pattern set and (first, stride) = (g, ngpu) the replicates need no
+ * communication at all; the host concatenates the newick texts.  newicks: the share's trees, one per line, in replicate
+ * order (capacity: count x pml_newick_capacity()); lnl / seconds (NULL or nrep entries): filled at the share's indices. */
+int64_t pml_newick_capacity(const pml_aln *);
+int pml_bootstrap_trees(pml_aln *, int64_t weight_seed, int64_t parsimony_seed, int nrep, int first, int stride, int radius,
+                        int rounds, double eps, char *newicks, size_t cap, double *lnl, double *seconds);
 
 /* ---- support estimation (integer, bit exact) --------------------------------------------------------------
  * TreeSupportDecorator.addSupportValues (TreeSupportDecorator.java:86-163) with Bipartition canonical form

@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
 #pragma unroll
             for (int v = 0; v < 3; ++v) r3[v] += __shfl_xor_sync(0xffffffffu, r3[v], o);
         }
-        if (args.peer.mail) peer_allreduce3(args.peer, args.pub.seq, r3);
+        const bool lost = args.peer.mail != nullptr && !peer_allreduce3(args.peer, args.pub.seq, r3);
         if (lane == 0) {
             args.result[0] = r3[0];
             args.result[1] = r3[1];
             args.result[2] = r3[2];
             args.result[3] = tt;
             *args.ticket = 0;
-            publish_result(args.pub, r3, tt);
+            publish_result(args.pub, r3, tt, lost);
             if (args.trace) {
                 args.trace[88] += clock64() - f3c;  // last CTA: final sum, NR step, publication
                 args.trace[89] += 1;

@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,9 @@
 #include <functional>
 #include <limits>
 #include <memory>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <sstream>
 #include <string>
 #include <unordered_map>
@@ -35,6 +39,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string& err) {
         if (handle) return true;
@@ -48,6 +54,8 @@ struct NcclApi {
         AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
         CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        GroupStart = (decltype(GroupStart))dlsym(handle, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(handle, "ncclGroupEnd");
         if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) {
             err = "libnccl.so.2 lacks required symbols";
             return false;
@@ -59,8 +67,28 @@ NcclApi g_nccl;
 
 }  // namespace
 
+// Ranks of a site-sharded group that live in ONE process (pml_group_create): what they share.
+struct PmlGroup {
+    int n = 0;
+    std::vector<int> devices;
+    std::vector<double*> mail;  // one mailbox per rank, on that rank's device, written by all peers through NVLink peer access
+    // pattern crunch of the alignment the ranks are loading: done once by the first rank that asks (see pml_aln_load)
+    std::mutex mu;
+    uint64_t crunch_key[5] = {0, 0, 0, 0, 0};
+    int crunch_uses = 0;
+    std::shared_ptr<const Patterns> crunch;
+    ~PmlGroup() {
+        for (int r = 0; r < (int)mail.size(); ++r)
+            if (mail[r]) {
+                cudaSetDevice(devices[r]);
+                cudaFree(mail[r]);
+            }
+    }
+};
+
 struct pml_ctx {
     int device = 0, rank = 0, nranks = 1, sms = 148;
+    std::shared_ptr<PmlGroup> group;  // set for ranks created by pml_group_create
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;
     std::string err;
@@ -85,23 +113,32 @@ struct pml_ctx {
     volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     double* slot_dev(double seq) const { return d_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
     // waits until the pass with this sequence number has published; out = {lnL, d1, d2, length, status}
+    bool comm_lost = false;  // a pass reported kNrCommLost: the group is unusable, every later call fails with PML_ECOMM
     bool wait_slot(double seq, double out[5]) {
-        volatile double* s = slot_host(seq);
+        const volatile unsigned long long* s = reinterpret_cast<const volatile unsigned long long*>(slot_host(seq));
+        const uint32_t flag = ll_flag(seq);
         long spins = 0;
         for (int i = 0; i < 5; ++i) {
-            while (s[2 * i + 1] != seq) {  // each (value, seq) pair arrives as one 16-byte write
+            while (!ll_try_read_host(s + 2 * i, flag, &out[i])) {
                 if ((++spins & 0xFFFFF) == 0 && cudaStreamQuery(stream) != cudaErrorNotReady) {
-                    if (s[2 * i + 1] == seq) break;
+                    if (ll_try_read_host(s + 2 * i, flag, &out[i])) break;
                     cuda(cudaStreamSynchronize(stream), "branch kernel");
                     if (err.empty()) err = "branch kernel finished without publishing its result";
                     return false;
                 }
             }
-            __atomic_thread_fence(__ATOMIC_ACQUIRE);
-            out[i] = s[2 * i];
+        }
+        if ((int)out[4] == kNrCommLost) {
+            comm_lost = true;
+            err = "peer reduction timed out: a rank of the group did not deliver its sums (crashed, failed before its launch, "
+                  "or out of step); the group must be destroyed";
+            return false;
         }
         return true;
     }
+    int fail_code() const { return comm_lost || err.rfind("nccl", 0) == 0 ? PML_ECOMM : PML_ENODEVICE; }
+    int* d_peer_lost = nullptr;            // sticky device flag of PeerReduce
+    unsigned long long peer_timeout_ns = 10ull * 1000 * 1000 * 1000;  // PEPRML_PEER_TIMEOUT_MS
     // optional per-launch device timing (pml_profile_begin/end)
     struct Timed { int kind; int64_t rows; cudaEvent_t t0, t1; };
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
@@ -222,7 +259,11 @@ struct pml_aln {
     unsigned int* d_ticket = nullptr;
     double* d_sumtable = nullptr;
     int32_t* d_sumscale = nullptr;
-    int ntrees = 0;
+    // The model constants and the product table are shared by every tree of this alignment, their validity is not:
+    // model_epoch counts model uploads (a tree's views are only good for the epoch they were built under), and the
+    // product table belongs to the tree that filled it last.
+    uint64_t model_epoch = 0;
+    const pml_tree* sumtable_owner = nullptr;
 };
 
 struct pml_tree {
@@ -235,7 +276,8 @@ struct pml_tree {
     std::vector<double> len_dev;  // what d_len holds (mirror), so that host-side edits of topo.len are uploaded lazily
     int64_t nr_retries = 0;       // Newton-Raphson passes that ended in the bad-curvature retry
     int last_swept = -1;          // branch the last smoothing sweep ended on
-    int prepared_branch = -1;     // branch whose sumtable is resident
+    int prepared_branch = -1;     // branch whose sumtable is resident (only while aln->sumtable_owner == this)
+    uint64_t model_epoch = 0;     // aln->model_epoch the stored views were computed under
     int64_t site_updates[3] = {0, 0, 0};
     int64_t launches = 0;
 
@@ -254,6 +296,21 @@ struct pml_tree {
 
 namespace {
 
+// 64-bit content hash (8 bytes per step) -- the key under which ranks of one process share a pattern crunch
+uint64_t hash_bytes(const void* data, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ n;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0xff51afd7ed558ccdull;
+        h ^= h >> 29;
+    }
+    for (; i < n; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+    return h;
+}
+
 constexpr int kPad = 128;            // pattern rows are padded to a multiple of this (tile height of the CLV kernels)
 constexpr double kDefaultLen = 0.1;
 
@@ -269,6 +326,7 @@ bool upload_model(pml_aln* a) {
     std::memcpy(h->rates, a->rates, sizeof a->rates);
     for (int i = 0; i < kStates; ++i)
         for (int k = 0; k < kStates; ++k) h->piV[i][k] = es.pi[i] * es.V[i][k];
+    ++a->model_epoch;  // every tree of this alignment drops its views before it plans again (adopt_model)
     return c->cuda(cudaMemcpyAsync(a->d_model, h, sizeof(DeviceModel), cudaMemcpyHostToDevice, c->stream), "model upload");
 }
 
@@ -283,6 +341,18 @@ const int32_t* device_weights(pml_aln* a, const int32_t* weights) {
             return nullptr;
     }
     return a->d_wcustom;
+}
+
+// A tree's stored views and its claim on the product table are void once the alignment's model changed under it (another
+// tree's alpha optimisation, pml_model_set) or another tree filled the table.  Called by every entry point before planning.
+void adopt_model(pml_tree* t) {
+    pml_aln* a = t->aln;
+    if (t->model_epoch != a->model_epoch) {
+        t->views.reset(t->topo);
+        t->prepared_branch = -1;
+        t->model_epoch = a->model_epoch;
+    }
+    if (a->sumtable_owner != t) t->prepared_branch = -1;
 }
 
 // host-side edits of branch lengths (set_branch, SPR moves, a freshly loaded tree) reach the device before the next launch
@@ -425,13 +495,16 @@ double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, c
     }
     const bool in_kernel = c->nranks == 1 || c->peer_ok;
     if (in_kernel) args.pub = pub;
-    if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks};
-    const int tk = c->tick(fused ? (args.a.clv ? 7 : 8) : (site_lnl ? 3 : (args.a.clv ? 4 : 6)), a->nloc);
+    if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks, c->d_peer_lost, c->peer_timeout_ns};
+    // kinds 7..10: fused update + pass, by (tip child of the update, tip far end); see PML_NKINDS in peprml.h
+    const int fused_kind = fused ? 7 + 2 * ((nv->left.clv == nullptr) || (nv->right.clv == nullptr) ? 1 : 0) + (args.a.clv ? 0 : 1) : 0;
+    const int tk = c->tick(fused ? fused_kind : (site_lnl ? 3 : (args.a.clv ? 4 : 6)), a->nloc);
     if (fused) launch_fused(*nv, args, a->npad, c->sms, c->stream);
     else launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
+    if (keep_table) a->sumtable_owner = t;
     if (!c->cuda(cudaGetLastError(), "branch kernel")) return 0.0;
     if (!in_kernel) {
         if (!c->allreduce(a->d_result, 3)) return 0.0;
@@ -458,7 +531,7 @@ int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     double r[3];
-    if (!branch_pass(t, e, dw, t->topo.len[e], false, true, r, kWantLnl)) return t->aln->ctx->err.rfind("nccl", 0) == 0 ? PML_ECOMM : PML_ENODEVICE;
+    if (!branch_pass(t, e, dw, t->topo.len[e], false, true, r, kWantLnl)) return t->aln->ctx->fail_code();
     *lnl = r[0];
     return PML_OK;
 }
@@ -579,27 +652,29 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
         }
     }
     t->last_swept = order.empty() ? -1 : order.back();
-    struct Pending { int e; double seq; };
-    // adopts the outcome of a queued step: host mirror of the length, convergence flag; false = retry needed / error
+    // z0: the branch's z before its FIRST pass of this visit -- raxmlHPC update() compares the final z with that one, also
+    // when bad-curvature retries moved the starting point in between
+    struct Pending { int e; double seq; double z0; };
+    // adopts the outcome of a queued step: host mirror of the length, convergence flag; false = error
     auto adopt = [&](const Pending& p, double r[5]) {
         if (!c->wait_slot(p.seq, r)) return false;
         const int status = (int)r[4];
         if (status == kNrSkipped) return true;
-        const double z0 = std::min(std::max(std::exp(-T.len[p.e]), kZmin), kZmax);
         T.len[p.e] = t->len_dev[p.e] = r[3];
-        if (status == kNrDone && std::fabs(std::exp(-r[3]) - z0) > 1.0e-5) smoothed = false;
+        if (status == kNrDone && std::fabs(std::exp(-r[3]) - p.z0) > 1.0e-5) smoothed = false;
         return true;
     };
-    auto queue_step = [&](int e) {
-        Pending p{e, branch_launch(t, e, dw, 0.0, false, false, kWantDerivs, true)};
+    auto queue_step = [&](int e, double z0 = -1.0) {
+        if (z0 < 0.0) z0 = std::min(std::max(std::exp(-T.len[e]), kZmin), kZmax);
+        Pending p{e, branch_launch(t, e, dw, 0.0, false, false, kWantDerivs, true), z0};
         t->views.branch_changed(T, e);  // the length is about to change
         t->prepared_branch = -1;
         return p;
     };
     size_t i = 0;
-    Pending prev{-1, 0.0};
+    Pending prev{-1, 0.0, 0.0};
     while (i < order.size() || prev.e >= 0) {
-        Pending cur{-1, 0.0};
+        Pending cur{-1, 0.0, 0.0};
         if (i < order.size()) {
             cur = queue_step(order[i]);
             if (cur.seq == 0.0) return false;
@@ -613,13 +688,13 @@ bool smooth_sweep(pml_tree* t, const int32_t* dw, bool& smoothed) {
                 if (cur.e >= 0 && !c->wait_slot(cur.seq, r)) return false;
                 if (!c->cuda(cudaMemsetAsync(c->d_poison, 0, sizeof(int), c->stream), "flag clear")) return false;
                 for (int guard = 0; guard < 64; ++guard) {
-                    const Pending again = queue_step(prev.e);
+                    const Pending again = queue_step(prev.e, prev.z0);
                     if (again.seq == 0.0 || !adopt(again, r)) return false;
                     if ((int)r[4] != kNrRetry) break;
                     ++t->nr_retries;
                     if (!c->cuda(cudaMemsetAsync(c->d_poison, 0, sizeof(int), c->stream), "flag clear")) return false;
                 }
-                prev = Pending{-1, 0.0};
+                prev = Pending{-1, 0.0, 0.0};
                 continue;  // cur is queued again on the next trip (i was not advanced)
             }
         }
@@ -649,8 +724,7 @@ bool set_alpha(pml_tree* t, double alpha) {
     a->alpha = alpha;
     gamma_mean_rates(alpha, kCats, a->rates);
     if (!upload_model(a)) return false;
-    t->views.reset(t->topo);
-    t->prepared_branch = -1;
+    adopt_model(t);
     return true;
 }
 
@@ -894,7 +968,8 @@ void setup_peer_mail(pml_ctx* c) {
     int32_t* d_gather = nullptr;
     std::vector<int32_t> h((size_t)kWords * c->nranks + c->nranks, 0);
     cudaIpcMemHandle_t mine;
-    bool ok = cudaMalloc(&c->d_mail, bytes) == cudaSuccess && cudaMemset(c->d_mail, 0, bytes) == cudaSuccess &&
+    bool ok = cudaMalloc(&c->d_peer_lost, sizeof(int)) == cudaSuccess && cudaMemset(c->d_peer_lost, 0, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&c->d_mail, bytes) == cudaSuccess && cudaMemset(c->d_mail, 0, bytes) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine, c->d_mail) == cudaSuccess && cudaMalloc(&d_gather, sizeof(int32_t) * h.size()) == cudaSuccess;
     // every rank must take part in the collectives below, whatever happened locally: a flag per rank travels with the handles
     if (ok) {
@@ -961,21 +1036,20 @@ int pml_comm_unique_id(unsigned char id[PML_UNIQUE_ID_BYTES]) {
     return PML_OK;
 }
 
-int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique_id, pml_ctx** out) {
-    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, PML_EINVAL, "bad rank/nranks");
-    *out = nullptr;
+static int create_base(int gpu_id, int rank, int nranks, std::unique_ptr<pml_ctx>& c) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return fail(nullptr, PML_ENODEVICE,
                     std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this engine has no CPU path");
     if (gpu_id < 0 || gpu_id >= ndev) return fail(nullptr, PML_EINVAL, "gpu_id out of range");
-    auto c = std::make_unique<pml_ctx>();
+    c = std::make_unique<pml_ctx>();
     c->device = gpu_id;
     c->host_nr = getenv("PEPRML_HOST_NR") != nullptr;
     c->fuse = getenv("PEPRML_NO_FUSE") == nullptr;
     c->rank = rank;
     c->nranks = nranks;
+    if (const char* ms = getenv("PEPRML_PEER_TIMEOUT_MS")) c->peer_timeout_ns = (unsigned long long)std::max(1.0, atof(ms)) * 1000000ull;
     if (!c->bind() || !c->cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream create"))
         return fail(nullptr, PML_ENODEVICE, c->err);
     cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, gpu_id);
@@ -990,6 +1064,15 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
         !c->cuda(cudaMalloc(&c->d_poison, sizeof(int)), "flag alloc") || !c->cuda(cudaMemset(c->d_poison, 0, sizeof(int)), "flag init"))
         return fail(nullptr, PML_ENOMEM, c->err);
     for (int i = 0; i < pml_ctx::kRing * kSlotDoubles; ++i) c->h_mapped[i] = 0.0;
+    return PML_OK;
+}
+
+int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique_id, pml_ctx** out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, PML_EINVAL, "bad rank/nranks");
+    *out = nullptr;
+    std::unique_ptr<pml_ctx> c;
+    const int rc = create_base(gpu_id, rank, nranks, c);
+    if (rc != PML_OK) return rc;
     if (nranks > 1) {
         if (!unique_id) return fail(nullptr, PML_EINVAL, "unique_id required when nranks > 1");
         std::string err;
@@ -1001,6 +1084,79 @@ int pml_ctx_create(int gpu_id, int rank, int nranks, const unsigned char* unique
         setup_peer_mail(c.get());
     }
     *out = c.release();
+    return PML_OK;
+}
+
+// All ranks of a group in THIS process (what `-T n` is for raxmlHPC-PTHREADS inside one JVM, RAxMLRunner.java:130-132):
+// rank i runs on gpu_ids[i].  The mailboxes of the in-kernel reduction are plain device allocations reached through
+// cudaDeviceEnablePeerAccess -- no CUDA IPC, which cannot map a handle in the process that exported it.  Every context must
+// then be driven by its own host thread, all threads making the same calls (a branch pass waits for its peers' sums).
+int pml_group_create(const int* gpu_ids, int ngpu, pml_ctx** out) {
+    if (!gpu_ids || !out || ngpu < 1 || ngpu > kMaxPeers) return fail(nullptr, PML_EINVAL, "pml_group_create: bad arguments");
+    for (int r = 0; r < ngpu; ++r) out[r] = nullptr;
+    for (int r = 0; r < ngpu; ++r)
+        for (int q = 0; q < r; ++q)
+            if (gpu_ids[r] == gpu_ids[q]) return fail(nullptr, PML_EINVAL, "pml_group_create: a GPU may carry one rank only");
+    std::vector<std::unique_ptr<pml_ctx>> cs(ngpu);
+    auto destroy_all = [&]() {
+        for (auto& c : cs)
+            if (c) pml_ctx_destroy(c.release());
+    };
+    for (int r = 0; r < ngpu; ++r) {
+        const int rc = create_base(gpu_ids[r], r, ngpu, cs[r]);
+        if (rc != PML_OK) {
+            cs[r].reset();
+            destroy_all();
+            return rc;
+        }
+    }
+    if (ngpu > 1) {
+        std::string err;
+        if (!g_nccl.load(err) || !g_nccl.GroupStart || !g_nccl.GroupEnd) {
+            destroy_all();
+            return fail(nullptr, PML_ECOMM, err.empty() ? "libnccl.so.2 lacks ncclGroupStart/End" : err);
+        }
+        ncclUniqueId u;
+        bool ok = g_nccl.GetUniqueId(&u) == ncclSuccess && g_nccl.GroupStart() == ncclSuccess;
+        for (int r = 0; ok && r < ngpu; ++r) ok = cudaSetDevice(gpu_ids[r]) == cudaSuccess && g_nccl.CommInitRank(&cs[r]->comm, ngpu, u, r) == ncclSuccess;
+        ok = g_nccl.GroupEnd() == ncclSuccess && ok;
+        if (!ok) {
+            destroy_all();
+            return fail(nullptr, PML_ECOMM, "pml_group_create: NCCL communicator setup failed");
+        }
+        auto g = std::make_shared<PmlGroup>();
+        g->n = ngpu;
+        g->devices.assign(gpu_ids, gpu_ids + ngpu);
+        g->mail.assign(ngpu, nullptr);
+        for (auto& c : cs) c->group = g;
+        bool peers = getenv("PEPRML_NO_PEER") == nullptr;
+        for (int r = 0; peers && r < ngpu; ++r)
+            for (int q = 0; peers && q < ngpu; ++q) {
+                int can = 0;
+                if (q != r && (cudaDeviceCanAccessPeer(&can, gpu_ids[r], gpu_ids[q]) != cudaSuccess || !can)) peers = false;
+            }
+        const size_t bytes = sizeof(double) * kPeerRing * ngpu * 6;
+        for (int r = 0; peers && r < ngpu; ++r) {
+            cudaSetDevice(gpu_ids[r]);
+            for (int q = 0; peers && q < ngpu; ++q) {
+                if (q == r) continue;
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(gpu_ids[q], 0);
+                if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (pe != cudaSuccess) peers = false;
+            }
+            peers = peers && cudaMalloc(&g->mail[r], bytes) == cudaSuccess && cudaMemset(g->mail[r], 0, bytes) == cudaSuccess &&
+                    cudaMalloc(&cs[r]->d_peer_lost, sizeof(int)) == cudaSuccess && cudaMemset(cs[r]->d_peer_lost, 0, sizeof(int)) == cudaSuccess;
+        }
+        for (int r = 0; peers && r < ngpu; ++r) {
+            cudaSetDevice(gpu_ids[r]);
+            peers = cudaMalloc(&cs[r]->d_mail_ptrs, sizeof(double*) * ngpu) == cudaSuccess &&
+                    cudaMemcpy(cs[r]->d_mail_ptrs, g->mail.data(), sizeof(double*) * ngpu, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaDeviceSynchronize() == cudaSuccess;
+        }
+        cudaGetLastError();
+        for (auto& c : cs) c->peer_ok = peers;
+    }
+    for (int r = 0; r < ngpu; ++r) out[r] = cs[r].release();
     return PML_OK;
 }
 
@@ -1020,6 +1176,7 @@ void pml_ctx_destroy(pml_ctx* c) {
     for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
     if (c->d_mail_ptrs) cudaFree(c->d_mail_ptrs);
     if (c->d_mail) cudaFree(c->d_mail);
+    if (c->d_peer_lost) cudaFree(c->d_peer_lost);
     if (c->d_trace_buf) cudaFree(c->d_trace_buf);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
     for (auto e : c->spare_events) cudaEventDestroy(e);
@@ -1108,7 +1265,60 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
     if (!c->bind()) return PML_ENODEVICE;
     auto a = std::make_unique<pml_aln>();
     a->ctx = c;
-    crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks);  // codes of this rank's block only
+    // The column sort is global, the residue codes a rank keeps are those of its own pattern block.  Ranks of one process
+    // (pml_group_create) crunch ONCE: the first rank to arrive does it, the others copy the result.  Ranks in separate
+    // processes split the radix sort between them and exchange the sorted column order with one NCCL allreduce.
+    if (c->group) {
+        PmlGroup& g = *c->group;
+        const uint64_t key[5] = {(uint64_t)(uintptr_t)chars, (uint64_t)ntax, (uint64_t)nsites,
+                                 hash_bytes(chars, (size_t)ntax * (size_t)nsites),
+                                 site_weights ? hash_bytes(site_weights, sizeof(int32_t) * (size_t)nsites) : 0};
+        std::shared_ptr<const Patterns> shared;
+        {
+            std::lock_guard<std::mutex> lock(g.mu);
+            if (!g.crunch || std::memcmp(g.crunch_key, key, sizeof key) != 0 || g.crunch_uses >= g.n) {
+                auto fresh = std::make_shared<Patterns>();
+                crunch_patterns(ntax, nsites, chars, site_weights, *fresh, 0, 1);
+                fresh->codes.clear();
+                fresh->codes.shrink_to_fit();
+                g.crunch = fresh;
+                std::memcpy(g.crunch_key, key, sizeof key);
+                g.crunch_uses = 0;
+            }
+            ++g.crunch_uses;
+            shared = g.crunch;
+            if (g.crunch_uses >= g.n) g.crunch.reset();  // everybody has it
+        }
+        a->pat.ntax = shared->ntax;
+        a->pat.nsites = shared->nsites;
+        a->pat.npat = shared->npat;
+        a->pat.weight = shared->weight;
+        a->pat.site_to_pat = shared->site_to_pat;
+        a->pat.codes_p0 = shared->npat * c->rank / c->nranks;
+        a->pat.codes_n = shared->npat * (c->rank + 1) / c->nranks - a->pat.codes_p0;
+        gather_codes(ntax, nsites, chars, shared->first, a->pat.codes_p0, a->pat.codes_n, a->pat.codes);
+    } else if (c->nranks > 1 && !getenv("PEPRML_NO_SHARED_CRUNCH")) {
+        const CrunchShare share = [c](int64_t* order, uint8_t* fresh, int64_t n) {
+            int64_t* d_order = nullptr;
+            uint8_t* d_fresh = nullptr;
+            bool ok = c->cuda(c->dev_alloc(&d_order, sizeof(int64_t) * (size_t)n), "crunch exchange alloc") &&
+                      c->cuda(c->dev_alloc(&d_fresh, (size_t)n), "crunch exchange alloc") &&
+                      c->cuda(cudaMemcpyAsync(d_order, order, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "crunch upload") &&
+                      c->cuda(cudaMemcpyAsync(d_fresh, fresh, (size_t)n, cudaMemcpyHostToDevice, c->stream), "crunch upload");
+            // every rank must enter the collectives, whatever happened locally (a local failure shows up as a sum that is not a permutation)
+            const bool sent = g_nccl.AllReduce(d_order, d_order, (size_t)n, ncclInt64, ncclSum, c->comm, c->stream) == ncclSuccess &&
+                              g_nccl.AllReduce(d_fresh, d_fresh, (size_t)n, ncclUint8, ncclSum, c->comm, c->stream) == ncclSuccess;
+            ok = ok && sent &&
+                 c->cuda(cudaMemcpyAsync(order, d_order, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "crunch download") &&
+                 c->cuda(cudaMemcpyAsync(fresh, d_fresh, (size_t)n, cudaMemcpyDeviceToHost, c->stream), "crunch download") && c->sync();
+            c->dev_free(d_order);
+            c->dev_free(d_fresh);
+            return ok;
+        };
+        crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks, &share);
+    } else {
+        crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks);  // codes of this rank's block only
+    }
     for (int i = 0; i < ntax; ++i) a->pat.names.emplace_back(names[i]);
     if (a->pat.npat == 0) return fail(c, PML_EINVAL, "alignment has no column with positive weight");
     const int64_t np = a->pat.npat;
@@ -1251,7 +1461,7 @@ int pml_tree_load(pml_aln* a, const char* newick, pml_tree** out) {
         pml_tree_free(t.release());
         return PML_ENOMEM;
     }
-    ++a->ntrees;
+    t->model_epoch = a->model_epoch;
     *out = t.release();
     return PML_OK;
 }
@@ -1263,6 +1473,7 @@ void pml_tree_free(pml_tree* t) {
     t->aln->ctx->dev_free(t->d_clv);
     t->aln->ctx->dev_free(t->d_scale);
     t->aln->ctx->dev_free(t->d_len);
+    if (t->aln->sumtable_owner == t) t->aln->sumtable_owner = nullptr;
     delete t;
 }
 
@@ -1310,6 +1521,7 @@ int pml_evaluate(pml_tree* t, const int32_t* weights, double* lnl, double* per_s
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     const int rc = evaluate_branch(t, t->topo.edge[0][0], weights, lnl);
     if (rc != PML_OK || !per_site) return rc;
     std::vector<double> pp(a->npad);
@@ -1326,12 +1538,13 @@ int pml_branch_derivs(pml_tree* t, int branch, double len, const int32_t* weight
     if (!t || branch < 0 || branch >= t->topo.nedges() || !(len >= 0.0)) return PML_EINVAL;
     pml_ctx* c = t->aln->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     double r[3];
     if (t->prepared_branch != branch) {
-        if (!branch_pass(t, branch, dw, len, true, false, r)) return PML_ENODEVICE;
-    } else if (!core_at(t, dw, len, r)) return PML_ENODEVICE;
+        if (!branch_pass(t, branch, dw, len, true, false, r)) return c->fail_code();
+    } else if (!core_at(t, dw, len, r)) return c->fail_code();
     if (lnl) *lnl = r[0];
     if (d1) *d1 = r[1];
     if (d2) *d2 = r[2];
@@ -1342,11 +1555,12 @@ int pml_smooth_branches(pml_tree* t, int sweeps, const int32_t* weights, int* co
     if (!t || sweeps < 1) return PML_EINVAL;
     pml_ctx* c = t->aln->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     bool smoothed = false;
     for (int s = 0; s < sweeps && !smoothed; ++s)
-        if (!smooth_sweep(t, dw, smoothed)) return PML_ENODEVICE;
+        if (!smooth_sweep(t, dw, smoothed)) return c->fail_code();
     if (converged) *converged = smoothed ? 1 : 0;
     return PML_OK;
 }
@@ -1356,21 +1570,22 @@ int pml_optimize(pml_tree* t, int opt_alpha, double eps, const int32_t* weights,
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     if (!(eps > 0.0)) eps = 0.1;
     const int32_t* dw = device_weights(a, weights);
     if (!dw) return PML_ENODEVICE;
     // modOpt: { smooth (2 sweeps max), Brent on alpha, smooth (3 sweeps max) } until a round gains <= eps
     a->alpha_step = 0.1;  // every call brackets alpha from the same first probe: results do not depend on earlier calls
     double cur, best = 0.0;
-    if (evaluate_branch(t, t->topo.edge[0][0], weights, &best) != PML_OK) return PML_ENODEVICE;
+    if (evaluate_branch(t, t->topo.edge[0][0], weights, &best) != PML_OK) return c->fail_code();
     int rounds = 0;
     do {
         cur = best;
-        if (!tree_evaluate(t, weights, dw, 0.0625, &best, opt_alpha != 0)) return PML_ENODEVICE;
+        if (!tree_evaluate(t, weights, dw, 0.0625, &best, opt_alpha != 0)) return c->fail_code();
         if (opt_alpha) {
-            if (!optimise_alpha(t, weights, 1.0e-3, &best)) return PML_ENODEVICE;
+            if (!optimise_alpha(t, weights, 1.0e-3, &best)) return c->fail_code();
         }
-        if (!tree_evaluate(t, weights, dw, 0.1, &best)) return PML_ENODEVICE;
+        if (!tree_evaluate(t, weights, dw, 0.1, &best)) return c->fail_code();
     } while (std::fabs(cur - best) > eps && ++rounds < 200);
     if (lnl) *lnl = best;
     if (alpha) *alpha = a->alpha;
@@ -1478,12 +1693,13 @@ int pml_score_spr_candidates(pml_tree* t, int node, int keep, int radius, const 
     if (node < T.ntax || node >= T.nnodes() || T.slot_of(node, keep) < 0) return fail(t->aln->ctx, PML_EINVAL, "bad (node, keep) pair");
     pml_ctx* c = t->aln->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     std::vector<int> cand = spr_targets(T, node, keep, radius);
     if ((int)cand.size() > *ncand) cand.resize(*ncand);
     std::vector<double> lazy;
-    if (!score_candidates(t, node, keep, cand, dw, lazy)) return PML_ENODEVICE;
+    if (!score_candidates(t, node, keep, cand, dw, lazy)) return c->fail_code();
     int n = 0;
     for (size_t i = 0; i < cand.size(); ++i) {
         if (!std::isfinite(lazy[i])) continue;
@@ -1499,20 +1715,21 @@ int pml_search(pml_tree* t, int radius, int max_rounds, double eps, const int32_
     if (!t || radius < 1 || max_rounds < 1) return PML_EINVAL;
     pml_ctx* c = t->aln->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     if (!(eps > 0.0)) eps = 0.1;
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
     double best;
-    if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return PML_ENODEVICE;
+    if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return c->fail_code();
     SearchStats st;
     for (int round = 0; round < max_rounds; ++round) {
         const double before = best;
-        if (!spr_round(t, dw, radius, best, st)) return PML_ENODEVICE;
+        if (!spr_round(t, dw, radius, best, st)) return c->fail_code();
         // settle all branch lengths on the new topology before the next round
         bool smoothed = false;
         for (int sweep = 0; sweep < 2 && !smoothed; ++sweep)
-            if (!smooth_sweep(t, dw, smoothed)) return PML_ENODEVICE;
-        if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return PML_ENODEVICE;
+            if (!smooth_sweep(t, dw, smoothed)) return c->fail_code();
+        if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return c->fail_code();
         if (best - before < eps) break;
     }
     if (lnl) *lnl = best;
@@ -1532,6 +1749,60 @@ int pml_bootstrap_weights_host(const int32_t* pw, int64_t npat, int64_t* seed, i
     return PML_OK;
 }
 
+int64_t pml_newick_capacity(const pml_aln* a) {
+    if (!a) return PML_EINVAL;
+    size_t longest = 0;
+    for (const std::string& n : a->pat.names) longest = std::max(longest, n.size());
+    return (int64_t)((size_t)a->pat.ntax * (2 * longest + 64) + 64);
+}
+
+int pml_bootstrap_trees(pml_aln* a, int64_t weight_seed, int64_t parsimony_seed, int nrep, int first, int stride, int radius,
+                        int rounds, double eps, char* newicks, size_t cap, double* lnl, double* seconds) {
+    if (!a || nrep < 0 || first < 0 || stride < 1 || radius < 1 || rounds < 0 || (!newicks && cap > 0)) return PML_EINVAL;
+    pml_ctx* c = a->ctx;
+    if (!c->bind()) return PML_ENODEVICE;
+    if (!(eps > 0.0)) eps = 0.1;
+    const int64_t np = a->pat.npat;
+    // the WHOLE weight stream is drawn (it is sequential by construction), so replicate r carries the same weights whatever
+    // the sharding; only this share's vectors are kept
+    std::vector<int32_t> w((size_t)np), mine;
+    std::vector<int> ids;
+    int64_t seed = weight_seed;
+    for (int r = 0; r < nrep; ++r) {
+        bootstrap_replicates(&seed, a->pat.weight, 1, w.data());
+        if (r >= first && (r - first) % stride == 0) {
+            mine.insert(mine.end(), w.begin(), w.end());
+            ids.push_back(r);
+        }
+    }
+    std::string text;
+    const double alpha_saved = a->alpha;
+    for (size_t k = 0; k < ids.size(); ++k) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int32_t* wk = mine.data() + k * (size_t)np;
+        pml_tree* t = nullptr;
+        int rc = pml_model_set(a, nullptr, 1.0);
+        if (rc == PML_OK) rc = pml_tree_start_parsimony(a, parsimony_seed + 1 + ids[k], wk, &t);
+        double l = 0.0, al = 1.0;
+        if (rc == PML_OK) rc = pml_optimize(t, 1, 5.0, wk, &l, &al);
+        int moves = 0;
+        if (rc == PML_OK && rounds > 0) rc = pml_search(t, radius, rounds, eps, wk, &l, &moves);
+        if (rc != PML_OK) {
+            pml_tree_free(t);
+            return rc;
+        }
+        const std::string nw = write_newick_result(t->topo, a->pat.names);
+        text += nw.substr(0, nw.size() - 5) + ";\n";  // RAxML_bootstrap form: no ":0.0" after the last parenthesis
+        if (lnl) lnl[ids[k]] = l;
+        pml_tree_free(t);
+        if (seconds) seconds[ids[k]] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    pml_model_set(a, nullptr, alpha_saved);
+    if (text.size() + 1 > cap) return fail(c, PML_EINVAL, "pml_bootstrap_trees: buffer too small (see pml_newick_capacity)");
+    if (newicks) std::memcpy(newicks, text.c_str(), text.size() + 1);
+    return PML_OK;
+}
+
 int pml_crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_weights, uint8_t* codes_out,
                         int32_t* weights_out, int64_t* site_to_pattern, int64_t* npatterns) {
     if (ntax < 1 || nsites < 1 || !chars || !npatterns) return PML_EINVAL;
@@ -1544,11 +1815,65 @@ int pml_crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const in
     return PML_OK;
 }
 
+int pml_crunch_patterns_sharded(int nranks, int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_weights,
+                                uint8_t* codes_out, int32_t* weights_out, int64_t* site_to_pattern, int64_t* npatterns) {
+    if (nranks < 1 || nranks > 64 || ntax < 1 || nsites < 1 || !chars || !npatterns) return PML_EINVAL;
+    // the ranks of a multi-process group, played by threads: the exchange is an element-wise sum behind a barrier
+    struct Exchange {
+        std::mutex mu;
+        std::condition_variable cv;
+        int arrived = 0, generation = 0;
+        std::vector<int64_t> order;
+        std::vector<uint8_t> fresh;
+    } ex;
+    std::vector<Patterns> pats(nranks);
+    std::vector<std::thread> pool;
+    for (int r = 0; r < nranks; ++r)
+        pool.emplace_back([&, r] {
+            const CrunchShare share = [&](int64_t* order, uint8_t* fresh, int64_t n) {
+                std::unique_lock<std::mutex> lock(ex.mu);
+                if (ex.arrived == 0) {
+                    ex.order.assign((size_t)n, 0);
+                    ex.fresh.assign((size_t)n, 0);
+                }
+                for (int64_t i = 0; i < n; ++i) {
+                    ex.order[i] += order[i];
+                    ex.fresh[i] = (uint8_t)(ex.fresh[i] + fresh[i]);
+                }
+                const int gen = ex.generation;
+                if (++ex.arrived == nranks) {
+                    ++ex.generation;
+                    ex.cv.notify_all();
+                } else ex.cv.wait(lock, [&] { return ex.generation != gen; });
+                std::copy(ex.order.begin(), ex.order.end(), order);
+                std::copy(ex.fresh.begin(), ex.fresh.end(), fresh);
+                if (--ex.arrived == 0) ex.order.clear();
+                return true;
+            };
+            crunch_patterns(ntax, nsites, chars, site_weights, pats[r], r, nranks, &share);
+        });
+    for (auto& th : pool) th.join();
+    const Patterns& p0 = pats[0];
+    for (int r = 1; r < nranks; ++r)
+        if (pats[r].npat != p0.npat || pats[r].weight != p0.weight || pats[r].site_to_pat != p0.site_to_pat || pats[r].first != p0.first)
+            return fail(nullptr, PML_ESTATE, "sharded pattern crunch: ranks disagree");
+    *npatterns = p0.npat;
+    if (codes_out)  // every rank gathered the codes of its own block: put the blocks side by side
+        for (int r = 0; r < nranks; ++r)
+            for (int t = 0; t < ntax; ++t)
+                std::copy(pats[r].codes.begin() + (size_t)t * pats[r].codes_n, pats[r].codes.begin() + (size_t)(t + 1) * pats[r].codes_n,
+                          codes_out + (size_t)t * p0.npat + pats[r].codes_p0);
+    if (weights_out) std::copy(p0.weight.begin(), p0.weight.end(), weights_out);
+    if (site_to_pattern) std::copy(p0.site_to_pat.begin(), p0.site_to_pat.end(), site_to_pattern);
+    return PML_OK;
+}
+
 int pml_evaluate_replicates(pml_tree* t, const int32_t* W, int nrep, double* lnl) {
     if (!t || !W || nrep < 1 || !lnl) return PML_EINVAL;
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
     if (!c->bind()) return PML_ENODEVICE;
+    adopt_model(t);
     double base;
     const int rc = evaluate_branch(t, t->topo.edge[0][0], nullptr, &base);  // fills d_site_lnl
     if (rc != PML_OK) return rc;

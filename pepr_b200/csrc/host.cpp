@@ -112,7 +112,8 @@ struct ColumnSorter {
 
 }  // namespace
 
-void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank, int nranks) {
+void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank, int nranks,
+                     const CrunchShare* share) {
     out.ntax = ntax;
     out.nsites = nsites;
     ColumnSorter cs{ntax, nsites, chars, {}};
@@ -146,9 +147,43 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
         for (int64_t i = 0; i < n; ++i) tmp[pos[cs.lut[chars[order[i]]]]++] = order[i];
         order.swap(tmp);
         lap("level 0");
-        parallel_for(kCodes, threads, [&](int64_t c) { cs.sort_range(order.data(), tmp.data(), fresh.data(), count[c], count[c + 1], 1); });
+        // buckets of this rank: all of them, or -- when the ranks share the sort -- its part of a greedy balanced split
+        bool mine[kCodes];
+        for (int c = 0; c < kCodes; ++c) mine[c] = true;
+        const bool shared = share != nullptr && nranks > 1;
+        if (shared) {
+            int by_size[kCodes];
+            for (int c = 0; c < kCodes; ++c) by_size[c] = c;
+            std::stable_sort(by_size, by_size + kCodes, [&](int a, int b) { return count[a + 1] - count[a] > count[b + 1] - count[b]; });
+            std::vector<int64_t> load(nranks, 0);
+            for (int i = 0; i < kCodes; ++i) {
+                const int c = by_size[i];
+                const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                load[r] += count[c + 1] - count[c];
+                mine[c] = r == rank;
+            }
+        }
+        parallel_for(kCodes, threads, [&](int64_t c) {
+            if (mine[c]) cs.sort_range(order.data(), tmp.data(), fresh.data(), count[c], count[c + 1], 1);
+            else {
+                std::fill(order.begin() + count[c], order.begin() + count[c + 1], 0);
+                std::fill(fresh.begin() + count[c], fresh.begin() + count[c + 1], 0);
+            }
+        });
+        lap("radix");
+        if (shared && !(*share)(order.data(), fresh.data(), n)) {
+            // the exchange failed: finish alone (costs time, not correctness).  Every rank sees the same failure.
+            std::vector<int64_t> again;
+            again.reserve(n);
+            for (int64_t s = 0; s < nsites; ++s)
+                if (!site_w || site_w[s] > 0) again.push_back(s);
+            for (int c = 0; c < kCodes; ++c) pos[c] = count[c];
+            for (int64_t i = 0; i < n; ++i) order[pos[cs.lut[chars[again[i]]]]++] = again[i];
+            std::fill(fresh.begin(), fresh.end(), 1);
+            parallel_for(kCodes, threads, [&](int64_t c) { cs.sort_range(order.data(), tmp.data(), fresh.data(), count[c], count[c + 1], 1); });
+        }
     }
-    lap("radix");
+    lap("exchange");
     // pattern index of every sorted column = running count of boundaries (two parallel passes over chunks)
     const int64_t chunk = 1 << 15, nchunks = (n + chunk - 1) / chunk;
     std::vector<int64_t> base(nchunks + 1, 0);
@@ -183,24 +218,33 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
     lap("weights");
     out.codes_p0 = out.npat * rank / nranks;
     out.codes_n = out.npat * (rank + 1) / nranks - out.codes_p0;
-    out.codes.assign((size_t)ntax * out.codes_n, 22);
+    gather_codes(ntax, nsites, chars, first, out.codes_p0, out.codes_n, out.codes);
+    out.first.swap(first);
+    lap("codes");
+}
+
+void gather_codes(int ntax, int64_t nsites, const uint8_t* chars, const std::vector<int64_t>& first, int64_t p0, int64_t n,
+                  std::vector<uint8_t>& codes) {
+    uint8_t lut[256];
+    for (int ch = 0; ch < 256; ++ch) lut[ch] = (uint8_t)residue_code((unsigned char)ch);
+    const int threads = nsites >= 20000 ? crunch_threads() : 1;
+    codes.assign((size_t)ntax * n, 22);
     // gather of the representatives' codes, two taxon rows per pass over the (32-bit) column list
     std::vector<uint32_t> first32;
     const bool narrow = nsites < (int64_t)1 << 32;
-    if (narrow) first32.assign(first.begin() + out.codes_p0, first.begin() + out.codes_p0 + out.codes_n);
+    if (narrow) first32.assign(first.begin() + p0, first.begin() + p0 + n);
     parallel_for((ntax + 1) / 2, threads, [&](int64_t pair) {
         const int t0r = (int)(2 * pair), t1r = std::min(ntax - 1, t0r + 1);
         const uint8_t* row0 = chars + (size_t)t0r * nsites;
         const uint8_t* row1 = chars + (size_t)t1r * nsites;
-        uint8_t* dst0 = out.codes.data() + (size_t)t0r * out.codes_n;
-        uint8_t* dst1 = out.codes.data() + (size_t)t1r * out.codes_n;
-        for (int64_t p = 0; p < out.codes_n; ++p) {
-            const size_t s = narrow ? (size_t)first32[p] : (size_t)first[out.codes_p0 + p];
-            dst0[p] = cs.lut[row0[s]];
-            dst1[p] = cs.lut[row1[s]];
+        uint8_t* dst0 = codes.data() + (size_t)t0r * n;
+        uint8_t* dst1 = codes.data() + (size_t)t1r * n;
+        for (int64_t p = 0; p < n; ++p) {
+            const size_t s = narrow ? (size_t)first32[p] : (size_t)first[p0 + p];
+            dst0[p] = lut[row0[s]];
+            dst1[p] = lut[row1[s]];
         }
     });
-    lap("codes");
 }
 
 bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,
@@ -730,6 +774,7 @@ bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv)
     mv.len_q = T.len[mv.e_q];
     mv.len_r = T.len[mv.e_r];
     mv.len_t = T.len[target];
+    mv.len_s = T.len[mv.e_s];
     // prune: q -- r through branch e_q
     set_link(T, mv.q, p, mv.r, mv.e_q);
     set_link(T, mv.r, p, mv.q, mv.e_q);
@@ -833,6 +878,10 @@ void spr_undo(Topology& T, ViewState& V, const SprMove& mv) {
     V.branch_changed(T, mv.e_q);
     V.branch_changed(T, mv.e_t);
     V.branch_changed(T, mv.e_r);
+    if (T.len[mv.e_s] != mv.len_s) {  // the caller re-optimised the subtree's branch on the rejected topology
+        T.len[mv.e_s] = mv.len_s;
+        V.branch_changed(T, mv.e_s);
+    }
 }
 
 std::vector<int> spr_targets(const Topology& T, int p, int s, int radius) {

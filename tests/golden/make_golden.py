@@ -241,6 +241,44 @@ def case_search_fasttree(d):
 CASES["search_fasttree"] = case_search_fasttree
 
 
+def case_search_parsimony(d):
+    """adds to search.json what RAxMLRunner.runRaxmlParsimonyWithBranchLengths produces (RAxMLRunner.java:215-280):
+    `-f d -y` -> RAxML_parsimonyTree, then `-f e -t` on it -> RAxML_result.<run>BL; and FastTree_WAG under a topological
+    constraint in the 0/1 alignment form FastTreeRunner writes (FastTreeRunner.java:243-273)"""
+    toks = gzip.open(os.path.join(d, "search.phy.gz"), "rt").read().split()
+    n = int(toks[0])
+    names, seqs = toks[2::2][:n], toks[3::2][:n]
+    tmp = tempfile.mkdtemp()
+    synth.write_phylip(os.path.join(tmp, "t.phy"), names, seqs)
+    run([RAX, "-f", "d", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "py", "-y", "-p", "12345"], tmp)
+    ptree = open(os.path.join(tmp, "RAxML_parsimonyTree.py")).read().strip()
+    run([RAX, "-f", "e", "-m", "PROTGAMMAWAG", "-s", "t.phy", "-n", "pyBL", "-t", "RAxML_parsimonyTree.py"], tmp)
+    g = json.load(open(os.path.join(d, "search.json")))
+    g["fy"] = info(tmp, "pyBL")
+    g["fy"]["parsimony_tree"] = ptree
+    g["fy"]["tree"] = open(os.path.join(tmp, "RAxML_result.pyBL")).read().strip()
+    # a constraint that CONTRADICTS the data: the first taxa of two different clades of the -f d tree forced together
+    sets = []
+    taxa = sorted(orc._leafsets(orc._parse_topology(g["fd"]["tree"]), sets))
+    cherries = [sorted(x) for x in sets if len(x) == 2]
+    forced = sorted([cherries[0][0], cherries[1][0], cherries[2][0]])
+    with open(os.path.join(tmp, "s.faa"), "w") as f:
+        for a, b in zip(names, seqs):
+            f.write(">%s\n%s\n" % (a, b))
+    with open(os.path.join(tmp, "c.txt"), "w") as f:
+        for a in names:
+            f.write(">%s\n%s\n" % (a, "1" if a in forced else "0"))
+    r = subprocess.run([FASTTREE, "-gamma", "-nosupport", "-constraints", "c.txt", "s.faa"], cwd=tmp, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    g["fasttree_constrained"] = {"forced_clade": forced, "tree": r.stdout.strip().splitlines()[0]}
+    json.dump(g, open(os.path.join(d, "search.json"), "w"), indent=1)
+    shutil.rmtree(tmp)
+
+
+CASES["search_parsimony"] = case_search_parsimony
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or list(CASES)
     for c in which:

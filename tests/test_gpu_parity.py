@@ -251,3 +251,37 @@ def test_real_data_per_site_lnl_and_search(gpu_ctx, golden):
     l2, a2 = t2.optimize(True, 0.1)
     assert l2 >= g.meta["fd"]["lnl"] - 0.5, (l2, g.meta["fd"]["lnl"])
     t2.close(); aln.close()
+
+
+def test_two_trees_on_one_alignment_do_not_see_each_others_state(gpu_ctx, golden):
+    """The model constants and the product table live with the alignment, the views with each tree: changing alpha through
+    tree A, or filling the table from tree B, must not leave the other tree on stale state (no manual invalidate here)."""
+    g = golden("small")
+    fe = g.meta["fe"]
+    m = orc.Model()
+    aln = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=fe["alpha"])
+    ta = pb.Tree(aln, fe["tree"])
+    tb = pb.Tree(aln, g.meta["fw"]["tree"])                      # same topology family, other branch lengths
+    la, lb = ta.evaluate(), tb.evaluate()                        # both trees now hold views computed under fe's alpha
+    ota, otb = orc.Tree(fe["tree"], g.names), orc.Tree(g.meta["fw"]["tree"], g.names)
+    assert abs(lb - orc.evaluate(m, otb, g.pat, g.w, fe["alpha"])) <= REL_ORACLE * abs(lb)
+    # alpha moves under tree B's feet
+    aln.set_model(0.37)
+    want_b = orc.evaluate(m, otb, g.pat, g.w, 0.37)
+    assert abs(tb.evaluate() - want_b) <= REL_ORACLE * abs(want_b)
+    want_a = orc.evaluate(m, ota, g.pat, g.w, 0.37)
+    assert abs(ta.evaluate() - want_a) <= REL_ORACLE * abs(want_a)
+    # an optimisation on A changes alpha again (through the engine this time); B must follow without being told
+    _, alpha = ta.optimize(True, 0.1)
+    want_b = orc.evaluate(m, otb, g.pat, g.w, alpha)
+    assert abs(tb.evaluate() - want_b) <= REL_ORACLE * abs(want_b)
+    # product table: A prepares branch 2, B overwrites the shared table with its own branch 2, A asks again at another length
+    a0 = ta.branch_derivs(2, 0.11)
+    b0 = tb.branch_derivs(2, 0.23)
+    a1 = ta.branch_derivs(2, 0.17)
+    fresh = pb.Tree(aln, ta.newick().replace("):0.0;", ");"))
+    want = fresh.branch_derivs(2, 0.17)
+    for x, y in zip(a1, want):
+        assert abs(x - y) <= 1e-9 * max(1.0, abs(y)), (a1, want)
+    assert a0 != a1 and b0 != a1
+    fresh.close(); ta.close(); tb.close(); aln.close()

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import pepr_b200 as pb
+from oracle import oracle as orc
 from pepr_b200 import runner as R
 
 pytestmark = pytest.mark.gpu
@@ -206,3 +207,42 @@ def test_cli_on_the_reference_example_genomes(tmp_path, golden):
     ref = np.array(g.meta["fg"]["per_site"])
     # `-f g` re-optimises the model on the given tree like raxmlHPC does, so alpha (hence every site) moves in the 4th decimal
     assert got.shape == ref.shape and abs(got.sum() - ref.sum()) < 0.1 and np.abs(got - ref).max() < 5e-3
+
+
+def _splits(newick):
+    sets = []
+    taxa = sorted(orc._leafsets(orc._parse_topology(newick), sets))
+    return {orc._canon(x, taxa) for x in sets if 1 < len(x) < len(taxa) - 1}
+
+
+def test_runner_parsimony_with_branch_lengths_is_y_then_f_e(gpu_ctx, golden):
+    """runRaxmlParsimonyWithBranchLengths (RAxMLRunner.java:215-280) = `-f d -y`, then `-f e -t` on that topology -- NOT a
+    topology search.  Golden `fy`: what raxmlHPC gives for exactly that pair of runs on the `search` alignment."""
+    g = golden("search")
+    fy = g.meta["fy"]
+    r = R.B200MLRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    # (1) the `-f e` half on raxmlHPC's own parsimony tree: its lnL within raxmlHPC's stopping tolerance
+    r.setStartTree(fy["parsimony_tree"])
+    r.run()
+    assert r.last_error is None and abs(r.getLikelihood() - fy["lnl"]) < 0.1, (r.getLikelihood(), fy["lnl"])
+    assert r.getParsimonyWithBLTree() == ""                     # not a parsimony-with-BL run: the reference finds no such file
+    # (2) the whole thing: the engine's own parsimony tree (another random addition order), branch lengths on THAT topology
+    r2 = R.B200MLRunner(ctx=gpu_ctx)
+    r2.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r2.setParsimonyWithBL(True)
+    r2.run()
+    assert r2.last_error is None
+    ptree, bl = r2.getParsimonyTree(), r2.getParsimonyWithBLTree()
+    assert ":" not in ptree and bl.endswith("):0.0;")
+    assert _splits(bl.replace("):0.0;", ");")) == _splits(ptree)            # the topology was not searched
+    host, _ = pb.parsimony_tree(g.names, g.seqs, 12345)
+    assert _splits(host.replace("):0.0;", ");")) == _splits(ptree)          # it IS the stepwise-addition parsimony tree
+    # two near-optimal parsimony trees of one alignment: likelihoods close, both below the ML search's tree
+    assert abs(r2.getLikelihood() - fy["lnl"]) < 40.0 and r2.getLikelihood() <= g.meta["fd"]["lnl"] + 0.5
+    # parsimony only (`-y`): no likelihood at all
+    r3 = R.B200MLRunner(ctx=gpu_ctx)
+    r3.setAlignment(R.SequenceAlignment(g.names, g.seqs))
+    r3.setParsimonyOnly(True)
+    r3.run()
+    assert r3.getParsimonyTree() == ptree and r3.getBestTree() == "" and r3.getLikelihood() is None

@@ -90,6 +90,25 @@ def test_pattern_crunch_threaded_radix_path_matches_oracle():
         assert w.sum() == (chars.shape[1] if weights is None else int(sw.sum()))
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_pattern_crunch_shared_between_ranks_equals_single_rank(golden, nranks):
+    """N > 1: every rank sorts only its first-residue buckets and the sorted column order is exchanged by a sum
+    (pml_aln_load does it with NCCL); patterns, weights, site map and the ranks' code blocks put side by side must be
+    bit-identical to the single-rank crunch -- on a golden alignment and on the threaded large-input path"""
+    g = golden("wide")
+    codes, w, s2p = pb.crunch_patterns(g.seqs, nranks=nranks)
+    assert (codes == g.pat).all() and (w == g.w).all() and (s2p == g.s2p).all()
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ARNDCQEGHILKMFPSTWYV-?XBZ", np.uint8)
+    base = letters[rng.integers(0, len(letters), size=(7, 700))]
+    chars = np.ascontiguousarray(base[:, rng.integers(0, 700, size=50_000)])
+    sw = rng.integers(0, 3, size=chars.shape[1]).astype(np.int32)
+    for weights in (None, sw):
+        one = pb.crunch_patterns(chars, weights)
+        many = pb.crunch_patterns(chars, weights, nranks=nranks)
+        assert all((a == b).all() for a, b in zip(one, many))
+
+
 def test_bootstrap_weights_bit_exact_with_reference(golden):
     g = golden("small")
     fj = g.meta["fj"]
