@@ -39,12 +39,9 @@ NTAX = 100
 SITES_PER_GPU = 100_000
 SEED = 3
 # Per pattern and kernel kind: algorithmic bytes (CLV traffic + tip codes + weights) and DMMA.8x8x4 issued per
-# 16-pattern tile and category warp.  One DMMA = 512 flop; four category warps per tile.
-KIND = {
-    "newview_tip_tip": (642, 0), "newview_tip_inner": (1281, 30), "newview_inner_inner": (1920, 60),
-    "evaluate": (660, 42), "branch_inner_inner": (1292, 72), "branch_tip_inner": (652, 42), "core": (648, 0),
-    "fused_ii_inner": (2560, 132), "fused_ii_tip": (1921, 102), "fused_ti_inner": (1921, 102), "fused_ti_tip": (1282, 72),
-}
+# 16-pattern tile and category warp come from the engine (pml_kind_info).  One DMMA = 512 flop; four
+# category warps per tile.
+KIND = {}
 FP64_PEAK_TFLOPS = 37.0
 FP64_PEAK_SOURCE = ("FP64 DMMA.8x8x4, measured on a pool B200 with tools/fp64_peak.cu (profiles/r01_fp64_pipe_peaks.log: 37.0 TFLOP/s "
                     "sustained, DFMA 33.5, one shared pipe); MEASURED_PEAKS.json carries no FP64 figure")
@@ -267,6 +264,8 @@ def main():
     import numpy as np
     import torch
     import pepr_b200 as pb
+    from pepr_b200 import engine as _eng
+    KIND.update({name: (b, d) for name, b, d in _eng.kinds()})
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -475,8 +474,7 @@ def main():
     e_wall = reduce_max(time.perf_counter() - t0)
     e2e_value = reduce_sum(float(e_su)) / e_wall
     # device -> host: every branch pass publishes five flagged doubles (80 B) through mapped memory; + the result tree
-    pass_kinds = ("evaluate", "branch_inner_inner", "branch_tip_inner", "core", "fused_ii_inner", "fused_ii_tip", "fused_ti_inner", "fused_ti_tip")
-    npass = sum(prof[k][1] for k in pass_kinds) / args.steps
+    npass = sum(v[1] for k, v in prof.items() if k.startswith(("evaluate", "branch", "core", "fused"))) / args.steps
     d2h = int(80 * npass + nwlen)
 
     # ---- strong scaling: 100 taxa x strong_sites IN TOTAL over the N ranks -------------------------------------------------

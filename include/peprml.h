@@ -125,11 +125,16 @@ int64_t pml_tree_nr_retries(const pml_tree *);
 /* ---- device-side timing of the engine's own kernels (CUDA events on the context's stream) -------------------
  * Between begin and end every launch of kind k is bracketed by a pair of events; end() synchronises and returns, per
  * kind, the summed device milliseconds, the launch count and the pattern rows processed.
- * kinds: 0 newview tip-tip, 1 newview tip-inner, 2 newview inner-inner, 3 root evaluate (branch pass with per-pattern lnL),
- * 4 branch pass between two inner nodes, 5 NR core on a stored table, 6 branch pass with a tip end,
- * 7-10 fused CLV update + branch pass: 7 inner children / inner far end, 8 inner children / tip far end, 9 one tip child /
- * inner far end, 10 one tip child / tip far end. */
-#define PML_NKINDS 11
+ * A side of an update or of a branch is an inner node (I), a tip (T) or a folded cherry (C: an inner node whose two children
+ * on that side are tips; its CLV is formed inside the consuming kernel and never stored).  Kinds:
+ *   0..5   CLV update by its two children: TT (stored cherry), TI, II, TC, CC, CI
+ *   6..8   branch pass, one end an inner node, the other I / T / C;   9..11  the same as root evaluate (per-pattern lnL kept)
+ *   12     Newton-Raphson iteration on a stored product table
+ *   13..27 fused CLV update + branch pass: 13 + 3 * (children of the update: TI, II, TC, CC, CI) + (far end: I, T, C)
+ * pml_kind_info gives a kind's name, its algorithmic bytes per pattern (CLV rows read and written + tip codes +
+ * weights) and the DMMA.8x8x4 it issues per 16-pattern tile and rate-category warp (512 flop each, four warps per tile). */
+#define PML_NKINDS 28
+int pml_kind_info(int kind, char *name, size_t cap, int *bytes_per_pattern, int *dmma_per_tile);
 int pml_profile_begin(pml_ctx *);
 int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKINDS], int64_t rows[PML_NKINDS]);
 

@@ -23,16 +23,19 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "peprml.h"), __file__]
     if force or _stale(LIB, deps):
-        objs = []
+        objs, jobs = [], []
         os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
         for s in SOURCES:
             o = os.path.join(HERE, "build", s + ".o")
             if force or _stale(o, deps):
-                cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-dc" if False else "-c", os.path.join(CSRC, s), "-o", o]
+                cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
                 if verbose:
                     print(" ".join(cmd))
-                subprocess.run(cmd, check=True)
+                jobs.append((cmd, subprocess.Popen(cmd)))   # the translation units compile side by side
             objs.append(o)
+        for cmd, job in jobs:
+            if job.wait() != 0:
+                raise subprocess.CalledProcessError(job.returncode, cmd)
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))

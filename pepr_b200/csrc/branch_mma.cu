@@ -21,6 +21,7 @@
 
 #include "kernels.h"
 #include "mma_common.cuh"
+#include "pmatrix.cuh"
 
 namespace pml {
 
@@ -36,26 +37,31 @@ constexpr int kRedSlots = 4;                            // row-sum slots between
 constexpr int kFinishBarrier = 3;                       // named barrier of the two finishing warps
 constexpr int kStageBarrier = 2;                        // named barrier of all warps but the producer (prologue)
 
-template <bool kTipA>
+// KA: what the a end is -- an inner node, a tip, or a folded cherry (Side in kernels.h; the b end is always an inner node)
+template <int KA>
 struct BranchPlan {
-    static constexpr int kInner = kTipA ? 1 : 2;
+    static constexpr bool kTipA = KA == kSideTip, kChA = KA == kSideCherry;
+    static constexpr int kInner = KA == kSideInner ? 2 : 1;
     // a stage = the CLV tiles of the inner ends + 256 B of per-row side data that travels with them:
     // [0,64) scaling counts of b, [64,128) scaling counts of a, [128,192) pattern weights, [192,208) residue codes of a
+    // (a cherry's first tip), [208,224) residue codes of a cherry's second tip
     static constexpr int kAuxDoubles = 32;
     static constexpr int kStageDoubles = kInner * kTileDoubles + kAuxDoubles;
-    static constexpr int kTipDoubles = kTipA ? kCodes * kTipVecPad : 0;
+    // tip: 23 x 20 table of pi V sums; cherry: the two 23 x 80 look-ups of its tips
+    static constexpr int kTipDoubles = kTipA ? kCodes * kTipVecPad : (kChA ? 2 * kCodes * kTipPad : 0);
     static constexpr int kRedDoubles = kRedSlots * kCats * kTileRows * 3;  // [slot][cat][row][f, f', f'']
     static constexpr int kSideInts = kRedSlots * kTileRows * 2;            // [slot][row][scaling count, weight]
     static constexpr int kExpDoubles = 3 * kCats * 24;                     // exp(lambda r t) * {1, lambda r, (lambda r)^2}, padded to 24 states
-    static constexpr int kMatDoubles = 2 * kStates * kStates;              // Vinv and pi V staged once per CTA
+    static constexpr int kMatDoubles = 3 * kStates * kStates;              // V (cherry end only), Vinv and pi V staged once per CTA
     static constexpr size_t kBarBytes = 256;
     static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(kTipDoubles + kRedDoubles + 8 + kExpDoubles + kMatDoubles) +
                                      sizeof(int) * kSideInts + sizeof(double) * (size_t)(kMmaGroups * kBranchDepth * kStageDoubles);
 };
 
-template <bool kTipA, bool kStore>
+template <int KA, bool kStore>
 __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs args, int ntiles) {
-    using Plan = BranchPlan<kTipA>;
+    using Plan = BranchPlan<KA>;
+    constexpr bool kTipA = Plan::kTipA, kChA = Plan::kChA, kInnerA = KA == kSideInner;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* in_full = reinterpret_cast<uint64_t*>(smem_raw);     // [group][kBranchDepth]
     uint64_t* in_empty = in_full + kMmaGroups * kBranchDepth;       // [group][kBranchDepth]
@@ -65,9 +71,10 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     double* s_red = s_tip + Plan::kTipDoubles;
     double* s_fin = s_red + Plan::kRedDoubles;                      // [2 finishing warps][3] (+2 spare)
     double* s_exp = s_fin + 8;                                      // [3][kCats][24]
-    double* s_vinv = s_exp + Plan::kExpDoubles;                     // [k][i]
+    double* s_v = s_exp + Plan::kExpDoubles;                        // [i][k]  (V, Vinv: the layout pmatrix.cuh builds P from)
+    double* s_vinv = s_v + kStates * kStates;                       // [k][i]
     double* s_piv = s_vinv + kStates * kStates;                     // [i][k]
-    int2* s_side = reinterpret_cast<int2*>(s_vinv + Plan::kMatDoubles);
+    int2* s_side = reinterpret_cast<int2*>(s_v + Plan::kMatDoubles);
     double* s_stage = reinterpret_cast<double*>(s_side + kRedSlots * kTileRows);
     const DeviceModel* dm = args.dm;
 
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     // of this SM waits behind them (measured: 10,000 cycles of prologue when the order was the other way round).
     constexpr int kStagers = kProducerWarp * 32;  // every warp but the producer
     const int tid = threadIdx.x;
-    double pre_vinv[2] = {0.0, 0.0}, pre_piv[2] = {0.0, 0.0}, pre_lambda = 0.0, pre_rate = 0.0;
+    double pre_vinv[2] = {0.0, 0.0}, pre_piv[2] = {0.0, 0.0}, pre_v[2] = {0.0, 0.0}, pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0;
     pdl_launch_dependents();
     if (warp != kProducerWarp) {
 #pragma unroll
@@ -87,8 +94,11 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             if (idx < kStates * kStates) {
                 pre_vinv[q] = (&dm->Vinv[0][0])[idx];
                 pre_piv[q] = (&dm->piV[0][0])[idx];
+                if (kChA) pre_v[q] = (&dm->V[0][0])[idx];
             }
         }
+        // cherry end: MMA warp w builds the look-up of tip (w >> 2) for category w & 3; lane k < 20 holds lambda_k * r_c
+        if (kChA && warp < kMmaWarps && lane < kStates) lr = dm->lambda[lane] * dm->rates[warp & 3];
         if (tid < kCats * 24 && tid % 24 < kStates) {
             pre_lambda = dm->lambda[tid % 24];
             pre_rate = dm->rates[tid / 24];
@@ -108,6 +118,8 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     pdl_wait();  // from here on the kernel touches what its predecessors wrote (see mma_common.cuh)
     // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
     const double tt = args.t_ptr ? nr_clamp_length(*args.t_ptr) : args.t;
+    double tip_len = 0.0;
+    if (kChA && warp < kMmaWarps) tip_len = (warp >> 2) == 0 ? *args.a.len1 : *args.a.len2;
     __syncthreads();
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, row-sum slot n % 4
@@ -122,20 +134,23 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             uint64_t* full = in_full + grp * kBranchDepth + slot;
             if (lane == 0) {
                 mbar_wait(in_empty + grp * kBranchDepth + slot, ((j / kBranchDepth) & 1) ^ 1);
-                mbar_expect_tx(full, Plan::kInner * (bytes + int_bytes) + int_bytes + (kTipA ? kTileRows : 0));
+                mbar_expect_tx(full, Plan::kInner * (bytes + int_bytes) + int_bytes + (kTipA ? kTileRows : 0) + (kChA ? 2 * kTileRows : 0));
             }
             __syncwarp();
             const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
             const size_t goff = tile * kTileDoubles;
             double* dst = s_stage + (size_t)(grp * kBranchDepth + slot) * Plan::kStageDoubles;
             unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
-            if (lane == 0) bulk_g2s(dst + (kTipA ? 0 : kTileDoubles), args.b.clv + goff, bytes, full);
+            if (lane == 0) bulk_g2s(dst + (kInnerA ? kTileDoubles : 0), args.b.clv + goff, bytes, full);
             else if (lane == 1) {
-                if (!kTipA) bulk_g2s(dst, args.a.clv + goff, bytes, full);
+                if (kInnerA) bulk_g2s(dst, args.a.clv + goff, bytes, full);
                 else bulk_g2s(aux + 192, args.a.codes + tile * kTileRows, kTileRows, full);
             } else if (lane == 2) bulk_g2s(aux, args.b.scale + tile * kTileRows, int_bytes, full);
             else if (lane == 3) bulk_g2s(aux + 128, args.weights + tile * kTileRows, int_bytes, full);
-            else if (lane == 4 && !kTipA) bulk_g2s(aux + 64, args.a.scale + tile * kTileRows, int_bytes, full);
+            else if (lane == 4) {
+                if (kInnerA) bulk_g2s(aux + 64, args.a.scale + tile * kTileRows, int_bytes, full);
+                else if (kChA) bulk_g2s(aux + 208, args.a.codes2 + tile * kTileRows, kTileRows, full);
+            }
         }
         return;
     }
@@ -147,6 +162,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         if (idx < kStates * kStates) {
             s_vinv[idx] = pre_vinv[q];
             s_piv[idx] = pre_piv[q];
+            if (kChA) s_v[idx] = pre_v[q];
         }
     }
     if (tid < kCats * 24) {
@@ -168,6 +184,14 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             else
                 for (int i = 0; i < kStates; ++i) acc += s_piv[i * kStates + k];
             s_tip[code * kTipVecPad + k] = acc;
+        }
+    }
+    if (kChA) {
+        named_barrier(kStageBarrier, kStagers);  // V and Vinv are in place
+        if (warp < kMmaWarps) {
+            double acc[3][3][2];
+            pmat::build_p_tiles(s_v, exp(lr * tip_len), lane, acc);
+            pmat::tiles_to_lookup(acc, lane, warp & 3, s_tip + (warp >> 2) * kCodes * kTipPad, kTipPad);
         }
     }
     named_barrier(kStageBarrier, kStagers);
@@ -286,7 +310,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         const int k = nt * 8 + g;
 #pragma unroll
         for (int kt = 0; kt < 5; ++kt) {
-            fragA[nt][kt] = (!kTipA && k < kStates) ? s_piv[kmap(kt, t) * kStates + k] : 0.0;
+            fragA[nt][kt] = (!kTipA && k < kStates) ? s_piv[kmap(kt, t) * kStates + k] : 0.0;   // inner or cherry end
             fragB[nt][kt] = k < kStates ? s_vinv[k * kStates + kmap(kt, t)] : 0.0;
         }
     }
@@ -319,15 +343,16 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         int2 side = make_int2(0, 0);  // category-0 warp, lanes 0-15: scaling counts and weight of row `lane`
         if (c == 0 && lane < kTileRows) {
             const int32_t* ai = reinterpret_cast<const int32_t*>(aux);
-            side.x = ai[lane] + (kTipA ? 0 : ai[kTileRows + lane]);
+            side.x = ai[lane] + (kInnerA ? ai[kTileRows + lane] : 0);
             side.y = ai[2 * kTileRows + lane];
         }
         AFrag fa[2], fb[2];
         double accA[2][3][2], accB[2][3][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            if (!kTipA) fa[m] = load_a(stage + m * kBlockDoubles, c, lane);
-            fb[m] = load_a(stage + (kTipA ? 0 : kTileDoubles) + m * kBlockDoubles, c, lane);
+            if (kInnerA) fa[m] = load_a(stage + m * kBlockDoubles, c, lane);
+            else if (kChA) fa[m] = cherry_a(s_tip, s_tip + kCodes * kTipPad, aux[192 + m * 8 + g], aux[208 + m * 8 + g], c, t);
+            fb[m] = load_a(stage + (kInnerA ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
             const int code = kTipA ? aux[192 + m * 8 + g] : 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
@@ -443,27 +468,34 @@ __global__ void k_publish(const double* result, Publish pub) {
     publish_result(pub, r, result[3]);
 }
 
-template <bool kTipA, bool kStore>
+template <int KA, bool kStore>
 void launch_one(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    launch_pdl(k_branch_mma<kTipA, kStore>, grid, kThreadsBranch, BranchPlan<kTipA>::kBytes, stream, args, ntiles);
+    launch_pdl(k_branch_mma<KA, kStore>, grid, kThreadsBranch, BranchPlan<KA>::kBytes, stream, args, ntiles);
+}
+
+template <int KA>
+void configure_one() {
+    cudaFuncSetAttribute(k_branch_mma<KA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<KA>::kBytes);
+    cudaFuncSetAttribute(k_branch_mma<KA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<KA>::kBytes);
 }
 
 }  // namespace
 
 void configure_branch_kernels() {
-    cudaFuncSetAttribute(k_branch_mma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<true>::kBytes);
-    cudaFuncSetAttribute(k_branch_mma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<true>::kBytes);
-    cudaFuncSetAttribute(k_branch_mma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<false>::kBytes);
-    cudaFuncSetAttribute(k_branch_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BranchPlan<false>::kBytes);
+    configure_one<kSideInner>();
+    configure_one<kSideTip>();
+    configure_one<kSideCherry>();
 }
 
 // args.result[0..2] = lnL, dlnL/dt, d2lnL/dt2 of this rank's patterns.  np must be a multiple of 16.
 void launch_branch_mma(const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
-    const bool tip = args.a.clv == nullptr, store = args.sumtable != nullptr;
-    if (tip) store ? launch_one<true, true>(args, np, sms, stream) : launch_one<true, false>(args, np, sms, stream);
-    else store ? launch_one<false, true>(args, np, sms, stream) : launch_one<false, false>(args, np, sms, stream);
+    const int ka = side_kind(args.a);
+    const bool store = args.sumtable != nullptr;
+    if (ka == kSideTip) store ? launch_one<kSideTip, true>(args, np, sms, stream) : launch_one<kSideTip, false>(args, np, sms, stream);
+    else if (ka == kSideCherry) store ? launch_one<kSideCherry, true>(args, np, sms, stream) : launch_one<kSideCherry, false>(args, np, sms, stream);
+    else store ? launch_one<kSideInner, true>(args, np, sms, stream) : launch_one<kSideInner, false>(args, np, sms, stream);
 }
 
 void launch_publish(const double* result, const Publish& pub, cudaStream_t stream) { k_publish<<<1, 1, 0, stream>>>(result, pub); }

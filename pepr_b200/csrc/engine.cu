@@ -108,6 +108,7 @@ struct pml_ctx {
     double** d_mail_ptrs = nullptr;
     std::vector<void*> peer_opened;
     bool peer_ok = false;
+    bool fold = true;      // PEPRML_NO_FOLD=1: cherries are stored like every other inner node (reference mode for tests)
     bool fuse = true;      // PEPRML_NO_FUSE=1: CLV update and branch pass always as two launches (reference mode for tests)
     bool host_nr = false;  // PEPRML_HOST_NR=1: Newton-Raphson steps on the host, one wait per branch (reference mode for tests)
     volatile double* slot_host(double seq) const { return h_mapped + ((int64_t)seq % kRing) * kSlotDoubles; }
@@ -292,6 +293,24 @@ struct pml_tree {
         }
         return s;
     }
+    // the view of v looking at its neighbour `toward`: a folded cherry is described by its two tips (never stored)
+    Side side_toward(int v, int toward) const {
+        if (!views.fold_cherries || !ViewState::is_cherry_view(topo, v, toward)) return side(v);
+        Side s{};
+        for (int k = 0; k < 3; ++k) {
+            const int nb = topo.nbr[v][k];
+            if (nb == toward) continue;
+            const uint8_t* codes = aln->d_codes + (size_t)nb * aln->npad;
+            if (!s.codes) {
+                s.codes = codes;
+                s.len1 = d_len + topo.edge[v][k];
+            } else {
+                s.codes2 = codes;
+                s.len2 = d_len + topo.edge[v][k];
+            }
+        }
+        return s;
+    }
 };
 
 namespace {
@@ -370,8 +389,8 @@ bool sync_lengths(pml_tree* t) {
 
 NewviewOp make_newview_op(pml_tree* t, const ViewOp& op) {
     NewviewOp nv{};
-    nv.left = t->side(op.child[0]);
-    nv.right = t->side(op.child[1]);
+    nv.left = t->side_toward(op.child[0], op.node);
+    nv.right = t->side_toward(op.child[1], op.node);
     nv.len_left = t->d_len + op.cedge[0];
     nv.len_right = t->d_len + op.cedge[1];
     nv.len_scale = 1.0;
@@ -379,6 +398,34 @@ NewviewOp make_newview_op(pml_tree* t, const ViewOp& op) {
     nv.out = t->clv(op.node);
     nv.out_scale = t->scale(op.node);
     return nv;
+}
+
+// Kernel kinds of pml_profile_begin/end (PML_NKINDS in peprml.h; names, algorithmic bytes and DMMA counts: pml_kind_info).
+// A side is an inner node (I), a tip (T) or a folded cherry (C).
+//   0..5   CLV update by its children, ordered: TT, TI, II, TC, CC, CI
+//   6..8   branch pass (one end inner), by the other end: I, T, C        9..11  the same as root evaluate (per-pattern lnL kept)
+//   12     Newton-Raphson iteration on a stored product table
+//   13..27 fused update + branch pass: 13 + 3 * (update's children: TI, II, TC, CC, CI) + (far end: I, T, C)
+int side_rank(const Side& s) {
+    const int k = side_kind(s);
+    return k == kSideTip ? 0 : (k == kSideCherry ? 1 : 2);
+}
+int newview_kind(const Side& l, const Side& r) {
+    static const int table[3][3] = {{0, 3, 1}, {3, 4, 5}, {1, 5, 2}};  // [rank][rank]: T, C, I
+    return table[side_rank(l)][side_rank(r)];
+}
+int far_index(const Side& s) { return side_kind(s) == kSideInner ? 0 : (side_kind(s) == kSideTip ? 1 : 2); }
+
+// one CLV kernel; counts the site-updates by the number of children that are not inner nodes (tips or folded cherries)
+void launch_newview(pml_tree* t, const NewviewOp& nv, bool count = true) {
+    pml_aln* a = t->aln;
+    pml_ctx* c = a->ctx;
+    const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+    const int tk = c->tick(newview_kind(nv.left, nv.right), a->nloc);
+    launch_newview_mma(nv, a->npad, c->sms, c->stream);
+    c->tock(tk);
+    ++t->launches;
+    if (count) t->site_updates[2 - ntip] += a->nloc;
 }
 
 // executes a traversal descriptor: one CLV kernel per entry; each builds its own P matrices from the device lengths
@@ -390,13 +437,30 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
         NewviewOp nv = make_newview_op(t, op);
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
         nv.trace = (c->trace_newview_tips < 0 || c->trace_newview_tips == ntip) ? c->d_trace : nullptr;
-        const int tk = c->tick(2 - ntip, a->nloc);
-        launch_newview_mma(nv, a->npad, c->sms, c->stream);
-        c->tock(tk);
-        ++t->launches;
-        t->site_updates[2 - ntip] += a->nloc;
+        launch_newview(t, nv);
     }
     return ops.empty() || c->cuda(cudaGetLastError(), "CLV kernels");
+}
+
+// Stores the folded view of cherry v (looking at `toward`) in v's own CLV slot after all -- the tip-tip kernel -- for the few
+// consumers that cannot form it themselves; returns the inner-node side.
+Side materialize_cherry(pml_tree* t, int v, int toward) {
+    const Topology& T = t->topo;
+    NewviewOp nv{};
+    int k = 0;
+    for (int q = 0; q < 3; ++q) {
+        if (T.nbr[v][q] == toward) continue;
+        (k == 0 ? nv.left : nv.right) = t->side(T.nbr[v][q]);
+        (k == 0 ? nv.len_left : nv.len_right) = t->d_len + T.edge[v][q];
+        ++k;
+    }
+    nv.len_scale = 1.0;
+    nv.dm = t->aln->d_model;
+    nv.out = t->clv(v);
+    nv.out_scale = t->scale(v);
+    launch_newview(t, nv, false);  // planning has already counted this update as a folded one
+    t->views.orient[v - T.ntax] = T.slot_of(v, toward);
+    return t->side(v);
 }
 
 // brings both ends of branch e up to date; (a, b) is returned with b inner and a the tip end if there is one
@@ -409,6 +473,7 @@ bool orient_branch(pml_tree* t, int e, int& a, int& b) {
     t->views.plan(t->topo, b, a, ops);
     return run_ops(t, ops);
 }
+
 
 bool fetch_result(pml_ctx* c, const double* d_result, int n, double* out) {
     if (!c->cuda(cudaMemcpyAsync(c->h_result, d_result, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream), "result download"))
@@ -434,34 +499,59 @@ bool ensure_sumtable(pml_aln* a) {
 enum : int { kWantLnl = 1, kWantDerivs = 2, kWantAll = 3 };
 double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, const int32_t* dw, double len, bool fused,
                            bool keep_table, bool site_lnl, int want, bool device_nr, const NewviewOp* nv = nullptr);
+// which consumers form a folded cherry themselves (the others get it stored by materialize_cherry)
+constexpr bool kBranchTakesCherry = true;   // branch kernel, far end
+constexpr bool kFusedTakesCherry = true;    // fused kernel: children of the update and far end
+
 double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool keep_table, bool site_lnl, int want, bool device_nr) {
     if (keep_table && !ensure_sumtable(t->aln)) return 0.0;
     pml_ctx* c = t->aln->ctx;
-    int x = t->topo.ea[e], y = t->topo.eb[e];
-    if (t->topo.is_tip(y)) std::swap(x, y);
+    const Topology& T = t->topo;
+    int x = T.ea[e], y = T.eb[e];
+    if (T.is_tip(y)) std::swap(x, y);
     std::vector<ViewOp> ops;
-    t->views.plan(t->topo, x, y, ops);
-    t->views.plan(t->topo, y, x, ops);
+    t->views.plan(T, x, y, ops);
+    t->views.plan(T, y, x, ops);
     // The last CLV update of the visit produces one end of this very branch: update and pass go out as ONE launch
     // (fused_mma.cu) unless the product table is wanted or both children of that node are tips.
     const bool fuse = c->fuse && !keep_table && !ops.empty() &&
-                      !(t->topo.is_tip(ops.back().child[0]) && t->topo.is_tip(ops.back().child[1]));
+                      !(T.is_tip(ops.back().child[0]) && T.is_tip(ops.back().child[1]));
     if (!fuse) {
         if (!run_ops(t, ops) || !sync_lengths(t)) return 0.0;
-        return branch_launch_sides(t, t->side(x), t->side(y), e, dw, len, false, keep_table, site_lnl, want, device_nr);
+        // the pass wants an inner node at one end (b); the other end (a) may be an inner node, a tip or a folded cherry
+        Side sa = t->side_toward(x, y), sb = t->side_toward(y, x);
+        if (side_kind(sb) != kSideInner && side_kind(sa) == kSideInner) {
+            std::swap(sa, sb);
+            std::swap(x, y);
+        }
+        if (side_kind(sb) != kSideInner) {  // neither end is stored: a cherry against a tip or a cherry (3 / 4 taxa)
+            if (side_kind(sb) != kSideCherry) {
+                std::swap(sa, sb);
+                std::swap(x, y);
+            }
+            sb = materialize_cherry(t, y, x);
+        }
+        if (side_kind(sa) == kSideCherry && !kBranchTakesCherry) sa = materialize_cherry(t, x, y);
+        return branch_launch_sides(t, sa, sb, e, dw, len, false, keep_table, site_lnl, want, device_nr);
     }
     const ViewOp last = ops.back();
     ops.pop_back();
     if (!run_ops(t, ops) || !sync_lengths(t)) return 0.0;
     const int far = last.node == x ? y : x;
+    Side sfar = t->side_toward(far, last.node);
+    if (side_kind(sfar) == kSideCherry && !kFusedTakesCherry) sfar = materialize_cherry(t, far, last.node);
     NewviewOp nv = make_newview_op(t, last);
+    if (!kFusedTakesCherry) {
+        if (side_kind(nv.left) == kSideCherry) nv.left = materialize_cherry(t, last.child[0], last.node);
+        if (side_kind(nv.right) == kSideCherry) nv.right = materialize_cherry(t, last.child[1], last.node);
+    }
     const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-    if (c->trace_fused && ntip == 0 && !t->topo.is_tip(far)) nv.trace = c->d_trace_buf;  // inner-inner update, inner far end
+    if (c->trace_fused && ntip == 0 && side_kind(sfar) == kSideInner) nv.trace = c->d_trace_buf;  // inner-inner update, inner far end
     t->site_updates[2 - ntip] += t->aln->nloc;
     Side sx{};
     sx.clv = nv.out;
     sx.scale = nv.out_scale;
-    return branch_launch_sides(t, t->side(far), sx, e, dw, len, true, false, site_lnl, want, device_nr, &nv);
+    return branch_launch_sides(t, sfar, sx, e, dw, len, true, false, site_lnl, want, device_nr, &nv);
 }
 
 // the pass itself between two given sides (sb inner; sa inner or tip); e names the branch for device NR and book-keeping;
@@ -496,9 +586,9 @@ double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, c
     const bool in_kernel = c->nranks == 1 || c->peer_ok;
     if (in_kernel) args.pub = pub;
     if (c->peer_ok) args.peer = PeerReduce{c->d_mail_ptrs, c->rank, c->nranks, c->d_peer_lost, c->peer_timeout_ns};
-    // kinds 7..10: fused update + pass, by (tip child of the update, tip far end); see PML_NKINDS in peprml.h
-    const int fused_kind = fused ? 7 + 2 * ((nv->left.clv == nullptr) || (nv->right.clv == nullptr) ? 1 : 0) + (args.a.clv ? 0 : 1) : 0;
-    const int tk = c->tick(fused ? fused_kind : (site_lnl ? 3 : (args.a.clv ? 4 : 6)), a->nloc);
+    // kinds: see launch_newview
+    const int fused_kind = fused ? 13 + 3 * (newview_kind(nv->left, nv->right) - 1) + far_index(args.a) : 0;
+    const int tk = c->tick(fused ? fused_kind : (site_lnl ? 9 : 6) + far_index(args.a), a->nloc);
     if (fused) launch_fused(*nv, args, a->npad, c->sms, c->stream);
     else launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
@@ -540,7 +630,7 @@ int evaluate_branch(pml_tree* t, int e, const int32_t* weights, double* lnl) {
 bool core_at(pml_tree* t, const int32_t* dw, double len, double out[3]) {
     pml_aln* a = t->aln;
     pml_ctx* c = a->ctx;
-    const int tk = c->tick(5, a->nloc);
+    const int tk = c->tick(12, a->nloc);
     launch_core(a->d_model, a->d_sumtable, a->d_sumscale, dw, a->npad, len, a->d_partials, a->d_result, c->stream);
     c->tock(tk);
     t->launches += 2;
@@ -851,6 +941,8 @@ bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets
     Side side_p{};
     side_p.clv = t->clv(p);
     side_p.scale = t->scale(p);
+    Side side_s = t->side_toward(s, p);  // the subtree's own view: an inner node, a tip or a folded cherry
+    if (side_kind(side_s) == kSideCherry && !(kBranchTakesCherry && kFusedTakesCherry)) side_s = materialize_cherry(t, s, p);
     constexpr size_t kLag = pml_ctx::kRing - 2;
     std::vector<std::pair<double, size_t>> queued;  // (sequence number, candidate index)
     size_t head = 0;
@@ -872,24 +964,26 @@ bool score_candidates(pml_tree* t, int p, int s, const std::vector<int>& targets
             break;
         }
         NewviewOp nv{};
-        nv.left = t->side(x);
-        nv.right = t->side(y);
+        nv.left = t->side_toward(x, y);
+        nv.right = t->side_toward(y, x);
         nv.len_left = nv.len_right = t->d_len + e;
         nv.len_scale = 0.5;
         nv.dm = a->d_model;
         nv.out = t->clv(p);
         nv.out_scale = t->scale(p);
-        const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-        t->site_updates[2 - ntip] += a->nloc;
+        const bool both_tips = side_kind(nv.left) == kSideTip && side_kind(nv.right) == kSideTip;
         double seq;
-        if (c->fuse && ntip < 2) {  // the insertion update and the pass over the subtree's branch as one launch
-            seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, true, false, false, kWantLnl, false, &nv);
+        if (c->fuse && !both_tips) {  // the insertion update and the pass over the subtree's branch as one launch
+            if (!kFusedTakesCherry) {
+                if (side_kind(nv.left) == kSideCherry) nv.left = materialize_cherry(t, x, y);
+                if (side_kind(nv.right) == kSideCherry) nv.right = materialize_cherry(t, y, x);
+            }
+            const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
+            t->site_updates[2 - ntip] += a->nloc;
+            seq = branch_launch_sides(t, side_s, side_p, mv.e_s, dw, len_s, true, false, false, kWantLnl, false, &nv);
         } else {
-            const int tk = c->tick(2 - ntip, a->nloc);
-            launch_newview_mma(nv, a->npad, c->sms, c->stream);
-            c->tock(tk);
-            ++t->launches;
-            seq = branch_launch_sides(t, t->side(s), side_p, mv.e_s, dw, len_s, false, false, false, kWantLnl, false);
+            launch_newview(t, nv);
+            seq = branch_launch_sides(t, side_s, side_p, mv.e_s, dw, len_s, false, false, false, kWantLnl, false);
         }
         if (seq == 0.0) {
             ok = false;
@@ -1047,6 +1141,7 @@ static int create_base(int gpu_id, int rank, int nranks, std::unique_ptr<pml_ctx
     c->device = gpu_id;
     c->host_nr = getenv("PEPRML_HOST_NR") != nullptr;
     c->fuse = getenv("PEPRML_NO_FUSE") == nullptr;
+    c->fold = getenv("PEPRML_NO_FOLD") == nullptr;
     c->rank = rank;
     c->nranks = nranks;
     if (const char* ms = getenv("PEPRML_PEER_TIMEOUT_MS")) c->peer_timeout_ns = (unsigned long long)std::max(1.0, atof(ms)) * 1000000ull;
@@ -1224,6 +1319,40 @@ int pml_timer_stop(pml_ctx* c, double* ms) {
         !c->cuda(cudaEventElapsedTime(&f, c->timer0, c->timer1), "timer read"))
         return PML_ENODEVICE;
     *ms = f;
+    return PML_OK;
+}
+
+int pml_kind_info(int kind, char* name, size_t cap, int* bytes_per_pattern, int* dmma_per_tile) {
+    if (kind < 0 || kind >= PML_NKINDS) return PML_EINVAL;
+    // per side: bytes read and DMMAs of its 20 x 20 product (a tip's is a table look-up)
+    static const char* far_name[3] = {"inner", "tip", "cherry"};
+    static const int side_bytes[3] = {640, 1, 2}, side_dmma[3] = {30, 0, 30};
+    static const char* nv_name[6] = {"tip_tip", "tip_inner", "inner_inner", "tip_cherry", "cherry_cherry", "cherry_inner"};
+    static const int nv_sides[6][2] = {{1, 1}, {1, 0}, {0, 0}, {1, 2}, {2, 2}, {2, 0}};
+    std::string n;
+    int bytes = 0, dmma = 0;
+    if (kind < 6) {
+        n = std::string("newview_") + nv_name[kind];
+        bytes = side_bytes[nv_sides[kind][0]] + side_bytes[nv_sides[kind][1]] + 640;
+        dmma = side_dmma[nv_sides[kind][0]] + side_dmma[nv_sides[kind][1]];
+    } else if (kind < 12) {
+        const int far = (kind - 6) % 3;
+        const bool eval = kind >= 9;
+        n = std::string(eval ? "evaluate_" : "branch_") + far_name[far];
+        bytes = 640 + side_bytes[far] + 12 + (eval ? 8 : 0);   // + scaling counts and weight (+ per-pattern lnL written)
+        dmma = 30 + side_dmma[far] + 12;
+    } else if (kind == 12) {
+        n = "core";
+        bytes = 648;
+    } else {
+        const int nv = 1 + (kind - 13) / 3, far = (kind - 13) % 3;
+        n = std::string("fused_") + nv_name[nv] + "_" + far_name[far];
+        bytes = side_bytes[nv_sides[nv][0]] + side_bytes[nv_sides[nv][1]] + 640 + side_bytes[far];
+        dmma = side_dmma[nv_sides[nv][0]] + side_dmma[nv_sides[nv][1]] + 30 + side_dmma[far] + 12;
+    }
+    if (name && cap > n.size()) std::memcpy(name, n.c_str(), n.size() + 1);
+    if (bytes_per_pattern) *bytes_per_pattern = bytes;
+    if (dmma_per_tile) *dmma_per_tile = dmma;
     return PML_OK;
 }
 
@@ -1452,6 +1581,7 @@ int pml_tree_load(pml_aln* a, const char* newick, pml_tree** out) {
     t->aln = a;
     std::string err;
     if (!parse_newick(newick, a->pat.names, kDefaultLen, t->topo, err)) return fail(c, PML_EINVAL, err);
+    t->views.fold_cherries = c->fold;
     t->views.reset(t->topo);
     const size_t inner = (size_t)a->pat.ntax - 2;
     bool ok = c->cuda(c->dev_alloc(&t->d_clv, sizeof(double) * inner * a->npad * kRow), "CLV arena alloc") &&
@@ -1511,7 +1641,10 @@ int64_t pml_tree_nr_retries(const pml_tree* t) { return t ? t->nr_retries : PML_
 
 int pml_tree_stats(const pml_tree* t, int64_t site_updates[3], int64_t* launches) {
     if (!t) return PML_EINVAL;
-    if (site_updates) std::memcpy(site_updates, t->site_updates, sizeof t->site_updates);
+    if (site_updates) {
+        std::memcpy(site_updates, t->site_updates, sizeof t->site_updates);
+        site_updates[0] += t->views.folded * t->aln->nloc;  // tip-tip updates formed inside their consumers (folded cherries)
+    }
     if (launches) *launches = t->launches;
     return PML_OK;
 }

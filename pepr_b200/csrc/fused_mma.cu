@@ -52,19 +52,39 @@ __device__ __forceinline__ void lookup_rows(const double* table, int code, int c
     }
 }
 
-// kNv: 0 = both children inner, 1 = left child is a tip, 2 = right child is a tip;  kTipY: the far end of the branch is a tip
-template <int kNv, bool kTipY>
+// KL, KR: the children of the update (tip / cherry / inner, ordered tip < cherry < inner, at least one not a tip);
+// KY: the far end of the branch.  A folded cherry (Side in kernels.h) is formed in registers from two tip look-ups.
+constexpr int kTableDoubles = kCodes * kTipPad;
+template <int KL, int KR, int KY>
 struct FusedPlan {
-    static constexpr bool kTipL = kNv == 1, kTipR = kNv == 2, kMixed = kNv != 0;
-    static constexpr int kInner = kMixed ? 1 : 2;
-    // NV stage: CLV tiles of the inner children + [0,64) / [64,128) their scaling counts, [128,144) codes of the tip child
-    static constexpr int kNvStageDoubles = kInner * kTileDoubles + 24;
-    // Y stage: CLV tile of the far end (unless a tip) + [0,64) its scaling counts, [64,128) pattern weights, [128,144) its codes
-    static constexpr int kYStageDoubles = (kTipY ? 0 : kTileDoubles) + 32;
+    static constexpr int kInner = (KL == kSideInner ? 1 : 0) + (KR == kSideInner ? 1 : 0);
+    static constexpr int kTablesL = KL == kSideTip ? 1 : (KL == kSideCherry ? 2 : 0);
+    static constexpr int kTablesR = KR == kSideTip ? 1 : (KR == kSideCherry ? 2 : 0);
+    static constexpr int kTablesY = KY == kSideCherry ? 2 : 0;
+    // branches whose P matrices the prologue builds: the two of the update, then the tips of the cherries (left, right, far end)
+    static constexpr int kBranches = 2 + (KL == kSideCherry ? 2 : 0) + (KR == kSideCherry ? 2 : 0) + (KY == kSideCherry ? 2 : 0);
+    __host__ __device__ static constexpr int branch_id(int pos) {  // 0, 1: the update's; 2, 3 / 4, 5 / 6, 7: tips of the left / right / far cherry
+        if (pos < 2) return pos;
+        int p = pos - 2;
+        if (KL == kSideCherry) {
+            if (p < 2) return 2 + p;
+            p -= 2;
+        }
+        if (KR == kSideCherry) {
+            if (p < 2) return 4 + p;
+            p -= 2;
+        }
+        return 6 + p;
+    }
+    // NV stage: CLV tiles of the inner children + [0,64) / [64,128) their scaling counts, [128,160) / [160,192) residue codes of
+    // the left / right child (tip: 16 B, cherry: 2 x 16 B)
+    static constexpr int kNvStageDoubles = kInner * kTileDoubles + 32;
+    // Y stage: CLV tile of the far end (inner node only) + [0,64) its scaling counts, [64,128) pattern weights, [128,160) its codes
+    static constexpr int kYStageDoubles = (KY == kSideInner ? kTileDoubles : 0) + 32;
     static constexpr int kModelDoubles = 3 * pmat::kMat;          // V, Vinv, pi V
     static constexpr int kExpDoubles = 3 * kCats * 24;
-    static constexpr int kTipDoubles = kMixed ? kCodes * kTipPad : 0;
-    static constexpr int kTipYDoubles = kTipY ? kCodes * kTipVecPad : 0;
+    static constexpr int kTipDoubles = (kTablesL + kTablesR + kTablesY) * kTableDoubles;
+    static constexpr int kTipYDoubles = KY == kSideTip ? kCodes * kTipVecPad : 0;
     static constexpr int kRedDoubles = kSlots * kCats * kTileRows * 3;
     static constexpr int kInts = kSlots * kCats * kTileRows /* max */ + kSlots * kTileRows /* sc */ + kSlots * kTileRows * 2 /* side */;
     static constexpr size_t kBarBytes = 512;
@@ -72,14 +92,16 @@ struct FusedPlan {
                                      sizeof(double) * (size_t)(kModelDoubles + kExpDoubles + kTipDoubles + kTipYDoubles + kRedDoubles + 8) +
                                      sizeof(int) * kInts +
                                      sizeof(double) * (size_t)(kSlots * kTileDoubles + kFDepth * (kNvStageDoubles + kYStageDoubles));
-    static_assert(kSlots * kTileDoubles >= 8 * pmat::kFragSlotDoubles && kSlots * kTileDoubles >= 4 * pmat::kFragSlotDoubles + kCats * pmat::kMat,
-                  "the product slots double as the staging area of the P matrices");
+    static_assert(kSlots * kTileDoubles >= 8 * pmat::kFragSlotDoubles, "the product slots double as the fragment exchange area");
+    static_assert(kBytes <= 227 * 1024, "shared memory budget of one CTA");
 };
 
-template <int kNv, bool kTipY>
+template <int KL, int KR, int KY>
 __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, BranchArgs args, int ntiles) {
-    using Plan = FusedPlan<kNv, kTipY>;
-    constexpr bool kTipL = Plan::kTipL, kTipR = Plan::kTipR, kMixed = Plan::kMixed;
+    using Plan = FusedPlan<KL, KR, KY>;
+    constexpr bool kInnerL = KL == kSideInner, kInnerR = KR == kSideInner, kInnerY = KY == kSideInner;
+    constexpr bool kTipL = KL == kSideTip, kTipR = KR == kSideTip, kTipY = KY == kSideTip;
+    constexpr bool kChL = KL == kSideCherry, kChR = KR == kSideCherry, kChY = KY == kSideCherry;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* nv_full = reinterpret_cast<uint64_t*>(smem_raw);  // [kFDepth]
     uint64_t* nv_empty = nv_full + kFDepth;                      // [kFDepth], 4 arrivals (NV warps)
@@ -94,8 +116,10 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     double* s_vinv = s_model + pmat::kMat;
     double* s_piv = s_model + 2 * pmat::kMat;
     double* s_exp = s_model + Plan::kModelDoubles;               // [3][kCats][24]
-    double* s_tip = s_exp + Plan::kExpDoubles;                   // mixed newview: 23 x 80 lookup of the tip child
-    double* s_tipy = s_tip + Plan::kTipDoubles;                  // tip far end: 23 x 20 lookup (pi V sums)
+    double* s_tabL = s_exp + Plan::kExpDoubles;                  // 23 x 80 look-ups of the left child (tip: 1, cherry: 2)
+    double* s_tabR = s_tabL + Plan::kTablesL * kTableDoubles;    // ... of the right child
+    double* s_tabY = s_tabR + Plan::kTablesR * kTableDoubles;    // ... of a cherry at the far end
+    double* s_tipy = s_tabY + Plan::kTablesY * kTableDoubles;    // tip far end: 23 x 20 lookup (pi V sums)
     double* s_red = s_tipy + Plan::kTipYDoubles;                 // [kSlots][kCats][16][3]
     double* s_fin = s_red + Plan::kRedDoubles;                   // [2][3] (+2)
     int* s_max = reinterpret_cast<int*>(s_fin + 8);              // [kSlots][kCats][16]
@@ -112,7 +136,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     // ---- static model constants first (before the dependency wait and before any bulk load is queued) ----------------
     double pre[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
     double pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0;
-    const int c_p = warp & 3, child_p = warp >> 2;  // MMA warp w builds P of (category w & 3, left / right child)
+    const int c_p = warp & 3;  // MMA warp w builds category w & 3 of the branches at positions (w >> 2), (w >> 2) + 2, ... (Plan::branch_id)
     if (warp != kProducerWarp) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -147,8 +171,17 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     // lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
-    double my_len = 0.0;
-    if (warp < kMmaWarps) my_len = (child_p == 0 ? *op.len_left : *op.len_right) * op.len_scale;
+    constexpr int kRounds = Plan::kBranches / 2;
+    double my_len[kRounds];
+    if (warp < kMmaWarps) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int id = Plan::branch_id(2 * r + (warp >> 2));
+            const double* src = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
+                                : id == 4 ? op.right.len1 : id == 5 ? op.right.len2 : id == 6 ? args.a.len1 : args.a.len2;
+            my_len[r] = *src * (id < 2 ? op.len_scale : 1.0);
+        }
+    }
     const double t_raw = args.t_ptr ? *args.t_ptr : args.t;
     if (warp != kProducerWarp) {
 #pragma unroll
@@ -175,10 +208,11 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             const uint32_t par = ((n / kFDepth) & 1) ^ 1;
             if (lane == 0) {
                 mbar_wait(nv_empty + slot, par);
-                mbar_expect_tx(nv_full + slot, Plan::kInner * (bytes + int_bytes) + (kMixed ? kTileRows : 0));
+                mbar_expect_tx(nv_full + slot, Plan::kInner * (bytes + int_bytes) + (kTipL ? kTileRows : 0) + (kChL ? 2 * kTileRows : 0) +
+                                                   (kTipR ? kTileRows : 0) + (kChR ? 2 * kTileRows : 0));
             } else if (lane == 4) {
                 mbar_wait(y_empty + slot, par);
-                mbar_expect_tx(y_full + slot, (kTipY ? kTileRows : bytes + int_bytes) + int_bytes);
+                mbar_expect_tx(y_full + slot, (kInnerY ? bytes + int_bytes : (kTipY ? kTileRows : 2 * kTileRows)) + int_bytes);
             }
             __syncwarp();
             const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
@@ -186,24 +220,27 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             double* dst = s_nvstage + (size_t)slot * Plan::kNvStageDoubles;
             unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
             double* ydst = s_ystage + (size_t)slot * Plan::kYStageDoubles;
-            unsigned char* yaux = reinterpret_cast<unsigned char*>(ydst + (kTipY ? 0 : kTileDoubles));
+            unsigned char* yaux = reinterpret_cast<unsigned char*>(ydst + (kInnerY ? kTileDoubles : 0));
             if (lane == 0) {
-                if (!kTipL) bulk_g2s(dst, op.left.clv + goff, bytes, nv_full + slot);
-                else bulk_g2s(dst, op.right.clv + goff, bytes, nv_full + slot);
+                if (kInnerL) bulk_g2s(dst, op.left.clv + goff, bytes, nv_full + slot);
+                else bulk_g2s(aux + 128, op.left.codes + tile * kTileRows, kTileRows, nv_full + slot);
             } else if (lane == 1) {
-                if (!kMixed) bulk_g2s(dst + kTileDoubles, op.right.clv + goff, bytes, nv_full + slot);
-                else bulk_g2s(aux + 128, (kTipL ? op.left.codes : op.right.codes) + tile * kTileRows, kTileRows, nv_full + slot);
+                if (kInnerR) bulk_g2s(dst + (kInnerL ? kTileDoubles : 0), op.right.clv + goff, bytes, nv_full + slot);
+                else bulk_g2s(aux + 160, op.right.codes + tile * kTileRows, kTileRows, nv_full + slot);
             } else if (lane == 2) {
-                bulk_g2s(aux, (kTipL ? op.right.scale : op.left.scale) + tile * kTileRows, int_bytes, nv_full + slot);
+                if (kInnerL) bulk_g2s(aux, op.left.scale + tile * kTileRows, int_bytes, nv_full + slot);
+                else if (kChL) bulk_g2s(aux + 144, op.left.codes2 + tile * kTileRows, kTileRows, nv_full + slot);
             } else if (lane == 3) {
-                if (!kMixed) bulk_g2s(aux + int_bytes, op.right.scale + tile * kTileRows, int_bytes, nv_full + slot);
+                if (kInnerR) bulk_g2s(aux + int_bytes, op.right.scale + tile * kTileRows, int_bytes, nv_full + slot);
+                else if (kChR) bulk_g2s(aux + 176, op.right.codes2 + tile * kTileRows, kTileRows, nv_full + slot);
             } else if (lane == 4) {
-                if (!kTipY) bulk_g2s(ydst, args.a.clv + goff, bytes, y_full + slot);
+                if (kInnerY) bulk_g2s(ydst, args.a.clv + goff, bytes, y_full + slot);
                 else bulk_g2s(yaux + 128, args.a.codes + tile * kTileRows, kTileRows, y_full + slot);
             } else if (lane == 5) {
                 bulk_g2s(yaux + 64, args.weights + tile * kTileRows, int_bytes, y_full + slot);
             } else if (lane == 6) {
-                if (!kTipY) bulk_g2s(yaux, args.a.scale + tile * kTileRows, int_bytes, y_full + slot);
+                if (kInnerY) bulk_g2s(yaux, args.a.scale + tile * kTileRows, int_bytes, y_full + slot);
+                else if (kChY) bulk_g2s(yaux + 144, args.a.codes2 + tile * kTileRows, kTileRows, y_full + slot);
             }
         }
         return;
@@ -218,23 +255,31 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         s_exp[2 * kCats * 24 + stid] = a * a * e;
     }
     double fragL[3][5], fragR[3][5];  // NV group: P fragments of the two children;  BR group: pi V (y end) and Vinv (x end)
-    double* s_x = s_prod;                                  // fragment exchange: [slot][15][32]
-    double* s_Ptip = s_prod + 4 * pmat::kFragSlotDoubles;  // mixed newview: P[c][i][j] of the tip child
+    double* s_x = s_prod;             // fragment exchange: [branch 0 / 1][category][15][32]
     if (warp < kMmaWarps) {
-        double acc[3][3][2];
-        pmat::build_p_tiles(s_model, exp(lr * my_len), lane, acc);
-        const bool tip_child = child_p == 0 ? kTipL : kTipR;
-        if (tip_child) pmat::tiles_to_smem(acc, lane, s_Ptip + c_p * pmat::kMat);
-        else {
-            double frag[3][5];
-            pmat::tiles_to_fragments(acc, lane, frag);
-            pmat::fragments_to_smem(frag, lane, s_x + (kMixed ? c_p : warp) * pmat::kFragSlotDoubles);
+        // an inner or cherry child's matrix leaves the accumulators as B fragments for the NV warp of its category; every tip's
+        // matrix -- a tip child's or a cherry's -- goes straight into its look-up table
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int id = Plan::branch_id(2 * r + (warp >> 2));
+            double acc[3][3][2];
+            pmat::build_p_tiles(s_model, exp(lr * my_len[r]), lane, acc);
+            double* table = nullptr;
+            if (id == 0 && kTipL) table = s_tabL;
+            else if (id == 1 && kTipR) table = s_tabR;
+            else if (id == 2 || id == 3) table = s_tabL + (id - 2) * kTableDoubles;
+            else if (id == 4 || id == 5) table = s_tabR + (id - 4) * kTableDoubles;
+            else if (id >= 6) table = s_tabY + (id - 6) * kTableDoubles;
+            if (table) pmat::tiles_to_lookup(acc, lane, c_p, table, kTipPad);
+            else {
+                double frag[3][5];
+                pmat::tiles_to_fragments(acc, lane, frag);
+                pmat::fragments_to_smem(frag, lane, s_x + (id * kCats + c_p) * pmat::kFragSlotDoubles);
+            }
         }
     }
-    named_barrier(kStageBarrier, kStagers);
-    if (kMixed) pmat::build_tip_lookup<kStagers>(s_Ptip, stid, s_tip, kTipPad);
     if (kTipY) {
-        // tipvec[code][k] = sum over the residues the code allows of pi_i V[i][k]
+        // tipvec[code][k] = sum over the residues the code allows of pi_i V[i][k]  (s_piv is in place since the __syncthreads above)
         for (int idx = stid; idx < kCodes * kStates; idx += kStagers) {
             const int code = idx / kStates, k = idx % kStates;
             double acc = 0.0;
@@ -246,10 +291,11 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             s_tipy[code * kTipVecPad + k] = acc;
         }
     }
+    named_barrier(kStageBarrier, kStagers);
     double efrag[3][2];
-    if (warp < 4) {  // NV group: both children's fragments come from the exchange area
+    if (warp < 4) {  // NV group: the fragments of both children come from the exchange area
         if (!kTipL) pmat::fragments_from_smem(fragL, lane, s_x + c_p * pmat::kFragSlotDoubles);
-        if (!kTipR) pmat::fragments_from_smem(fragR, lane, s_x + (kMixed ? c_p : kCats + c_p) * pmat::kFragSlotDoubles);
+        if (!kTipR) pmat::fragments_from_smem(fragR, lane, s_x + (kCats + c_p) * pmat::kFragSlotDoubles);
     } else if (warp < kMmaWarps) {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -419,24 +465,22 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             const long long k1 = tr ? clock64() : 0;
             const double* stage = s_nvstage + (size_t)slot * Plan::kNvStageDoubles;
             const unsigned char* aux = reinterpret_cast<const unsigned char*>(stage + Plan::kInner * kTileDoubles);
-            int code[2] = {0, 0};
-            if (kMixed) {
-                code[0] = aux[128 + g];
-                code[1] = aux[128 + 8 + g];
-            }
             int32_t sc_sum = 0;
-            if (c == 0 && lane < kTileRows) {
+            if (Plan::kInner > 0 && c == 0 && lane < kTileRows) {
                 const int32_t* sci = reinterpret_cast<const int32_t*>(aux);
-                sc_sum = sci[lane] + (Plan::kInner == 2 ? sci[kTileRows + lane] : 0);
+                sc_sum = (kInnerL ? sci[lane] : 0) + (kInnerR ? sci[kTileRows + lane] : 0);
             }
             double accL[2][3][2], accR[2][3][2];
             AFrag aL[2], aR[2];
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                if (kTipL) lookup_rows(s_tip, code[m], c, t, accL[m]);
+                const int row = m * 8 + g;
+                if (kTipL) lookup_rows(s_tabL, aux[128 + row], c, t, accL[m]);
+                else if (kChL) aL[m] = cherry_a(s_tabL, s_tabL + kTableDoubles, aux[128 + row], aux[144 + row], c, t);
                 else aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
-                if (kTipR) lookup_rows(s_tip, code[m], c, t, accR[m]);
-                else aR[m] = load_a(stage + (kTipL ? 0 : kTileDoubles) + m * kBlockDoubles, c, lane);
+                if (kTipR) lookup_rows(s_tabR, aux[160 + row], c, t, accR[m]);
+                else if (kChR) aR[m] = cherry_a(s_tabR, s_tabR + kTableDoubles, aux[160 + row], aux[176 + row], c, t);
+                else aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
             }
 #pragma unroll
             for (int m = 0; m < 2; ++m)
@@ -548,11 +592,11 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         const long long b2 = trb ? clock64() : 0;
         const double* prod = s_prod + (size_t)pslot * kTileDoubles;
         const double* ystage = s_ystage + (size_t)yslot * Plan::kYStageDoubles;
-        const unsigned char* yaux = reinterpret_cast<const unsigned char*>(ystage + (kTipY ? 0 : kTileDoubles));
+        const unsigned char* yaux = reinterpret_cast<const unsigned char*>(ystage + (kInnerY ? kTileDoubles : 0));
         int2 side = make_int2(0, 0);
         if (c == 0 && lane < kTileRows) {
             const int32_t* ai = reinterpret_cast<const int32_t*>(yaux);
-            side.x = s_sc[pslot * kTileRows + lane] + (kTipY ? 0 : ai[lane]);
+            side.x = s_sc[pslot * kTileRows + lane] + (kInnerY ? ai[lane] : 0);
             side.y = ai[kTileRows + lane];
         }
         AFrag fx[2], fy[2];
@@ -560,7 +604,8 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             fx[m] = load_a(prod + m * kBlockDoubles, c, lane);
-            if (!kTipY) fy[m] = load_a(ystage + m * kBlockDoubles, c, lane);
+            if (kInnerY) fy[m] = load_a(ystage + m * kBlockDoubles, c, lane);
+            else if (kChY) fy[m] = cherry_a(s_tabY, s_tabY + kTableDoubles, yaux[128 + m * 8 + g], yaux[144 + m * 8 + g], c, t);
             const int code = kTipY ? yaux[128 + m * 8 + g] : 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
@@ -629,32 +674,44 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     }
 }
 
-template <int kNv, bool kTipY>
+template <int KL, int KR, int KY>
 void launch_one(const NewviewOp& op, const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    launch_pdl(k_fused<kNv, kTipY>, grid, kThreadsFused, FusedPlan<kNv, kTipY>::kBytes, stream, op, args, ntiles);
+    launch_pdl(k_fused<KL, KR, KY>, grid, kThreadsFused, FusedPlan<KL, KR, KY>::kBytes, stream, op, args, ntiles);
+}
+template <int KL, int KR>
+void launch_far(const NewviewOp& op, const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
+    const int ky = side_kind(args.a);
+    if (ky == kSideInner) launch_one<KL, KR, kSideInner>(op, args, np, sms, stream);
+    else if (ky == kSideTip) launch_one<KL, KR, kSideTip>(op, args, np, sms, stream);
+    else launch_one<KL, KR, kSideCherry>(op, args, np, sms, stream);
+}
+template <int KL, int KR>
+void configure_pair() {
+    cudaFuncSetAttribute(k_fused<KL, KR, kSideInner>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<KL, KR, kSideInner>::kBytes);
+    cudaFuncSetAttribute(k_fused<KL, KR, kSideTip>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<KL, KR, kSideTip>::kBytes);
+    cudaFuncSetAttribute(k_fused<KL, KR, kSideCherry>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<KL, KR, kSideCherry>::kBytes);
 }
 
 }  // namespace
 
 void configure_fused_kernels() {
-    cudaFuncSetAttribute(k_fused<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<0, false>::kBytes);
-    cudaFuncSetAttribute(k_fused<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<0, true>::kBytes);
-    cudaFuncSetAttribute(k_fused<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<1, false>::kBytes);
-    cudaFuncSetAttribute(k_fused<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<1, true>::kBytes);
-    cudaFuncSetAttribute(k_fused<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<2, false>::kBytes);
-    cudaFuncSetAttribute(k_fused<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedPlan<2, true>::kBytes);
+    configure_pair<kSideTip, kSideInner>();
+    configure_pair<kSideInner, kSideInner>();
+    configure_pair<kSideTip, kSideCherry>();
+    configure_pair<kSideCherry, kSideCherry>();
+    configure_pair<kSideCherry, kSideInner>();
 }
 
-// op: the CLV update of the branch's x end (at least one inner child); args.a: the y end (inner or tip), args.b is ignored
-// (the x end is op.out).  No product table (args.sumtable must be null).  np must be a multiple of 16.
-void launch_fused(const NewviewOp& op, const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
-    const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr, ty = args.a.clv == nullptr;
-    const int nv = tl ? 1 : (tr ? 2 : 0);
-    if (nv == 0) ty ? launch_one<0, true>(op, args, np, sms, stream) : launch_one<0, false>(op, args, np, sms, stream);
-    else if (nv == 1) ty ? launch_one<1, true>(op, args, np, sms, stream) : launch_one<1, false>(op, args, np, sms, stream);
-    else ty ? launch_one<2, true>(op, args, np, sms, stream) : launch_one<2, false>(op, args, np, sms, stream);
+// op: the CLV update of the branch's x end (children not both tips); args.a: the y end (inner, tip or folded cherry), args.b is
+// ignored (the x end is op.out).  No product table (args.sumtable must be null).  np must be a multiple of 16.
+void launch_fused(const NewviewOp& in, const BranchArgs& args, int64_t np, int sms, cudaStream_t stream) {
+    const NewviewOp op = canonical_children(in);
+    const int kl = side_kind(op.left), kr = side_kind(op.right);
+    if (kl == kSideTip) kr == kSideCherry ? launch_far<kSideTip, kSideCherry>(op, args, np, sms, stream) : launch_far<kSideTip, kSideInner>(op, args, np, sms, stream);
+    else if (kl == kSideCherry) kr == kSideCherry ? launch_far<kSideCherry, kSideCherry>(op, args, np, sms, stream) : launch_far<kSideCherry, kSideInner>(op, args, np, sms, stream);
+    else launch_far<kSideInner, kSideInner>(op, args, np, sms, stream);
 }
 
 }  // namespace pml

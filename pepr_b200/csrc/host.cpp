@@ -543,6 +543,13 @@ std::string write_newick_result(const Topology& T, const std::vector<std::string
 // =========================================================================================== traversal ======
 void ViewState::plan(const Topology& T, int v, int toward_node, std::vector<ViewOp>& ops) {
     if (T.is_tip(v)) return;
+    if (fold_cherries && is_cherry_view(T, v, toward_node)) {
+        if (!fresh[v - T.ntax]) {
+            fresh[v - T.ntax] = 1;
+            ++folded;
+        }
+        return;
+    }
     const int s = T.slot_of(v, toward_node);
     if (orient[v - T.ntax] == s) return;
     ViewOp op{};
@@ -563,6 +570,8 @@ void ViewState::plan(const Topology& T, int v, int toward_node, std::vector<View
 
 void ViewState::branch_changed(const Topology& T, int e) {
     // walk away from the branch on both sides; a stored CLV at x (reached from y) contains the branch unless it faces y
+    if (T.is_tip(T.ea[e])) touch(T, T.eb[e]);  // a folded cherry contains exactly the branches of its two tips
+    if (T.is_tip(T.eb[e])) touch(T, T.ea[e]);
     std::vector<std::pair<int, int>> stack{{T.ea[e], T.eb[e]}, {T.eb[e], T.ea[e]}};
     while (!stack.empty()) {
         const auto [x, y] = stack.back();
@@ -794,6 +803,7 @@ bool spr_apply(Topology& T, ViewState& V, int p, int s, int target, SprMove& mv)
     T.eb[mv.e_r] = mv.b;
     T.len[mv.e_t] = T.len[mv.e_r] = 0.5 * mv.len_t;
     V.orient[p - T.ntax] = -1;
+    for (int v : {p, mv.q, mv.r, mv.a, mv.b}) V.touch(T, v);
     V.branch_changed(T, mv.e_q);
     V.branch_changed(T, mv.e_t);
     V.branch_changed(T, mv.e_r);
@@ -829,6 +839,7 @@ bool spr_prune(Topology& T, ViewState& V, int p, int s, SprMove& mv) {
     T.len[mv.e_q] = mv.len_q + mv.len_r;
     T.nbr[p][mv.slot_q] = T.nbr[p][mv.slot_r] = -1;
     V.orient[p - T.ntax] = -1;
+    for (int v : {p, mv.q, mv.r}) V.touch(T, v);
     V.branch_changed(T, mv.e_q);
     return true;
 }
@@ -848,6 +859,7 @@ void spr_unprune(Topology& T, ViewState& V, const SprMove& mv) {
     T.len[mv.e_q] = mv.len_q;
     T.len[mv.e_r] = mv.len_r;
     V.orient[p - T.ntax] = -1;
+    for (int v : {p, mv.q, mv.r}) V.touch(T, v);
     // views computed on the pruned tree that look across the place where p belongs lack the subtree behind s
     V.branch_changed(T, mv.e_q);
     V.branch_changed(T, mv.e_r);
@@ -875,6 +887,7 @@ void spr_undo(Topology& T, ViewState& V, const SprMove& mv) {
     T.len[mv.e_q] = mv.len_q;
     T.len[mv.e_r] = mv.len_r;
     V.orient[p - T.ntax] = -1;
+    for (int v : {p, mv.q, mv.r, mv.a, mv.b}) V.touch(T, v);
     V.branch_changed(T, mv.e_q);
     V.branch_changed(T, mv.e_t);
     V.branch_changed(T, mv.e_r);

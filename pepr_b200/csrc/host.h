@@ -68,7 +68,32 @@ struct ViewOp {
 // faces, -1 = stale.
 struct ViewState {
     std::vector<int> orient;
-    void reset(const Topology& t) { orient.assign(t.ntax - 2 > 0 ? t.ntax - 2 : 0, -1); }
+    // Cherry folding: the view of an inner node whose two other neighbours are tips is never stored -- every consumer forms it
+    // from the two tips (Side in kernels.h) -- so planning emits no op for it and it can never be stale.
+    bool fold_cherries = false;
+    static bool is_cherry_view(const Topology& t, int v, int toward_node) {
+        if (t.is_tip(v)) return false;
+        int tips = 0, others = 0;
+        for (int s = 0; s < 3; ++s) {
+            const int nb = t.nbr[v][s];
+            if (nb == toward_node) continue;
+            ++others;
+            if (nb >= 0 && t.is_tip(nb)) ++tips;
+        }
+        return others == 2 && tips == 2;
+    }
+    // A folded view still counts as one CLV update whenever a stored one would have been recomputed: fresh[v] is what
+    // orient[v] == slot would say if the cherry were stored (cleared by branch_changed / topology edits), `folded` counts the
+    // updates that planning skipped.
+    std::vector<char> fresh;
+    int64_t folded = 0;
+    void touch(const Topology& t, int v) {
+        if (v >= t.ntax && (size_t)(v - t.ntax) < fresh.size()) fresh[v - t.ntax] = 0;
+    }
+    void reset(const Topology& t) {
+        orient.assign(t.ntax - 2 > 0 ? t.ntax - 2 : 0, -1);
+        fresh.assign(orient.size(), 0);
+    }
     // appends the ops needed so that node v holds a CLV summarising everything except the subtree behind `toward`
     void plan(const Topology& t, int v, int toward_node, std::vector<ViewOp>& ops);
     // a branch length changed: every stored CLV whose subtree contains that branch becomes stale

@@ -20,12 +20,21 @@ struct DeviceModel {
     double piV[kStates][kStates];   // pi_i * V[i][k]
 };
 
-// one side of a branch: an inner node's CLV (+ cumulative scaling counts) or a tip's residue codes
+// one side of a branch: an inner node's CLV (+ cumulative scaling counts), a tip's residue codes, or a CHERRY -- an inner
+// node both of whose children on that side are tips.  A cherry's CLV is the product of two tip look-ups and is never
+// stored: every consumer forms it on the fly from the two code rows and the two tip branch lengths (no 640 B/pattern round
+// trip through HBM, no launch).  Its scaling count is 0: with both lengths inside the Newton-Raphson range the
+// fastest rate category alone keeps one of the 80 products far above 2^-256.
 struct Side {
-    const double* clv;      // nullptr for a tip
-    const int32_t* scale;   // nullptr for a tip
-    const uint8_t* codes;   // tip residue codes (0..22), nullptr for inner
+    const double* clv;      // inner node only
+    const int32_t* scale;   // inner node only
+    const uint8_t* codes;   // tip: its residue codes (0..22); cherry: codes of its first tip
+    const uint8_t* codes2;  // cherry only: codes of its second tip
+    const double* len1;     // cherry only: where the branch lengths of its two tips live on the device
+    const double* len2;
 };
+enum SideKind : int { kSideInner = 0, kSideTip = 1, kSideCherry = 2 };
+inline int side_kind(const Side& s) { return s.clv ? kSideInner : (s.codes2 ? kSideCherry : kSideTip); }
 
 struct NewviewOp {
     Side left, right;
@@ -38,7 +47,9 @@ struct NewviewOp {
     long long* trace;  // optional (profiling aid): per warp of CTA 0, cycles spent in each phase of the pipeline
 };
 
-// CLV update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 64 and all buffers hold np rows
+// the children ordered tip < cherry < inner (their product commutes exactly): the CLV kernels exist for that order only
+NewviewOp canonical_children(const NewviewOp& op);
+// CLV update on the FP64 tensor path (TMA-fed DMMA); np must be a multiple of 128 and all buffers hold np rows
 void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream);
 // raises the dynamic shared-memory limit of the tensor-path kernels on the current device (once per context)
 void configure_mma_kernels();

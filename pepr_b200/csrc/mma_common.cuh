@@ -147,6 +147,21 @@ __device__ __forceinline__ AFrag load_a(const double* block, int c, int lane) {
     f.v[4] = x[128 + lane];
     return f;
 }
+// A fragments of a cherry (Side in kernels.h): the lane's five state values of row g are products of the two tips' look-up
+// entries (23 x 80 tables, rows padded to kTipPad doubles) -- the CLV a tip-tip update would have stored, never materialised
+__device__ __forceinline__ AFrag cherry_a(const double* tab_a, const double* tab_b, int code_a, int code_b, int c, int t) {
+    const double* ra = tab_a + code_a * kTipPad + c * kStates;
+    const double* rb = tab_b + code_b * kTipPad + c * kStates;
+    const double2 a0 = *reinterpret_cast<const double2*>(ra + 2 * t), b0 = *reinterpret_cast<const double2*>(rb + 2 * t);
+    const double2 a1 = *reinterpret_cast<const double2*>(ra + 8 + 2 * t), b1 = *reinterpret_cast<const double2*>(rb + 8 + 2 * t);
+    AFrag f;
+    f.v[0] = a0.x * b0.x;
+    f.v[1] = a0.y * b0.y;
+    f.v[2] = a1.x * b1.x;
+    f.v[3] = a1.y * b1.y;
+    f.v[4] = ra[16 + t] * rb[16 + t];
+    return f;
+}
 // D fragments (states nt*8 + 2t + {0,1}; nt = 2 only for t < 2) of one 8-row block back into the blocked layout
 __device__ __forceinline__ void store_d(double* block, int c, int lane, const double (&d)[3][2]) {
     double* x = block + c * kCatDoubles;

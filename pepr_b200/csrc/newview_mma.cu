@@ -50,55 +50,67 @@ __device__ __forceinline__ void lookup_rows(const double* table, int code, int c
 //               write the scaling counts.
 //   warp 10     producer: refills the stages with one bulk copy per inner child as soon as a stage has been consumed.
 // Everything an MMA warp does besides its 60 DMMAs is ~70 instructions, so the pipe stays busy; stores cost no LSU work.
-constexpr int kThreadsNewview = 384;   // warp 11 only helps with the P matrices: 12 warps keep the register budget at 168
+//
+// A child is an inner node (its CLV tile streams in), a tip (23 x 80 look-up by residue code) or a cherry (product of two
+// tip look-ups formed in registers, then multiplied by its branch matrix like an inner child -- see Side in kernels.h).
+// The host orders the children tip < cherry < inner, which leaves five instances.
+constexpr int kThreadsNewview = 384;   // warp 11 only helps with the prologue: 12 warps keep the register budget at 168
 constexpr int kProdSlots = 4;
 constexpr int kStagers = kThreadsNewview - 32;  // every warp but the producer takes part in the prologue
 constexpr int kStageBarrier = 2;
+constexpr int kTableDoubles = kCodes * kTipPad;
 
-template <bool kTipL, bool kTipR>
+template <int KL, int KR>
 struct SmemPlan {
-    static constexpr int kInner = (kTipL ? 0 : 1) + (kTipR ? 0 : 1);
-    // a stage = the CLV tiles of the inner children + 192 B of per-row side data that travels with them:
-    // [0,64) / [64,128) scaling counts of the inner children, [128,144) residue codes of the tip child
-    static constexpr int kAuxDoubles = 24;
+    static constexpr int kInner = (KL == kSideInner ? 1 : 0) + (KR == kSideInner ? 1 : 0);
+    static constexpr int kTablesL = KL == kSideTip ? 1 : (KL == kSideCherry ? 2 : 0);
+    static constexpr int kTablesR = KR == kSideTip ? 1 : (KR == kSideCherry ? 2 : 0);
+    static constexpr int kTables = kTablesL + kTablesR;
+    // branches whose P matrices the prologue builds: the two of the update, then the tips of a cherry child
+    static constexpr int kBranches = 2 + (KL == kSideCherry ? 2 : 0) + (KR == kSideCherry ? 2 : 0);
+    // a stage = the CLV tiles of the inner children + 256 B of per-row side data that travels with them:
+    // [0,64) / [64,128) scaling counts of the inner children, [128,160) residue codes on the left (tip: 16, cherry: 2 x 16),
+    // [160,192) residue codes on the right
+    static constexpr int kAuxDoubles = 32;
     static constexpr int kStageDoubles = kInner * kTileDoubles + kAuxDoubles;
-    static constexpr int kTipDoubles = kCodes * kTipPad;             // exactly one child is a tip in the mixed case
     static constexpr int kMaxInts = kProdSlots * kCats * kTileRows;  // [slot][cat][row]
     static constexpr size_t kBarBytes = 256;
-    static_assert(kProdSlots * kTileDoubles >= 8 * pmat::kFragSlotDoubles && kProdSlots * kTileDoubles >= 4 * pmat::kFragSlotDoubles + kCats * pmat::kMat,
-                  "the product slots double as the staging area of the P matrices");
-    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(pmat::kModelDoubles + (kInner == 2 ? 0 : kTipDoubles)) +
+    static_assert(kProdSlots * kTileDoubles >= 8 * pmat::kFragSlotDoubles, "the product slots double as the fragment exchange area");
+    static constexpr size_t kBytes = kBarBytes + sizeof(double) * (size_t)(2 * pmat::kMat + kTables * kTableDoubles) +
                                      sizeof(int) * (kMaxInts + kProdSlots * kTileRows) +
                                      sizeof(double) * (size_t)(kProdSlots * kTileDoubles + kMmaGroups * kDepth * kStageDoubles);
 };
 
-// at least one child is an inner node (the tip-tip case has its own kernel below)
-template <bool kTipL, bool kTipR>
+// at least one child is not a tip (the tip-tip case has its own kernel below, used only where a cherry must be stored)
+template <int KL, int KR>
 __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op, int ntiles) {
-    using Plan = SmemPlan<kTipL, kTipR>;
-    constexpr bool kMixed = kTipL || kTipR;
+    using Plan = SmemPlan<KL, KR>;
+    constexpr bool kInnerL = KL == kSideInner, kInnerR = KR == kSideInner;
+    constexpr bool kTipL = KL == kSideTip, kTipR = KR == kSideTip;
+    constexpr bool kChL = KL == kSideCherry, kChR = KR == kSideCherry;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* in_full = reinterpret_cast<uint64_t*>(smem_raw);    // [group][kDepth]
     uint64_t* in_empty = in_full + kMmaGroups * kDepth;            // [group][kDepth]
     uint64_t* prod_full = in_empty + kMmaGroups * kDepth;          // [kProdSlots]
     uint64_t* prod_empty = prod_full + kProdSlots;                 // [kProdSlots]
-    double* s_model = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);
-    double* s_tip = s_model + pmat::kModelDoubles;
-    int* s_max = reinterpret_cast<int*>(s_tip + (kMixed ? Plan::kTipDoubles : 0));
+    double* s_model = reinterpret_cast<double*>(smem_raw + Plan::kBarBytes);   // V, Vinv
+    double* s_tabL = s_model + 2 * pmat::kMat;                     // look-ups of the left child (tip: 1, cherry: 2)
+    double* s_tabR = s_tabL + Plan::kTablesL * kTableDoubles;
+    int* s_max = reinterpret_cast<int*>(s_tabR + Plan::kTablesR * kTableDoubles);
     int* s_sc = s_max + Plan::kMaxInts;                            // [kProdSlots][16] summed scaling counts of the children
     double* s_prod = reinterpret_cast<double*>(s_sc + kProdSlots * kTileRows);
     double* s_stage = s_prod + kProdSlots * kTileDoubles;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long t_entry = 0;
-    // model constants and branch lengths are requested before the producer queues the first tiles (see branch_mma.cu)
+    // model constants are requested before the producer queues the first tiles (see branch_mma.cu)
     const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
     pmat::ModelRegs regs{};
     pdl_launch_dependents();
     if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, stid);
-    // MMA warp w builds the matrix of (category w & 3, left branch for group 0 / right branch for group 1): lane k < 20 holds
-    // lambda_k * r_c now and exp(lambda_k r_c t) once the branch length may be read
-    const int c_p = warp & 3, child_p = warp >> 2;
+    // P matrices: MMA warp w builds category w & 3 of the branches at positions (w >> 2), (w >> 2) + 2, ... of the list
+    // {left, right, tips of a left cherry, tips of a right cherry}: lane k < 20 holds lambda_k * r_c
+    const int c_p = warp & 3;
     double lr = 0.0;
     if (warp < kMmaWarps && lane < kStates) lr = op.dm->lambda[lane] * op.dm->rates[c_p];
     if (threadIdx.x == 0) {
@@ -114,9 +126,18 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
-    // the length is requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
-    double my_len = 0.0;
-    if (warp < kMmaWarps) my_len = (child_p == 0 ? *op.len_left : *op.len_right) * op.len_scale;
+    // the lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
+    constexpr int kRounds = Plan::kBranches / 2;
+    double my_len[kRounds];
+    if (warp < kMmaWarps) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;  // 0, 1: the update's branches; 2, 3 / 4, 5: cherry tips
+            const double* src = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
+                                : id == 4 ? op.right.len1 : op.right.len2;
+            my_len[r] = *src * (id < 2 ? op.len_scale : 1.0);
+        }
+    }
     if (warp != kProducerWarp) pmat::matrices_to_smem<kStagers>(regs, stid, s_model);  // V and Vinv
     __syncthreads();
 
@@ -125,14 +146,16 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
 
     if (warp == kProducerWarp) {
         // ---------------------------------------------------------------------------------------------- producer
-        // lane 0 waits for the stage and announces the bytes, then lanes 0-3 hand one bulk copy each to the TMA engine
+        // lane 0 waits for the stage and announces the bytes, then lanes 0-7 hand one bulk copy each to the TMA engine
         constexpr uint32_t bytes = kTileDoubles * sizeof(double), sc_bytes = kTileRows * sizeof(int32_t);
+        constexpr uint32_t tx = Plan::kInner * (bytes + sc_bytes) + (kTipL ? kTileRows : 0) + (kChL ? 2 * kTileRows : 0) +
+                                (kTipR ? kTileRows : 0) + (kChR ? 2 * kTileRows : 0);
         for (int n = 0; n < cta_tiles; ++n) {
             const int grp = n % kMmaGroups, j = n / kMmaGroups, slot = j % kDepth;
             uint64_t* full = in_full + grp * kDepth + slot;
             if (lane == 0) {
                 mbar_wait(in_empty + grp * kDepth + slot, ((j / kDepth) & 1) ^ 1);
-                mbar_expect_tx(full, Plan::kInner * (bytes + sc_bytes) + (kMixed ? kTileRows : 0));
+                mbar_expect_tx(full, tx);
             }
             __syncwarp();
             const size_t tile = (size_t)blockIdx.x + (size_t)n * gridDim.x;
@@ -140,46 +163,53 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             double* dst = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
             unsigned char* aux = reinterpret_cast<unsigned char*>(dst + Plan::kInner * kTileDoubles);
             if (lane == 0) {
-                if (!kTipL) bulk_g2s(dst, op.left.clv + goff, bytes, full);
-                else bulk_g2s(dst, op.right.clv + goff, bytes, full);
+                if (kInnerL) bulk_g2s(dst, op.left.clv + goff, bytes, full);
+                else bulk_g2s(aux + 128, op.left.codes + tile * kTileRows, kTileRows, full);
             } else if (lane == 1) {
-                if (!kMixed) bulk_g2s(dst + kTileDoubles, op.right.clv + goff, bytes, full);
-                else bulk_g2s(aux + 128, (kTipL ? op.left.codes : op.right.codes) + tile * kTileRows, kTileRows, full);
+                if (kInnerR) bulk_g2s(dst + (kInnerL ? kTileDoubles : 0), op.right.clv + goff, bytes, full);
+                else bulk_g2s(aux + 160, op.right.codes + tile * kTileRows, kTileRows, full);
             } else if (lane == 2) {
-                bulk_g2s(aux, (kTipL ? op.right.scale : op.left.scale) + tile * kTileRows, sc_bytes, full);
-            } else if (lane == 3 && !kMixed) {
-                bulk_g2s(aux + sc_bytes, op.right.scale + tile * kTileRows, sc_bytes, full);
+                if (kInnerL) bulk_g2s(aux, op.left.scale + tile * kTileRows, sc_bytes, full);
+                else if (kChL) bulk_g2s(aux + 144, op.left.codes2 + tile * kTileRows, kTileRows, full);
+            } else if (lane == 3) {
+                if (kInnerR) bulk_g2s(aux + sc_bytes, op.right.scale + tile * kTileRows, sc_bytes, full);
+                else if (kChR) bulk_g2s(aux + 176, op.right.codes2 + tile * kTileRows, kTileRows, full);
             }
         }
         return;
     }
 
-    // every other warp: P matrices of both branches in shared memory (product slots, free until the first tile is done)
+    // every other warp: the P matrices.  An inner or cherry child's matrix leaves the accumulators as B fragments (shared with
+    // the other group's warp of the same category through the product slots, free until the first tile is done); a tip's
+    // matrix -- a tip child's or a cherry's -- goes straight into its look-up table.
     const bool trp = op.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     if (trp) op.trace[90] += clock64() - t_entry;
-    // Each MMA warp builds ONE of the eight matrices on the tensor pipe.  An inner child's matrix is turned into B fragments
-    // and shared with the partner warp of the other group through shared memory; a tip child's matrix goes to shared memory
-    // for the lookup table.
     double fragL[3][5], fragR[3][5];
-    double* s_x = s_prod;                                          // fragment exchange: [slot][15][32]
-    double* s_Ptip = s_prod + 4 * pmat::kFragSlotDoubles;          // mixed case: P[c][i][j] of the tip child
+    double* s_x = s_prod;  // fragment exchange: [branch 0 / 1][category][15][32]
     if (warp < kMmaWarps) {
-        double acc[3][3][2];
-        pmat::build_p_tiles(s_model, exp(lr * my_len), lane, acc);
-        const bool tip_child = child_p == 0 ? kTipL : kTipR;
-        if (tip_child) pmat::tiles_to_smem(acc, lane, s_Ptip + c_p * pmat::kMat);
-        else {
-            if (child_p == 0) pmat::tiles_to_fragments(acc, lane, fragL);
-            else pmat::tiles_to_fragments(acc, lane, fragR);
-            pmat::fragments_to_smem(child_p == 0 ? fragL : fragR, lane, s_x + (kMixed ? c_p : warp) * pmat::kFragSlotDoubles);
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;
+            double acc[3][3][2];
+            pmat::build_p_tiles(s_model, exp(lr * my_len[r]), lane, acc);
+            double* table = nullptr;
+            if (id == 0 && kTipL) table = s_tabL;
+            else if (id == 1 && kTipR) table = s_tabR;
+            else if (id == 2 || id == 3) table = s_tabL + (id - 2) * kTableDoubles;
+            else if (id >= 4) table = s_tabR + (id - 4) * kTableDoubles;
+            if (table) pmat::tiles_to_lookup(acc, lane, c_p, table, kTipPad);
+            else {
+                double frag[3][5];
+                pmat::tiles_to_fragments(acc, lane, frag);
+                pmat::fragments_to_smem(frag, lane, s_x + (id * kCats + c_p) * pmat::kFragSlotDoubles);
+            }
         }
     }
     named_barrier(kStageBarrier, kStagers);
     if (trp) op.trace[92] += clock64() - t_entry;
-    if (kMixed) pmat::build_tip_lookup<kStagers>(s_Ptip, stid, s_tip, kTipPad);
-    if (warp < kMmaWarps) {  // the other child's fragments were built by the partner warp
-        if (!kTipL && child_p == 1) pmat::fragments_from_smem(fragL, lane, s_x + c_p * pmat::kFragSlotDoubles);
-        if (!kTipR && child_p == 0) pmat::fragments_from_smem(fragR, lane, s_x + (kMixed ? c_p : kCats + c_p) * pmat::kFragSlotDoubles);
+    if (warp < kMmaWarps) {
+        if (!kTipL) pmat::fragments_from_smem(fragL, lane, s_x + c_p * pmat::kFragSlotDoubles);
+        if (!kTipR) pmat::fragments_from_smem(fragR, lane, s_x + (kCats + c_p) * pmat::kFragSlotDoubles);
     }
     named_barrier(kStageBarrier, kStagers);  // the product slots are free for their real purpose
     if (warp > kProducerWarp) return;
@@ -267,24 +297,22 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         long long tk1 = tr ? clock64() : 0;
         const double* stage = s_stage + (size_t)(grp * kDepth + slot) * Plan::kStageDoubles;
         const unsigned char* aux = reinterpret_cast<const unsigned char*>(stage + Plan::kInner * kTileDoubles);
-        int code[2] = {0, 0};
-        if (kMixed) {
-            code[0] = aux[128 + g];
-            code[1] = aux[128 + 8 + g];
-        }
-        int32_t sc_sum = 0;  // category-0 warp, lanes 0-15: scaling counts of the children of row `lane`
-        if (c == 0 && lane < kTileRows) {
+        int32_t sc_sum = 0;  // category-0 warp, lanes 0-15: scaling counts of the inner children of row `lane`
+        if (Plan::kInner > 0 && c == 0 && lane < kTileRows) {
             const int32_t* sci = reinterpret_cast<const int32_t*>(aux);
-            sc_sum = sci[lane] + (Plan::kInner == 2 ? sci[kTileRows + lane] : 0);
+            sc_sum = (kInnerL ? sci[lane] : 0) + (kInnerR ? sci[kTileRows + lane] : 0);
         }
         double accL[2][3][2], accR[2][3][2];
         AFrag aL[2], aR[2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-            if (kTipL) lookup_rows(s_tip, code[m], c, t, accL[m]);
+            const int row = m * 8 + g;
+            if (kTipL) lookup_rows(s_tabL, aux[128 + row], c, t, accL[m]);
+            else if (kChL) aL[m] = cherry_a(s_tabL, s_tabL + kTableDoubles, aux[128 + row], aux[144 + row], c, t);
             else aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
-            if (kTipR) lookup_rows(s_tip, code[m], c, t, accR[m]);
-            else aR[m] = load_a(stage + (kTipL ? 0 : kTileDoubles) + m * kBlockDoubles, c, lane);
+            if (kTipR) lookup_rows(s_tabR, aux[160 + row], c, t, accR[m]);
+            else if (kChR) aR[m] = cherry_a(s_tabR, s_tabR + kTableDoubles, aux[160 + row], aux[176 + row], c, t);
+            else aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
         }
 #pragma unroll
         for (int m = 0; m < 2; ++m)
@@ -483,32 +511,50 @@ __global__ void __launch_bounds__(kTipTipThreads, 1) k_newview_tiptip(NewviewOp 
     }
 }
 
-template <bool kTipL, bool kTipR>
+template <int KL, int KR>
 void launch_one(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
-    using Plan = SmemPlan<kTipL, kTipR>;
+    using Plan = SmemPlan<KL, KR>;
     const int ntiles = (int)(np / kTileRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    launch_pdl(k_newview_mma<kTipL, kTipR>, grid, kThreadsNewview, Plan::kBytes, stream, op, ntiles);
+    launch_pdl(k_newview_mma<KL, KR>, grid, kThreadsNewview, Plan::kBytes, stream, op, ntiles);
+}
+
+template <int KL, int KR>
+void configure_one() {
+    cudaFuncSetAttribute(k_newview_mma<KL, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<KL, KR>::kBytes);
 }
 
 }  // namespace
 
 void configure_mma_kernels() {
-    cudaFuncSetAttribute(k_newview_mma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<true, false>::kBytes);
-    cudaFuncSetAttribute(k_newview_mma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<false, true>::kBytes);
-    cudaFuncSetAttribute(k_newview_mma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmemPlan<false, false>::kBytes);
+    configure_one<kSideTip, kSideCherry>();
+    configure_one<kSideTip, kSideInner>();
+    configure_one<kSideCherry, kSideCherry>();
+    configure_one<kSideCherry, kSideInner>();
+    configure_one<kSideInner, kSideInner>();
     cudaFuncSetAttribute(k_newview_tiptip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TipTipSmem));
 }
 
+NewviewOp canonical_children(const NewviewOp& in) {
+    auto rank = [](const Side& s) { const int k = side_kind(s); return k == kSideTip ? 0 : (k == kSideCherry ? 1 : 2); };
+    NewviewOp op = in;
+    if (rank(op.left) > rank(op.right)) {  // the product of the two children commutes exactly
+        std::swap(op.left, op.right);
+        std::swap(op.len_left, op.len_right);
+    }
+    return op;
+}
+
 // np must be a multiple of 128 (the engine pads pattern rows to 128)
-void launch_newview_mma(const NewviewOp& op, int64_t np, int sms, cudaStream_t stream) {
-    const bool tl = op.left.clv == nullptr, tr = op.right.clv == nullptr;
-    if (tl && tr) {
+void launch_newview_mma(const NewviewOp& in, int64_t np, int sms, cudaStream_t stream) {
+    const NewviewOp op = canonical_children(in);
+    const int kl = side_kind(op.left), kr = side_kind(op.right);
+    if (kl == kSideTip && kr == kSideTip) {
         const int64_t nblk = np / kBlockRows;
         launch_pdl(k_newview_tiptip, (int)(nblk < sms ? nblk : sms), kTipTipThreads, sizeof(TipTipSmem), stream, op, np);
-    } else if (tl) launch_one<true, false>(op, np, sms, stream);
-    else if (tr) launch_one<false, true>(op, np, sms, stream);
-    else launch_one<false, false>(op, np, sms, stream);
+    } else if (kl == kSideTip) kr == kSideCherry ? launch_one<kSideTip, kSideCherry>(op, np, sms, stream) : launch_one<kSideTip, kSideInner>(op, np, sms, stream);
+    else if (kl == kSideCherry) kr == kSideCherry ? launch_one<kSideCherry, kSideCherry>(op, np, sms, stream) : launch_one<kSideCherry, kSideInner>(op, np, sms, stream);
+    else launch_one<kSideInner, kSideInner>(op, np, sms, stream);
 }
 
 }  // namespace pml

@@ -168,6 +168,39 @@ __device__ __forceinline__ void tiles_to_smem(const double (&acc)[3][3][2], int 
             if (i < kStates && j < kStates) *reinterpret_cast<double2*>(Pc + i * kStates + j) = make_double2(acc[nt][jt][0], acc[nt][jt][1]);
         }
 }
+// accumulators -> the 23 x 80 look-up of a tip on that branch, tip[code][c*20 + i] = sum_j P_c[i][j] indicator(code)[j], written
+// straight from the warp that built the matrix (category c): residue codes are single columns of P_c, B = N|D (columns 2, 3),
+// Z = Q|E (columns 5, 6), undetermined = the row sum.  Rows padded to `pad` doubles.
+__device__ __forceinline__ void tiles_to_lookup(const double (&acc)[3][3][2], int lane, int c, double* table, int pad) {
+    const int g = lane >> 2, t = lane & 3, quad = lane & ~3;
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+        const int i = nt * 8 + g;
+        const bool row_ok = i < kStates;
+        double* col = table + c * kStates + i;
+        double sum = 0.0;
+#pragma unroll
+        for (int jt = 0; jt < 3; ++jt)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const int j = jt * 8 + 2 * t + x;
+                if (j < kStates) {
+                    if (row_ok) col[j * pad] = acc[nt][jt][x];
+                    sum += acc[nt][jt][x];
+                }
+            }
+        const double q5 = __shfl_sync(0xffffffffu, acc[nt][0][1], quad | 2), e6 = __shfl_sync(0xffffffffu, acc[nt][0][0], quad | 3);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (row_ok) {
+            if (t == 1) col[20 * pad] = acc[nt][0][0] + acc[nt][0][1];
+            if (t == 0) {
+                col[21 * pad] = q5 + e6;
+                col[22 * pad] = sum;
+            }
+        }
+    }
+}
 // fragment exchange between the two MMA groups: [warp slot][fragment][lane]
 __device__ __forceinline__ void fragments_to_smem(const double (&frag)[3][5], int lane, double* slot) {
 #pragma unroll

@@ -12,9 +12,18 @@ c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
 
 
-# kernel kinds of pml_profile_begin/end (PML_NKINDS in include/peprml.h), in index order
-KINDS = ["newview_tip_tip", "newview_tip_inner", "newview_inner_inner", "evaluate", "branch_inner_inner", "core", "branch_tip_inner",
-         "fused_ii_inner", "fused_ii_tip", "fused_ti_inner", "fused_ti_tip"]
+NKINDS = 28   # PML_NKINDS in include/peprml.h
+
+
+def kinds():
+    """kernel kinds of pml_profile_begin/end in index order: [(name, algorithmic bytes per pattern, DMMA per tile and warp)]"""
+    out = []
+    for k in range(NKINDS):
+        name = C.create_string_buffer(64)
+        b, d = C.c_int(0), C.c_int(0)
+        lib().pml_kind_info(k, name, 64, C.byref(b), C.byref(d))
+        out.append((name.value.decode(), b.value, d.value))
+    return out
 
 
 class EngineError(RuntimeError):
@@ -84,6 +93,7 @@ def lib():
         L.pml_timer_start.argtypes = [C.c_void_p]
         L.pml_timer_stop.argtypes = [C.c_void_p, c_f64p]
         L.pml_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pml_kind_info.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.pml_bootstrap_weights_host.argtypes = [C.c_void_p, C.c_int64, c_i64p, C.c_int, C.c_void_p]
         L.pml_crunch_patterns.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
         L.pml_crunch_patterns_sharded.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
@@ -149,12 +159,11 @@ class Context:
 
     def profile_end(self):
         """-> dict kind -> (device ms, launches, pattern rows)"""
-        ms = (C.c_double * len(KINDS))()
-        n = (C.c_int64 * len(KINDS))()
-        rows = (C.c_int64 * len(KINDS))()
+        ms = (C.c_double * NKINDS)()
+        n = (C.c_int64 * NKINDS)()
+        rows = (C.c_int64 * NKINDS)()
         self.check(lib().pml_profile_end(self.h, ms, n, rows), "pml_profile_end")
-        kinds = KINDS
-        return {k: (ms[i], n[i], rows[i]) for i, k in enumerate(kinds)}
+        return {k[0]: (ms[i], n[i], rows[i]) for i, k in enumerate(kinds())}
 
     def close(self):
         if self.h:

@@ -233,6 +233,54 @@ def test_fused_update_and_branch_pass_equals_two_launches(golden, case):
     assert f[7] == t[7] and f[6] < t[6]          # same site-updates, fewer launches
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["small", "dup", "deep", "wide"])
+def test_folded_cherries_equal_stored_cherries(golden, case):
+    """Cherry folding (an inner node with two tip children is never stored: its consumers form the product of the two tip
+    look-ups themselves) against the engine with every CLV stored (PEPRML_NO_FOLD=1): per-site lnL, derivatives on every
+    branch, smoothing sweeps, `-f e`, lazy SPR scores; same site-update count, fewer launches."""
+    import os
+    g = golden(case)
+    fe = g.meta["fe"]
+    res = {}
+    for mode in ("fold", "stored"):
+        if mode == "stored":
+            os.environ["PEPRML_NO_FOLD"] = "1"
+        else:
+            os.environ.pop("PEPRML_NO_FOLD", None)
+        ctx = pb.Context(0)
+        os.environ.pop("PEPRML_NO_FOLD", None)
+        aln = pb.Alignment(ctx, g.names, g.seqs, alpha=fe["alpha"])
+        tree = pb.Tree(aln, fe["tree"])
+        lnl, ps = tree.evaluate(per_site=True)
+        assert abs(lnl - fe["lnl"]) <= REL_REF * abs(fe["lnl"])
+        der = np.array([tree.branch_derivs(e, 0.07 + 0.01 * (e % 5)) for e in range(tree.num_branches)])
+        su0, ln0 = tree.stats()
+        for e in range(tree.num_branches):
+            tree.set_branch(e, 0.05 + 0.01 * (e % 7))
+        tree.smooth(2)
+        lens = [tree.branch(e)[2] for e in range(tree.num_branches)]
+        l2 = tree.evaluate()
+        su1, ln1 = tree.stats()
+        spr = []
+        for node in range(len(g.names), min(len(g.names) + 4, 2 * len(g.names) - 2)):
+            for keep in tree.neighbors(node):
+                tg, sc = tree.score_spr_candidates(node, keep, 3)
+                spr += sorted(zip(tg.tolist(), sc.tolist()))
+        tree.close()
+        t2 = pb.Tree(aln, g.meta["tree_in"])
+        l3, a3 = t2.optimize(True, 0.1)
+        t2.close(); aln.close(); ctx.close()
+        res[mode] = (lnl, ps, np.array(lens), l2, l3, a3, ln1 - ln0, sum(su1) - sum(su0), der, np.array(spr))
+    f, t = res["fold"], res["stored"]
+    assert abs(f[0] - t[0]) <= 1e-12 * abs(t[0]) and np.abs(f[1] - t[1]).max() <= 1e-9
+    assert np.allclose(f[8], t[8], rtol=1e-9, atol=1e-9), np.abs(f[8] - t[8]).max()
+    assert np.allclose(f[2], t[2], rtol=1e-8, atol=1e-12) and abs(f[3] - t[3]) <= 1e-10 * abs(t[3])
+    assert abs(f[4] - t[4]) <= 1e-3 and abs(f[5] - t[5]) <= 1e-4 * t[5]
+    assert f[9].shape == t[9].shape and np.allclose(f[9], t[9], rtol=1e-10)
+    assert f[7] <= t[7] and f[6] < t[6]          # no more site-updates (a folded view never evicts a stored one), fewer launches
+
+
 def test_real_data_per_site_lnl_and_search(gpu_ctx, golden):
     """the reference's own example genomes (tests/golden/make_real.py): per-site lnL against raxmlHPC -f g, and the engine's
     search from a parsimony start tree ends at least as high as raxmlHPC -f d did (two strains are identical: branches at
