@@ -347,11 +347,13 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             side.y = ai[2 * kTileRows + lane];
         }
         AFrag fa[2], fb[2];
+        CherryIn cA{};
+        if (kChA) cA = cherry_begin(s_tip, s_tip + kCodes * kTipPad, aux + 192, aux + 208, g, c, t);  // formed inside the turn (mma_common.cuh)
+        int multiplied = 0;
         double accA[2][3][2], accB[2][3][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             if (kInnerA) fa[m] = load_a(stage + m * kBlockDoubles, c, lane);
-            else if (kChA) fa[m] = cherry_a(s_tip, s_tip + kCodes * kTipPad, aux[192 + m * 8 + g], aux[208 + m * 8 + g], c, t);
             fb[m] = load_a(stage + (kInnerA ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
             const int code = kTipA ? aux[192 + m * 8 + g] : 0;
 #pragma unroll
@@ -379,6 +381,8 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
                     for (int nt = 0; nt < 3; ++nt) dmma(accB[m][nt][0], accB[m][nt][1], fb[m].v[kt], fragB[nt][kt]);
+        } else if (kChA) {
+            multiplied = children_mma<kSideCherry, kSideInner>(fa, fb, cA, cA, fragA, fragB, accA, accB, t);
         } else {
 #pragma unroll
             for (int m = 0; m < 2; ++m)
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         for (int m = 0; m < 2; ++m) fs[m][0][0] = fs[m][0][1] = fs[m][1][0] = fs[m][1][1] = 0.0;
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) {
+            if (multiplied & 1) break;
             accA[0][nt][0] *= accB[0][nt][0];
             accA[0][nt][1] *= accB[0][nt][1];
         }
@@ -403,6 +408,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         dmma(fs[0][1][0], fs[0][1][1], accA[0][0][1], efrag[0][1]);
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) {
+            if (multiplied & 2) break;
             accA[1][nt][0] *= accB[1][nt][0];
             accA[1][nt][1] *= accB[1][nt][1];
         }

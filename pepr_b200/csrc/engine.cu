@@ -436,7 +436,8 @@ bool run_ops(pml_tree* t, const std::vector<ViewOp>& ops) {
     for (const ViewOp& op : ops) {
         NewviewOp nv = make_newview_op(t, op);
         const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-        nv.trace = (c->trace_newview_tips < 0 || c->trace_newview_tips == ntip) ? c->d_trace : nullptr;
+        static const char* only = getenv("PEPRML_TRACE_KIND");  // profiling aid: trace CLV kernels of one kind only (launch_newview)
+        nv.trace = (only ? atoi(only) == newview_kind(nv.left, nv.right) : (c->trace_newview_tips < 0 || c->trace_newview_tips == ntip)) ? c->d_trace : nullptr;
         launch_newview(t, nv);
     }
     return ops.empty() || c->cuda(cudaGetLastError(), "CLV kernels");
@@ -546,7 +547,11 @@ double branch_launch(pml_tree* t, int e, const int32_t* dw, double len, bool kee
         if (side_kind(nv.right) == kSideCherry) nv.right = materialize_cherry(t, last.child[1], last.node);
     }
     const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
-    if (c->trace_fused && ntip == 0 && side_kind(sfar) == kSideInner) nv.trace = c->d_trace_buf;  // inner-inner update, inner far end
+    {
+        static const char* only = getenv("PEPRML_TRACE_KIND");  // profiling aid: trace fused kernels of one kind only
+        const int kind = 13 + 3 * (newview_kind(nv.left, nv.right) - 1) + far_index(sfar);
+        if (c->trace_fused && (only ? atoi(only) == kind : kind == 16)) nv.trace = c->d_trace_buf;  // default: inner-inner update, inner far end
+    }
     t->site_updates[2 - ntip] += t->aln->nloc;
     Side sx{};
     sx.clv = nv.out;

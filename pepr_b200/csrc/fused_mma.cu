@@ -472,15 +472,16 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             }
             double accL[2][3][2], accR[2][3][2];
             AFrag aL[2], aR[2];
+            CherryIn cL{}, cR{};
+            if (kChL) cL = cherry_begin(s_tabL, s_tabL + kTableDoubles, aux + 128, aux + 144, g, c, t);
+            if (kChR) cR = cherry_begin(s_tabR, s_tabR + kTableDoubles, aux + 160, aux + 176, g, c, t);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 const int row = m * 8 + g;
                 if (kTipL) lookup_rows(s_tabL, aux[128 + row], c, t, accL[m]);
-                else if (kChL) aL[m] = cherry_a(s_tabL, s_tabL + kTableDoubles, aux[128 + row], aux[144 + row], c, t);
-                else aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
+                else if (kInnerL) aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
                 if (kTipR) lookup_rows(s_tabR, aux[160 + row], c, t, accR[m]);
-                else if (kChR) aR[m] = cherry_a(s_tabR, s_tabR + kTableDoubles, aux[160 + row], aux[176 + row], c, t);
-                else aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
+                else if (kInnerR) aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
             }
 #pragma unroll
             for (int m = 0; m < 2; ++m)
@@ -491,15 +492,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 }
             mma_turn_begin(0);
             const long long k2 = tr ? clock64() : 0;
-#pragma unroll
-            for (int kt = 0; kt < 5; ++kt)
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < 3; ++nt) {
-                        if (!kTipL) dmma(accL[m][nt][0], accL[m][nt][1], aL[m].v[kt], fragL[nt][kt]);
-                        if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
-                    }
+            const int multiplied = children_mma<KL, KR>(aL, aR, cL, cR, fragL, fragR, accL, accR, t);
             const long long k3 = tr ? clock64() : 0;
             mma_turn_end(0);
             __syncwarp();
@@ -511,8 +504,10 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 big[m] = 0;
 #pragma unroll
                 for (int nt = 0; nt < 3; ++nt) {
-                    accL[m][nt][0] *= accR[m][nt][0];
-                    accL[m][nt][1] *= accR[m][nt][1];
+                    if (!(multiplied >> m & 1)) {
+                        accL[m][nt][0] *= accR[m][nt][0];
+                        accL[m][nt][1] *= accR[m][nt][1];
+                    }
                     if (nt < 2 || t < 2) big[m] = max(big[m], max(__double2hiint(accL[m][nt][0]) & 0x7fffffff, __double2hiint(accL[m][nt][1]) & 0x7fffffff));
                 }
                 big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 1));
@@ -600,12 +595,13 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             side.y = ai[kTileRows + lane];
         }
         AFrag fx[2], fy[2];
+        CherryIn cY{};
+        if (kChY) cY = cherry_begin(s_tabY, s_tabY + kTableDoubles, yaux + 128, yaux + 144, g, c, t);  // formed inside the turn (mma_common.cuh)
         double accY[2][3][2], accX[2][3][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             fx[m] = load_a(prod + m * kBlockDoubles, c, lane);
             if (kInnerY) fy[m] = load_a(ystage + m * kBlockDoubles, c, lane);
-            else if (kChY) fy[m] = cherry_a(s_tabY, s_tabY + kTableDoubles, yaux[128 + m * 8 + g], yaux[144 + m * 8 + g], c, t);
             const int code = kTipY ? yaux[128 + m * 8 + g] : 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
@@ -629,17 +625,12 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         const long long b3 = trb ? clock64() : 0;
         mma_turn_begin(1);
         const long long b4 = trb ? clock64() : 0;
-#pragma unroll
-        for (int kt = 0; kt < 5; ++kt) {
-            if (kt < 3 && prev_n >= 0) contraction_step(kt, fs);  // previous tile: one link of each chain per k step
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    if (!kTipY) dmma(accY[m][nt][0], accY[m][nt][1], fy[m].v[kt], fragL[nt][kt]);
-                    dmma(accX[m][nt][0], accX[m][nt][1], fx[m].v[kt], fragR[nt][kt]);
-                }
-        }
+        // previous tile's contraction: one link of each chain ahead of the first three k steps of block 0
+        const bool have_prev = prev_n >= 0;
+        auto slip_in = [&](int kt) {
+            if (kt < 3 && have_prev) contraction_step(kt, fs);
+        };
+        const int multiplied = children_mma<KY, kSideInner>(fy, fx, cY, cY, fragL, fragR, accY, accX, t, slip_in);
         const long long b5 = trb ? clock64() : 0;
         mma_turn_end(1);
         __syncwarp();
@@ -649,8 +640,8 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-                sv[m][nt][0] = accY[m][nt][0] * accX[m][nt][0];
-                sv[m][nt][1] = accY[m][nt][1] * accX[m][nt][1];
+                sv[m][nt][0] = (multiplied >> m & 1) ? accY[m][nt][0] : accY[m][nt][0] * accX[m][nt][0];
+                sv[m][nt][1] = (multiplied >> m & 1) ? accY[m][nt][1] : accY[m][nt][1] * accX[m][nt][1];
             }
         side_prev = side;
         prev_n = n;

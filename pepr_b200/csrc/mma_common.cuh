@@ -147,20 +147,140 @@ __device__ __forceinline__ AFrag load_a(const double* block, int c, int lane) {
     f.v[4] = x[128 + lane];
     return f;
 }
-// A fragments of a cherry (Side in kernels.h): the lane's five state values of row g are products of the two tips' look-up
-// entries (23 x 80 tables, rows padded to kTipPad doubles) -- the CLV a tip-tip update would have stored, never materialised
-__device__ __forceinline__ AFrag cherry_a(const double* tab_a, const double* tab_b, int code_a, int code_b, int c, int t) {
-    const double* ra = tab_a + code_a * kTipPad + c * kStates;
-    const double* rb = tab_b + code_b * kTipPad + c * kStates;
-    const double2 a0 = *reinterpret_cast<const double2*>(ra + 2 * t), b0 = *reinterpret_cast<const double2*>(rb + 2 * t);
-    const double2 a1 = *reinterpret_cast<const double2*>(ra + 8 + 2 * t), b1 = *reinterpret_cast<const double2*>(rb + 8 + 2 * t);
-    AFrag f;
-    f.v[0] = a0.x * b0.x;
-    f.v[1] = a0.y * b0.y;
-    f.v[2] = a1.x * b1.x;
-    f.v[3] = a1.y * b1.y;
-    f.v[4] = ra[16 + t] * rb[16 + t];
-    return f;
+// ---- folded cherries (Side in kernels.h) ---------------------------------------------------------------------------------
+// The CLV a tip-tip update would have stored is the product of the two tips' look-up entries (23 x 80 tables, rows padded to
+// kTipPad doubles).  A consumer forms the five state values a lane feeds into the k-tiles JUST IN TIME inside its own MMA
+// turn: the raw table entries of the first k-tile pair are fetched before the turn, every later pair while the DMMAs of the
+// previous one issue, and the multiplications sit between this warp's own DMMAs.  (Formed ahead of the turn, those FP64
+// multiplications queued behind the other group's DMMAs: +300 clk on every tile's critical path.)
+struct CherryRows {
+    const double* a[2];   // per 8-row block m: row of the first / second tip's look-up for this lane's pattern, category applied
+    const double* b[2];
+};
+__device__ __forceinline__ CherryRows cherry_rows(const double* tab_a, const double* tab_b, int code_a0, int code_b0, int code_a1, int code_b1, int c) {
+    CherryRows r;
+    r.a[0] = tab_a + code_a0 * kTipPad + c * kStates;
+    r.b[0] = tab_b + code_b0 * kTipPad + c * kStates;
+    r.a[1] = tab_a + code_a1 * kTipPad + c * kStates;
+    r.b[1] = tab_b + code_b1 * kTipPad + c * kStates;
+    return r;
+}
+// raw entries of block m, chunk ch (k-tiles 2ch, 2ch+1: states {2t, 2t+1} of the first / second octet; chunk 2: state 16 + t)
+struct CherryRaw {
+    double2 a, b;
+};
+__device__ __forceinline__ CherryRaw cherry_fetch(const CherryRows& r, int m, int ch, int t) {
+    CherryRaw v;
+    if (ch < 2) {
+        v.a = *reinterpret_cast<const double2*>(r.a[m] + 8 * ch + 2 * t);
+        v.b = *reinterpret_cast<const double2*>(r.b[m] + 8 * ch + 2 * t);
+    } else {
+        v.a = make_double2(r.a[m][16 + t], 0.0);
+        v.b = make_double2(r.b[m][16 + t], 0.0);
+    }
+    return v;
+}
+// what a cherry side carries into the turn: its rows and the raw entries of the first two chunks (block 0), fetched before the turn
+struct CherryIn {
+    CherryRows rows;
+    CherryRaw r0, r1;
+};
+__device__ __forceinline__ CherryIn cherry_begin(const double* tab_a, const double* tab_b, const unsigned char* codes_a, const unsigned char* codes_b,
+                                                 int g, int c, int t) {
+    CherryIn in;
+    in.rows = cherry_rows(tab_a, tab_b, codes_a[g], codes_b[g], codes_a[8 + g], codes_b[8 + g], c);
+    in.r0 = cherry_fetch(in.rows, 0, 0, t);
+    in.r1 = cherry_fetch(in.rows, 0, 1, t);
+    return in;
+}
+constexpr int kSideInnerK = 0, kSideTipK = 1, kSideCherryK = 2;  // = SideKind (kernels.h)
+
+// Where the element-wise product of the two children is taken (12 FP64 multiplications per warp and tile).  Issued after the
+// turn has been handed over they queue behind the other group's DMMAs (~28 clk each, in-order issue: +300 clk on the group's
+// cycle); issued inside the turn they cost the tensor pipe the latency of the last DMMAs.  kProductsInTurn: block 0's products
+// go out under block 1's DMMAs, block 1's right behind its last DMMA, still inside the turn.
+#ifndef PML_PRODUCTS_IN_TURN
+#define PML_PRODUCTS_IN_TURN 2
+#endif
+
+// The MMA turn of a CLV update, block-major: acc?[m][nt] += A?[m][kt] * frag?[nt][kt] over the five k-tiles for both children, then
+// (PML_PRODUCTS_IN_TURN) accL[m] *= accR[m].  A child that is an inner node brings its A fragments (a?), a tip takes no part (its
+// look-up rows already sit in the accumulators), a cherry its rows and first raw entries (c?).  A cherry's products for a
+// chunk are issued one chunk AHEAD of the DMMAs that use them, its raw entries fetched two chunks ahead.
+// Returns the blocks whose products have been taken (bit m).
+struct NoExtra {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+// extra(kt) is called ahead of the DMMAs of k-tile kt of block 0 (the fused kernel slips the previous tile's contraction in there)
+template <int KL, int KR, typename Extra = NoExtra>
+__device__ __forceinline__ int children_mma(const AFrag (&aL)[2], const AFrag (&aR)[2], const CherryIn& cL, const CherryIn& cR,
+                                            const double (&fragL)[3][5], const double (&fragR)[3][5], double (&accL)[2][3][2],
+                                            double (&accR)[2][3][2], int t, Extra extra = Extra()) {
+    constexpr bool kCL = KL == kSideCherryK, kCR = KR == kSideCherryK;
+    CherryRaw rawL = cL.r1, rawR = cR.r1;       // raw entries of the chunk after the next one to be multiplied
+    double vL[2] = {0.0, 0.0}, vR[2] = {0.0, 0.0};  // products of the chunk whose DMMAs come next
+    if (kCL) {
+        vL[0] = cL.r0.a.x * cL.r0.b.x;
+        vL[1] = cL.r0.a.y * cL.r0.b.y;
+    }
+    if (kCR) {
+        vR[0] = cR.r0.a.x * cR.r0.b.x;
+        vR[1] = cR.r0.a.y * cR.r0.b.y;
+    }
+    int done = 0;
+#pragma unroll
+    for (int step = 0; step < 6; ++step) {  // (block, chunk) pairs in order
+        const int m = step / 3, ch = step % 3;
+        // products of the NEXT chunk (their raw entries arrived a chunk ago), then the fetch for the one after it
+        double nL[2] = {0.0, 0.0}, nR[2] = {0.0, 0.0};
+        if (step < 5) {
+            const int ch1 = (step + 1) % 3;
+            if (kCL) {
+                nL[0] = rawL.a.x * rawL.b.x;
+                if (ch1 < 2) nL[1] = rawL.a.y * rawL.b.y;
+            }
+            if (kCR) {
+                nR[0] = rawR.a.x * rawR.b.x;
+                if (ch1 < 2) nR[1] = rawR.a.y * rawR.b.y;
+            }
+        }
+        if (step < 4) {
+            const int m2 = (step + 2) / 3, ch2 = (step + 2) % 3;
+            if (kCL) rawL = cherry_fetch(cL.rows, m2, ch2, t);
+            if (kCR) rawR = cherry_fetch(cR.rows, m2, ch2, t);
+        }
+#pragma unroll
+        for (int kk = 0; kk < (ch < 2 ? 2 : 1); ++kk) {
+            const int kt = 2 * ch + kk;
+            if (m == 0) extra(kt);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                if (KL != kSideTipK) dmma(accL[m][nt][0], accL[m][nt][1], kCL ? vL[kk] : aL[m].v[kt], fragL[nt][kt]);
+                if (KR != kSideTipK) dmma(accR[m][nt][0], accR[m][nt][1], kCR ? vR[kk] : aR[m].v[kt], fragR[nt][kt]);
+            }
+        }
+        vL[0] = nL[0];
+        vL[1] = nL[1];
+        vR[0] = nR[0];
+        vR[1] = nR[1];
+        if (PML_PRODUCTS_IN_TURN >= 1 && step == 3) {  // block 0 has long left the pipe
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                accL[0][nt][0] *= accR[0][nt][0];
+                accL[0][nt][1] *= accR[0][nt][1];
+            }
+            done |= 1;
+        }
+    }
+    if (PML_PRODUCTS_IN_TURN >= 2) {
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            accL[1][nt][0] *= accR[1][nt][0];
+            accL[1][nt][1] *= accR[1][nt][1];
+        }
+        done |= 2;
+    }
+    return done;
 }
 // D fragments (states nt*8 + 2t + {0,1}; nt = 2 only for t < 2) of one 8-row block back into the blocked layout
 __device__ __forceinline__ void store_d(double* block, int c, int lane, const double (&d)[3][2]) {

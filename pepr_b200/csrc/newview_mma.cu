@@ -304,15 +304,16 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         double accL[2][3][2], accR[2][3][2];
         AFrag aL[2], aR[2];
+        CherryIn cL{}, cR{};
+        if (kChL) cL = cherry_begin(s_tabL, s_tabL + kTableDoubles, aux + 128, aux + 144, g, c, t);
+        if (kChR) cR = cherry_begin(s_tabR, s_tabR + kTableDoubles, aux + 160, aux + 176, g, c, t);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             const int row = m * 8 + g;
             if (kTipL) lookup_rows(s_tabL, aux[128 + row], c, t, accL[m]);
-            else if (kChL) aL[m] = cherry_a(s_tabL, s_tabL + kTableDoubles, aux[128 + row], aux[144 + row], c, t);
-            else aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
+            else if (kInnerL) aL[m] = load_a(stage + m * kBlockDoubles, c, lane);
             if (kTipR) lookup_rows(s_tabR, aux[160 + row], c, t, accR[m]);
-            else if (kChR) aR[m] = cherry_a(s_tabR, s_tabR + kTableDoubles, aux[160 + row], aux[176 + row], c, t);
-            else aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
+            else if (kInnerR) aR[m] = load_a(stage + (kInnerL ? kTileDoubles : 0) + m * kBlockDoubles, c, lane);
         }
 #pragma unroll
         for (int m = 0; m < 2; ++m)
@@ -324,15 +325,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         // this group's turn on the FP64 tensor pipe; 12 (6) independent accumulator chains lie between two dependent MMAs
         mma_turn_begin(grp);
         long long tk2 = tr ? clock64() : 0;
-#pragma unroll
-        for (int kt = 0; kt < 5; ++kt)
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int nt = 0; nt < 3; ++nt) {
-                    if (!kTipL) dmma(accL[m][nt][0], accL[m][nt][1], aL[m].v[kt], fragL[nt][kt]);
-                    if (!kTipR) dmma(accR[m][nt][0], accR[m][nt][1], aR[m].v[kt], fragR[nt][kt]);
-                }
+        const int multiplied = children_mma<KL, KR>(aL, aR, cL, cR, fragL, fragR, accL, accR, t);
         long long tk3 = tr ? clock64() : 0;
         mma_turn_end(grp);
         __syncwarp();
@@ -346,8 +339,10 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             big[m] = 0;
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-                accL[m][nt][0] *= accR[m][nt][0];
-                accL[m][nt][1] *= accR[m][nt][1];
+                if (!(multiplied >> m & 1)) {
+                    accL[m][nt][0] *= accR[m][nt][0];
+                    accL[m][nt][1] *= accR[m][nt][1];
+                }
                 if (nt < 2 || t < 2) big[m] = max(big[m], max(__double2hiint(accL[m][nt][0]) & 0x7fffffff, __double2hiint(accL[m][nt][1]) & 0x7fffffff));
             }
             big[m] = max(big[m], __shfl_xor_sync(0xffffffffu, big[m], 1));
