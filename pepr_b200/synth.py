@@ -124,6 +124,49 @@ def simulate(ntax, nsites, seed, pmatrix, rates, pi, missing_frac=0.0, block=(20
     return names, [bytes(r).decode() for r in mat], nwk
 
 
+def simulate_wag_device(ntax, nsites, seed, device="cuda", alpha=1.0, mean_bl=0.08):
+    """The same model and the same kind of tree as simulate_wag, drawn on a CUDA device with torch (plumbing: 2000 taxa x 1 M
+    sites take seconds instead of a quarter of an hour on the host).  The random stream is torch's, so the alignment is NOT
+    the one simulate_wag gives for the same seed.  -> names, uint8 array [ntax, nsites] of residue letters, newick"""
+    import torch
+    m = WagModel(alpha)
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    ncat = len(m.rates)
+    # sites are laid out category by category while the states evolve; a fixed column permutation mixes them at the end
+    bounds = [nsites * k // ncat for k in range(ncat + 1)]
+    items = random_tree(ntax, rng)
+    rows = {}
+
+    def evolve(node, parent):
+        t = float(rng.exponential(mean_bl)) + 0.005
+        child = torch.empty(nsites, dtype=torch.uint8, device=device)
+        for k in range(ncat):
+            P = np.clip(m.pmatrix(t, m.rates[k]), 0, None)
+            P /= P.sum(1, keepdims=True)
+            cdf = torch.from_numpy(P.cumsum(1)).to(device)
+            lo, hi = bounds[k], bounds[k + 1]
+            u = torch.rand(hi - lo, generator=gen, dtype=torch.float64, device=device)
+            child[lo:hi] = (u[:, None] > cdf[parent[lo:hi].long()]).sum(1).clamp_(max=19).to(torch.uint8)
+        nm = node[0]
+        if isinstance(nm, str):
+            rows[nm] = child
+            return "%s:%.6f" % (nm, t)
+        return "(%s,%s):%.6f" % (evolve(nm[0], child), evolve(nm[1], child), t)
+
+    pi = torch.from_numpy(np.asarray(m.pi) / np.sum(m.pi)).to(device)
+    root = torch.multinomial(pi, nsites, replacement=True, generator=gen).to(torch.uint8)
+    nwk = "(" + ",".join(evolve(x, root) for x in items) + ");"
+    names = sorted(rows)
+    perm = torch.randperm(nsites, generator=gen, device=device)
+    letters = torch.from_numpy(np.frombuffer(AA.encode(), np.uint8).copy()).to(device)
+    out = np.empty((ntax, nsites), np.uint8)
+    for i, nme in enumerate(names):
+        out[i] = letters[rows.pop(nme)[perm].long()].cpu().numpy()
+    return names, out, nwk
+
+
 def write_phylip(path, names, seqs):
     """relaxed phylip as SequenceAlignment.getAlignmentAsExtendedPhylipUsingTaxonNames writes it
     (SequenceAlignment.java:489-522): 'ntax len', then name padded to longest+1 followed by the whole sequence."""
