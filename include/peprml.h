@@ -122,6 +122,21 @@ int pml_tree_stats(const pml_tree *, int64_t site_updates[3], int64_t *kernel_la
  * the smoothing pipeline drop the branch it had queued speculatively */
 int64_t pml_tree_nr_retries(const pml_tree *);
 
+/* ---- topological constraints (FastTreeRunner.java:53-83: `FastTree -constraints file`; encoder :243-273) -----------------------
+ * text = FastTree's constraint alignment (">name" + a row of 0 / 1 / - per taxon, one column per split; unlisted taxa are free).
+ * While set, pml_tree_start_parsimony grows its tree only through insertions that keep every split possible, and pml_search /
+ * pml_bootstrap_trees score only pruning-regrafting moves whose result displays every split.  NULL or "" clears.
+ * pml_constraints_from_tree writes the constraint alignment of a tree exactly as getFastTreeConstraintsForTree does (taxa
+ * sorted, one column per node); returns the bytes needed including the terminator. */
+int pml_aln_set_constraints(pml_aln *, const char *text);
+int pml_aln_num_constraints(const pml_aln *);      /* splits that can fail (two or more taxa on either side) */
+int pml_tree_satisfies_constraints(const pml_tree *); /* 1 / 0 */
+int64_t pml_constraints_from_tree(const char *newick, char *buf, size_t cap);
+/* host only (no device): the constrained stepwise-addition parsimony tree, and whether a tree displays every split */
+int64_t pml_parsimony_tree_constrained(int ntax, int64_t nsites, const char *const *names, const uint8_t *chars, int64_t seed,
+                                       const char *constraints, char *buf, size_t cap, int64_t *score);
+int pml_newick_satisfies_constraints(const char *newick, const char *const *names, int ntax, const char *constraints);
+
 /* ---- device-side timing of the engine's own kernels (CUDA events on the context's stream) -------------------
  * Between begin and end every launch of kind k is bracketed by a pair of events; end() synchronises and returns, per
  * kind, the summed device milliseconds, the launch count and the pattern rows processed.

@@ -265,6 +265,7 @@ struct pml_aln {
     // product table belongs to the tree that filled it last.
     uint64_t model_epoch = 0;
     const pml_tree* sumtable_owner = nullptr;
+    Constraints constraints;  // pml_aln_set_constraints: splits every tree built or searched on this alignment must display
 };
 
 struct pml_tree {
@@ -1015,7 +1016,18 @@ bool spr_round(pml_tree* t, const int32_t* dw, int radius, double& best, SearchS
     for (int p = T.ntax; p < T.nnodes(); ++p) {
         for (int k = 0; k < 3; ++k) {
             const int s = T.nbr[p][k];
-            const std::vector<int> targets = spr_targets(T, p, s, radius);
+            std::vector<int> targets = spr_targets(T, p, s, radius);
+            if (!t->aln->constraints.empty()) {  // topological constraints: only moves that keep every split (FastTree -constraints)
+                std::vector<int> kept;
+                for (int target : targets) {
+                    Topology trial = T;
+                    ViewState scratch;
+                    scratch.reset(trial);
+                    SprMove mv;
+                    if (spr_apply(trial, scratch, p, s, target, mv) && satisfies(trial, t->aln->constraints)) kept.push_back(target);
+                }
+                targets.swap(kept);
+            }
             if (targets.empty()) continue;
             int best_target = -1;
             double best_lazy = -1e300;
@@ -1777,7 +1789,7 @@ int pml_tree_start_parsimony(pml_aln* a, int64_t seed, const int32_t* weights, p
         return true;
     };
     Topology topo;
-    ok = ok && parsimony_start_tree(a->pat, seed, kDefaultLen, topo, nullptr, &scan);
+    ok = ok && parsimony_start_tree(a->pat, seed, kDefaultLen, topo, nullptr, &scan, &a->constraints);
     c->sync();
     c->dev_free(d_down);
     c->dev_free(d_up);
@@ -1802,6 +1814,33 @@ int64_t pml_parsimony_tree(int ntax, int64_t nsites, const char* const* names, c
     const std::string s = write_newick_result(topo, pat.names);
     if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
     return (int64_t)s.size() + 1;
+}
+
+int64_t pml_parsimony_tree_constrained(int ntax, int64_t nsites, const char* const* names, const uint8_t* chars, int64_t seed,
+                                       const char* constraints, char* buf, size_t cap, int64_t* score) {
+    if (ntax < 3 || nsites < 1 || !names || !chars) return PML_EINVAL;
+    Patterns pat;
+    crunch_patterns(ntax, nsites, chars, nullptr, pat);
+    for (int i = 0; i < ntax; ++i) pat.names.emplace_back(names[i]);
+    Constraints cons;
+    std::string err;
+    if (constraints && *constraints && !parse_constraints(constraints, pat.names, cons, err)) return fail(nullptr, PML_EINVAL, err);
+    Topology topo;
+    if (!parsimony_start_tree(pat, seed, kDefaultLen, topo, score, nullptr, &cons) || topo.ntax != ntax)
+        return fail(nullptr, PML_EINVAL, "parsimony start tree failed (contradictory constraints?)");
+    const std::string s = write_newick_result(topo, pat.names);
+    if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size() + 1;
+}
+
+int pml_newick_satisfies_constraints(const char* newick, const char* const* names, int ntax, const char* constraints) {
+    if (!newick || !names || ntax < 3 || !constraints) return PML_EINVAL;
+    std::vector<std::string> nm(names, names + ntax);
+    Topology topo;
+    Constraints cons;
+    std::string err;
+    if (!parse_newick(newick, nm, kDefaultLen, topo, err) || !parse_constraints(constraints, nm, cons, err)) return fail(nullptr, PML_EINVAL, err);
+    return satisfies(topo, cons) ? 1 : 0;
 }
 
 int pml_tree_spr(pml_tree* t, int node, int keep, int target) {
@@ -1857,6 +1896,8 @@ int pml_search(pml_tree* t, int radius, int max_rounds, double eps, const int32_
     if (!(eps > 0.0)) eps = 0.1;
     const int32_t* dw = device_weights(t->aln, weights);
     if (!dw) return PML_ENODEVICE;
+    if (!satisfies(t->topo, t->aln->constraints))
+        return fail(c, PML_ESTATE, "pml_search: the tree does not display the alignment's topological constraints (start from pml_tree_start_parsimony)");
     double best;
     if (!lnl_at(t, t->topo.edge[0][0], dw, best)) return c->fail_code();
     SearchStats st;
@@ -1873,6 +1914,35 @@ int pml_search(pml_tree* t, int radius, int max_rounds, double eps, const int32_
     if (lnl) *lnl = best;
     if (accepted_moves) *accepted_moves = st.accepted;
     return PML_OK;
+}
+
+int pml_aln_set_constraints(pml_aln* a, const char* text) {
+    if (!a) return PML_EINVAL;
+    if (!text || !*text) {
+        a->constraints = Constraints();
+        return PML_OK;
+    }
+    std::string err;
+    Constraints parsed;
+    if (!parse_constraints(text, a->pat.names, parsed, err)) return fail(a->ctx, PML_EINVAL, err);
+    a->constraints = std::move(parsed);
+    return PML_OK;
+}
+
+int pml_aln_num_constraints(const pml_aln* a) { return a ? (int)a->constraints.splits.size() : PML_EINVAL; }
+
+int pml_tree_satisfies_constraints(const pml_tree* t) {
+    if (!t) return PML_EINVAL;
+    return satisfies(t->topo, t->aln->constraints) ? 1 : 0;
+}
+
+int64_t pml_constraints_from_tree(const char* newick, char* buf, size_t cap) {
+    if (!newick) return PML_EINVAL;
+    std::string err;
+    const std::string s = constraints_from_tree(newick, err);
+    if (s.empty()) return fail(nullptr, PML_EINVAL, err);
+    if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int64_t)s.size() + 1;
 }
 
 int pml_bootstrap_weights(const pml_aln* a, int64_t* seed, int nrep, int32_t* out) {

@@ -997,7 +997,7 @@ struct HostParsimony {
 }  // namespace
 
 bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score_out,
-                          const ParsimonyScan* scan) {
+                          const ParsimonyScan* scan, const Constraints* constraints) {
     const int n = pat.ntax;
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
@@ -1042,14 +1042,19 @@ bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len,
         }
         if (!(*scan)(g, pre, k < n ? order[k] : -1, total_score, cost)) return false;
         if (k == n) break;
-        // cheapest branch (above node v) for the next taxon; the first one in `pre` wins a tie
+        // cheapest branch (above node v) for the next taxon; the first one in `pre` wins a tie.  Under topological constraints
+        // only the branches that keep every split possible among the taxa present are candidates (there always is one as long
+        // as the splits are compatible with each other)
+        std::vector<char> allowed;
+        if (constraints && !constraints->empty()) allowed = allowed_insertions(g, pre, order[k], *constraints);
         int best_v = -1;
         int64_t best_cost = 0;
         for (size_t i = 0; i < pre.size(); ++i)
-            if (best_v < 0 || cost[i] < best_cost) {
+            if ((allowed.empty() || allowed[i]) && (best_v < 0 || cost[i] < best_cost)) {
                 best_v = pre[i];
                 best_cost = cost[i];
             }
+        if (best_v < 0) return false;  // contradictory constraints
         // insert a new inner node above best_v
         const int w = g.add_node(-1), x = g.add_node(order[k]);
         const int par = g.parent[best_v];
@@ -1071,6 +1076,183 @@ bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len,
     else text = "(" + pat.names[g.taxon[root]] + "," + nw(t0) + ");";
     std::string err;
     return parse_newick(text, pat.names, default_len, out, err);
+}
+
+// =========================================================================================== constraints ====
+namespace {
+inline bool bit(const std::vector<uint64_t>& b, int i) { return (b[(size_t)i >> 6] >> (i & 63)) & 1ull; }
+inline void set_bit(std::vector<uint64_t>& b, int i) { b[(size_t)i >> 6] |= 1ull << (i & 63); }
+inline bool subset(const std::vector<uint64_t>& a, const std::vector<uint64_t>& of) {
+    for (size_t w = 0; w < a.size(); ++w)
+        if (a[w] & ~of[w]) return false;
+    return true;
+}
+inline bool disjoint(const std::vector<uint64_t>& a, const std::vector<uint64_t>& b) {
+    for (size_t w = 0; w < a.size(); ++w)
+        if (a[w] & b[w]) return false;
+    return true;
+}
+inline int count_bits(const std::vector<uint64_t>& a) {
+    int c = 0;
+    for (uint64_t w : a) c += __builtin_popcountll(w);
+    return c;
+}
+}  // namespace
+
+bool parse_constraints(const std::string& text, const std::vector<std::string>& names, Constraints& out, std::string& err) {
+    out = Constraints();
+    out.ntax = (int)names.size();
+    const size_t words = ((size_t)out.ntax + 63) / 64;
+    std::unordered_map<std::string, int> index;
+    for (int i = 0; i < out.ntax; ++i) index[names[i]] = i;
+    std::vector<std::pair<int, std::string>> rows;
+    std::istringstream in(text);
+    std::string line;
+    int cur = -1;
+    while (std::getline(in, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            std::string nm = line.substr(1);
+            const size_t sp = nm.find_first_of(" \t");
+            if (sp != std::string::npos) nm.resize(sp);
+            auto it = index.find(nm);
+            if (it == index.end()) {
+                err = "constraints name a taxon that is not in the alignment: " + nm;
+                return false;
+            }
+            cur = it->second;
+            rows.push_back({cur, std::string()});
+        } else if (cur >= 0) rows.back().second += line;
+    }
+    size_t ncol = 0;
+    for (auto& r : rows) ncol = std::max(ncol, r.second.size());
+    for (size_t col = 0; col < ncol; ++col) {
+        SplitConstraint sc{std::vector<uint64_t>(words, 0), std::vector<uint64_t>(words, 0)};
+        for (auto& r : rows) {
+            const char ch = col < r.second.size() ? r.second[col] : '-';
+            if (ch == '1') set_bit(sc.one, r.first);
+            else if (ch == '0') set_bit(sc.zero, r.first);
+        }
+        if (count_bits(sc.one) >= 2 && count_bits(sc.zero) >= 2) out.splits.push_back(std::move(sc));  // the others hold in every tree
+    }
+    return true;
+}
+
+std::string constraints_from_tree(const std::string& newick, std::string& err) {
+    RawTree t;
+    if (!parse_raw(newick, t, err)) return "";
+    std::vector<std::string> taxa;
+    for (const RawNode& n : t.nodes)
+        if (n.kids.empty() && !n.label.empty()) taxa.push_back(n.label);
+    std::sort(taxa.begin(), taxa.end());
+    const int ntax = (int)taxa.size(), nnodes = (int)t.nodes.size();
+    // leaf set of every node (node ids are in preorder: children after parents)
+    std::vector<std::vector<char>> has((size_t)nnodes, std::vector<char>((size_t)ntax, 0));
+    for (int v = nnodes - 1; v >= 0; --v) {
+        const RawNode& n = t.nodes[v];
+        if (n.kids.empty() && !n.label.empty()) has[v][std::lower_bound(taxa.begin(), taxa.end(), n.label) - taxa.begin()] = 1;
+        for (int k : n.kids)
+            for (int i = 0; i < ntax; ++i) has[v][i] |= has[k][i];
+    }
+    std::string out;
+    for (int i = 0; i < ntax; ++i) {
+        out += ">" + taxa[i] + "\n";
+        for (int v = 0; v < nnodes; ++v) out += has[v][i] ? '1' : '0';
+        out += "\n";
+    }
+    return out;
+}
+
+bool satisfies(const Topology& T, const Constraints& C) {
+    if (C.empty()) return true;
+    const size_t words = ((size_t)T.ntax + 63) / 64;
+    // taxa behind every branch, seen from taxon 0 (depth-first from its neighbour; children before parents on the way back)
+    std::vector<std::vector<uint64_t>> below;  // one set per directed edge away from taxon 0, in completion order
+    std::vector<std::vector<uint64_t>> at((size_t)T.nnodes(), std::vector<uint64_t>(words, 0));
+    struct Item { int v, from; bool done; };
+    std::vector<Item> stack{{T.nbr[0][0], 0, false}};
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        if (T.is_tip(it.v)) {
+            set_bit(at[it.v], it.v);
+            below.push_back(at[it.v]);
+            continue;
+        }
+        if (!it.done) {
+            stack.push_back({it.v, it.from, true});
+            for (int s = 0; s < 3; ++s)
+                if (T.nbr[it.v][s] != it.from && T.nbr[it.v][s] >= 0) stack.push_back({T.nbr[it.v][s], it.v, false});
+        } else {
+            for (int s = 0; s < 3; ++s) {
+                const int nb = T.nbr[it.v][s];
+                if (nb == it.from || nb < 0) continue;
+                for (size_t w = 0; w < words; ++w) at[it.v][w] |= at[nb][w];
+            }
+            below.push_back(at[it.v]);
+        }
+    }
+    for (const SplitConstraint& sc : C.splits) {
+        bool ok = false;
+        for (const auto& S : below) {
+            if ((subset(sc.one, S) && disjoint(sc.zero, S)) || (subset(sc.zero, S) && disjoint(sc.one, S))) {
+                ok = true;
+                break;
+            }
+        }
+        if (!ok) return false;
+    }
+    return true;
+}
+
+std::vector<char> allowed_insertions(const GrowTree& g, const std::vector<int>& pre, int next_taxon, const Constraints& C) {
+    const int N = (int)g.parent.size();
+    const size_t words = ((size_t)C.ntax + 63) / 64;
+    std::vector<char> allowed(pre.size(), 1);
+    // taxa below every node (the root tip, node 0, is above everything and belongs to no set); `pre` lists parents first
+    std::vector<std::vector<uint64_t>> desc((size_t)N, std::vector<uint64_t>(words, 0));
+    std::vector<uint64_t> present(words, 0);
+    set_bit(present, g.taxon[0]);
+    for (size_t i = pre.size(); i-- > 0;) {
+        const int v = pre[i];
+        if (g.left[v] < 0) {
+            set_bit(desc[v], g.taxon[v]);
+            set_bit(present, g.taxon[v]);
+        } else
+            for (size_t w = 0; w < words; ++w) desc[v][w] = desc[g.left[v]][w] | desc[g.right[v]][w];
+    }
+    std::vector<int> anc_b((size_t)N, 0);
+    std::vector<char> anc_a((size_t)N, 0), wit_a((size_t)N, 0), wit_b((size_t)N, 0);
+    for (const SplitConstraint& sc : C.splits) {
+        const bool in_one = bit(sc.one, next_taxon), in_zero = bit(sc.zero, next_taxon);
+        if (!in_one && !in_zero) continue;  // the new taxon is free in this split: nothing it does can break it
+        // A = the side the new taxon belongs to, B = the other side, both restricted to the taxa already in the tree
+        std::vector<uint64_t> A(words), B(words);
+        for (size_t w = 0; w < words; ++w) {
+            A[w] = (in_one ? sc.one[w] : sc.zero[w]) & present[w];
+            B[w] = (in_one ? sc.zero[w] : sc.one[w]) & present[w];
+        }
+        if (count_bits(A) == 0 || count_bits(B) == 0) continue;  // first of its side, or nobody to be separated from
+        // witnesses of the split in the current tree: nodes holding all of A and none of B (they must take the new taxon in),
+        // nodes holding all of B and none of A (they must not)
+        int total_b = 0;
+        for (int v : pre) {
+            wit_a[v] = subset(A, desc[v]) && disjoint(B, desc[v]);
+            wit_b[v] = subset(B, desc[v]) && disjoint(A, desc[v]);
+            total_b += wit_b[v];
+        }
+        for (size_t i = 0; i < pre.size(); ++i) {  // parents first: what the strict ancestors offer
+            const int v = pre[i], par = g.parent[v];
+            const bool has_par = par > 0;  // node 0 is the root tip
+            anc_a[v] = has_par && (anc_a[par] || wit_a[par]);
+            anc_b[v] = has_par ? anc_b[par] + wit_b[par] : 0;
+            // attached above v the new taxon joins v's set (in the new node) and every ancestor's
+            const bool ok = wit_a[v] || anc_a[v] || (total_b - anc_b[v]) > 0;
+            if (!ok) allowed[i] = 0;
+        }
+    }
+    return allowed;
 }
 
 }  // namespace pml

@@ -152,8 +152,31 @@ struct GrowTree {
 // score of the current tree and, when next_taxon >= 0, cost[i] = weighted number of patterns that gain a change if
 // next_taxon is attached to the branch above pre[i].  The engine supplies a GPU implementation (csrc/parsimony.cu).
 using ParsimonyScan = std::function<bool(const GrowTree& g, const std::vector<int>& pre, int next_taxon, int64_t& score, std::vector<int64_t>& cost)>;
+
+// ---- topological constraints (FastTree -constraints, FastTreeRunner.java:53-83, 243-273) --------------------------------------
+// A constraint is a split of (some of) the taxa: the tree must have a branch with all `one` taxa on one side and all `zero`
+// taxa on the other; taxa in neither set are free.  Bits are taxon indices of the alignment.
+struct SplitConstraint {
+    std::vector<uint64_t> one, zero;
+};
+struct Constraints {
+    int ntax = 0;
+    std::vector<SplitConstraint> splits;   // only splits that can fail (two or more taxa on either side)
+    bool empty() const { return splits.empty(); }
+};
+// FastTree's constraint alignment: ">name" lines followed by a row of 0 / 1 / - (one column per split); names must be taxa of the
+// alignment, taxa that are not listed are unconstrained
+bool parse_constraints(const std::string& text, const std::vector<std::string>& names, Constraints& out, std::string& err);
+// the constraint alignment of a tree as FastTreeRunner.getFastTreeConstraintsForTree writes it: taxa sorted, one column per
+// node of the tree (1 = the taxon descends from that node)
+std::string constraints_from_tree(const std::string& newick, std::string& err);
+bool satisfies(const Topology& T, const Constraints& C);
+// stepwise addition: may next_taxon be attached to the branch above pre[i] without making a split impossible among the taxa
+// present afterwards?
+std::vector<char> allowed_insertions(const GrowTree& g, const std::vector<int>& pre, int next_taxon, const Constraints& C);
+
 bool parsimony_start_tree(const Patterns& pat, int64_t seed, double default_len, Topology& out, int64_t* score,
-                          const ParsimonyScan* scan = nullptr);
+                          const ParsimonyScan* scan = nullptr, const Constraints* constraints = nullptr);
 inline uint32_t parsimony_code_mask(int code) {
     if (code < 20) return 1u << code;
     if (code == 20) return (1u << 2) | (1u << 3);

@@ -93,6 +93,15 @@ def lib():
         L.pml_timer_start.argtypes = [C.c_void_p]
         L.pml_timer_stop.argtypes = [C.c_void_p, c_f64p]
         L.pml_profile_end.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pml_aln_set_constraints.argtypes = [C.c_void_p, C.c_char_p]
+        L.pml_aln_num_constraints.argtypes = [C.c_void_p]
+        L.pml_tree_satisfies_constraints.argtypes = [C.c_void_p]
+        L.pml_constraints_from_tree.restype = C.c_int64
+        L.pml_constraints_from_tree.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        L.pml_parsimony_tree_constrained.restype = C.c_int64
+        L.pml_parsimony_tree_constrained.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_int64, C.c_char_p, C.c_char_p,
+                                                     C.c_size_t, c_i64p]
+        L.pml_newick_satisfies_constraints.argtypes = [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p]
         L.pml_kind_info.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.pml_bootstrap_weights_host.argtypes = [C.c_void_p, C.c_int64, c_i64p, C.c_int, C.c_void_p]
         L.pml_crunch_patterns.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]
@@ -274,6 +283,11 @@ class Alignment:
         trees = [t for t in buf.value.decode().split("\n") if t]
         return list(zip(ids, trees)), lnl[:nrep], secs[:nrep]
 
+    def set_constraints(self, text):
+        """FastTree constraint alignment (None clears): every tree grown or searched on this alignment must display its splits"""
+        self.ctx.check(lib().pml_aln_set_constraints(self.h, text.encode() if text else None), "pml_aln_set_constraints")
+        return lib().pml_aln_num_constraints(self.h)
+
     def close(self):
         if self.h:
             lib().pml_aln_free(self.h)
@@ -374,6 +388,9 @@ class Tree:
         self.ctx.check(lib().pml_evaluate_replicates(self.h, _ptr(W), W.shape[0], _ptr(out)), "pml_evaluate_replicates")
         return out
 
+    def satisfies_constraints(self):
+        return bool(lib().pml_tree_satisfies_constraints(self.h))
+
     def newick(self):
         n = lib().pml_tree_newick(self.h, None, 0)
         buf = C.create_string_buffer(n)
@@ -387,6 +404,16 @@ class Tree:
 
 
 # ---- host-only entry points (no GPU needed) ----------------------------------------------------------------
+def constraints_from_tree(newick):
+    """FastTreeRunner.getFastTreeConstraintsForTree (FastTreeRunner.java:243-273): the constraint alignment of a tree"""
+    n = lib().pml_constraints_from_tree(newick.encode(), None, 0)
+    if n < 0:
+        raise EngineError("pml_constraints_from_tree failed: %s" % lib().pml_last_error(None).decode())
+    buf = C.create_string_buffer(int(n))
+    lib().pml_constraints_from_tree(newick.encode(), buf, n)
+    return buf.value.decode()
+
+
 def wag_pmatrix(t, rate=1.0):
     P = np.zeros((20, 20))
     lib().pml_wag_pmatrix(t, rate, _ptr(P))
@@ -454,6 +481,29 @@ def parsimony_tree(names, seqs, seed=12345):
     buf = C.create_string_buffer(n)
     lib().pml_parsimony_tree(chars.shape[0], C.c_int64(chars.shape[1]), arr, _ptr(chars), C.c_int64(seed), buf, n, C.byref(score))
     return buf.value.decode(), score.value
+
+
+def parsimony_tree_constrained(names, seqs, constraints, seed=12345):
+    """host-only: the stepwise-addition parsimony tree grown through constraint-preserving insertions only"""
+    chars = seqs if isinstance(seqs, np.ndarray) else np.stack([np.frombuffer(s.encode(), np.uint8) for s in seqs])
+    chars = np.ascontiguousarray(chars, np.uint8)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    score = C.c_int64()
+    args = (chars.shape[0], C.c_int64(chars.shape[1]), arr, _ptr(chars), C.c_int64(seed), constraints.encode() if constraints else None)
+    n = lib().pml_parsimony_tree_constrained(*args, None, 0, C.byref(score))
+    if n < 0:
+        raise EngineError("pml_parsimony_tree_constrained: " + lib().pml_last_error(None).decode())
+    buf = C.create_string_buffer(n)
+    lib().pml_parsimony_tree_constrained(*args, buf, n, C.byref(score))
+    return buf.value.decode(), score.value
+
+
+def newick_satisfies_constraints(newick, names, constraints):
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    rc = lib().pml_newick_satisfies_constraints(newick.encode(), arr, len(names), constraints.encode())
+    if rc < 0:
+        raise EngineError("pml_newick_satisfies_constraints: " + lib().pml_last_error(None).decode())
+    return bool(rc)
 
 
 def support_tree(main_newick, trees, as_percent=False):

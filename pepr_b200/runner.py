@@ -73,6 +73,8 @@ class B200MLRunner:
         self._lnl = None
         self._alpha = None
         self.tree_options = ""                  # what PEPRTracker.setTreeOptions would receive
+        self.constraints = None                 # FastTree constraint alignment (B200FastTreeRunner passes it on)
+        self.site_weights = None                # integer column weights (raxmlHPC -a): gene-wise jackknife masks use them
 
     # ---- configuration (RAxMLRunner setters) ------------------------------------------------------------------
     def setAlignment(self, alignment):
@@ -115,9 +117,18 @@ class B200MLRunner:
         if self.strict:
             raise _e.EngineError(msg)
 
+    def setSiteWeights(self, weights):
+        """integer weight per alignment column (raxmlHPC `-a weightFile`); None = every column once.  A gene-wise jackknife
+        replicate is the 0 / 1 mask of the genes it keeps (gene_block_weights) over ONE resident supermatrix instead of a new
+        concatenated alignment per replicate"""
+        self.site_weights = None if weights is None else np.ascontiguousarray(weights, np.int32)
+
     def _load(self):
         a = self.alignment
-        return _e.Alignment(self.ctx, a.names, a.seqs, alpha=1.0, model=self.matrix)
+        aln = _e.Alignment(self.ctx, a.names, a.seqs, alpha=1.0, model=self.matrix, site_weights=self.site_weights)
+        if self.constraints:
+            aln.set_constraints(self.constraints)
+        return aln
 
     def _optimise(self, aln, newick):
         tree = _e.Tree(aln, newick)
@@ -287,7 +298,10 @@ class B200FastTreeRunner:
     (getRaxmlBranchLengths, :142-199).  Here the tree comes from the engine's own ML search (parsimony start tree, lazy
     SPR, WAG+G4 branch lengths -- so it always carries `-f e` quality lengths), supports are replicate percentages.
     FastTree's CAT/ME heuristics are not reproduced: trees are compared by their splits (tests/test_gpu_search.py).
-    Refused loudly, not ignored: topological constraints (`-constraints`) and nucleotide alignments (`-gtr -nt`)."""
+    Topological constraints (`-constraints file`, FastTreeRunner.java:53-83) are honoured: setConstraints takes FastTree's
+    constraint alignment, setConstraintTree a tree (encoded exactly as getFastTreeConstraintsForTree does, :243-273); the start
+    tree grows through constraint-preserving insertions only and the search scores only moves that keep every split.
+    Refused loudly, not ignored: nucleotide alignments (`-gtr -nt`)."""
 
     def __init__(self, gpu=0, ctx=None, strict=False):
         self._ml = B200MLRunner(gpu=gpu, ctx=ctx, strict=strict)
@@ -300,6 +314,11 @@ class B200FastTreeRunner:
 
     def setConstraints(self, constraints):
         self.constraints = constraints
+
+    def setConstraintTree(self, tree_string):
+        """FastTreeRunner.setConstraintTree (FastTreeRunner.java:224-229)"""
+        if tree_string is not None:
+            self.setConstraints(_e.constraints_from_tree(tree_string))
 
     def setBootstrapReps(self, n):
         self.bootstrap_reps = int(n)
@@ -315,21 +334,23 @@ class B200FastTreeRunner:
 
     def run(self):
         self.result, self.last_error = None, None
-        if self.constraints is not None or self.nucleotide:
-            self.last_error = "B200FastTreeRunner: constraints / nucleotide alignments are not supported by the engine"
+        if self.nucleotide:
+            self.last_error = "B200FastTreeRunner: nucleotide alignments are not supported by the engine"
             logger.error(self.last_error)
             if self.strict:
                 raise _e.EngineError(self.last_error)
             return
         self._ml.setAlignment(self.alignment)
         self._ml.setBootstrapReps(self.bootstrap_reps)
+        self._ml.constraints = self.constraints
         self._ml.algorithm = ML_ALGORITHM
         self._ml.start_tree = None
         self._ml.run()
         if self._ml.last_error is not None:
             self.last_error = self._ml.last_error   # reference convention: logged, result stays null
             return
-        self.tree_options = "peprml search -m PROTGAMMAWAG" + ("" if self.bootstrap_reps else " -nosupport")
+        self.tree_options = "peprml search -m PROTGAMMAWAG" + ("" if self.bootstrap_reps else " -nosupport") + (
+            " -constraints <%d columns>" % len(self.constraints.split("\n")[1]) if self.constraints else "")
         self.result = self._ml.getBestTreeWithSupports() if self.bootstrap_reps > 0 else self._ml.getBestTree()
 
     def getResult(self):
@@ -340,6 +361,185 @@ class B200FastTreeRunner:
 
     def close(self):
         self._ml.close()
+
+
+# tree-building methods of PhylogeneticTreeBuilder (HandyConstants.java:36-68)
+MAXIMUM_LIKELIHOOD, PARSIMONY, PARSIMONY_BL, FAST_TREE, NEIGHBOR_JOINING, MR_BAYES = "ml", "parsimony", "parsimony_bl", "FastTree", "nj", "mb"
+
+
+class B200TreeBuilder:
+    """drop-in for PhylogeneticTreeBuilder on the likelihood path (PhylogeneticTreeBuilder.java:97-129 run and the four build*
+    methods :137-196): the method dispatch PEPR's pipeline talks to, with the engine's runners behind it.
+      ml            -> B200MLRunner.run: getBestTree, or getBestTreeWithSupports when bootstrapReps > 0   (buildRaxmlTree)
+      parsimony     -> setParsimonyOnly, getParsimonyTree                                                (buildRaxmlParsimonyTree)
+      parsimony_bl  -> setParsimonyWithBL, getParsimonyWithBLTree                                        (buildRaxmlParsimonyTreeWithBL)
+      FastTree      -> B200FastTreeRunner with constraint tree, bootstrap reps, raxml branch lengths     (buildFastTree)
+    Neighbour joining and MrBayes are not on the accelerated path: run() records that in last_error and leaves the tree
+    string None, which is what the reference's callers see when a tool fails (ExecUtilities.java:29-35)."""
+
+    def __init__(self, gpu=0, ctx=None, strict=False):
+        self._gpu, self._ctx, self.strict = gpu, ctx, strict
+        self.alignment, self.tree_building_method, self.ml_matrix = None, MR_BAYES, "PROTGAMMAWAG"
+        self.processes, self.bootstrap_reps = 1, 100          # PhylogeneticTreeBuilder.java:51-52
+        self.use_raxml_branch_lengths, self.nucleotide, self.use_taxon_names = False, False, True
+        self.constraint_tree, self.run_name, self.tree_string, self.last_error = None, None, None, None
+        self.runner = None
+
+    def setAlignment(self, alignment):
+        self.alignment = alignment
+
+    def getAlignment(self):
+        return self.alignment
+
+    def setTreeBuildingMethod(self, method):
+        self.tree_building_method = method
+
+    def setProcesses(self, n):
+        self.processes = int(n)
+
+    def setBootstrapReps(self, n):
+        self.bootstrap_reps = int(n)
+
+    def getBootstrapReps(self):
+        return self.bootstrap_reps
+
+    def setMLMatrix(self, m):
+        self.ml_matrix = m
+
+    def setConstraintTree(self, tree_string):
+        self.constraint_tree = tree_string
+
+    def setRunName(self, name):
+        self.run_name = name
+
+    def getRunName(self):
+        return self.run_name
+
+    def useRaxmlBranchLengths(self, flag):
+        self.use_raxml_branch_lengths = bool(flag)
+
+    def setNucleotide(self, flag):
+        self.nucleotide = bool(flag)
+
+    def getTreeString(self):
+        return self.tree_string
+
+    def setTreeString(self, s):
+        self.tree_string = s
+
+    def run(self):
+        self.tree_string, self.last_error = None, None
+        m = self.tree_building_method
+        if m in (MAXIMUM_LIKELIHOOD, PARSIMONY, PARSIMONY_BL):
+            r = self.runner = B200MLRunner(self.processes, gpu=self._gpu, ctx=self._ctx, strict=self.strict)
+            try:
+                r.setBootstrapReps(self.bootstrap_reps)
+                r.setAlignment(self.alignment)
+                if m == MAXIMUM_LIKELIHOOD:
+                    r.setMatrix(self.ml_matrix)
+                elif m == PARSIMONY:
+                    r.setParsimonyOnly(True)
+                else:
+                    r.setParsimonyWithBL(True)
+                r.run()
+                self.last_error = r.last_error
+                if r.last_error is None:
+                    if m == MAXIMUM_LIKELIHOOD:
+                        self.tree_string = r.getBestTree() if self.bootstrap_reps == 0 else r.getBestTreeWithSupports()
+                    elif m == PARSIMONY:
+                        self.tree_string = r.getParsimonyTree()
+                    else:
+                        self.tree_string = r.getParsimonyWithBLTree()
+            finally:
+                r.close()
+        elif m == FAST_TREE:
+            f = self.runner = B200FastTreeRunner(gpu=self._gpu, ctx=self._ctx, strict=self.strict)
+            try:
+                f.setNucleotide(self.nucleotide)
+                f.setAlignment(self.alignment)
+                f.setBootstrapReps(self.bootstrap_reps)
+                f.setUseRaxmlBranchLengths(self.use_raxml_branch_lengths)
+                if self.constraint_tree is not None:
+                    f.setConstraintTree(self.constraint_tree)
+                f.run()
+                self.last_error, self.tree_string = f.last_error, f.getResult()
+            finally:
+                f.close()
+        else:
+            self.last_error = "B200TreeBuilder: method '%s' is not on the accelerated path (ml, parsimony, parsimony_bl, FastTree)" % m
+            logger.error(self.last_error)
+            if self.strict:
+                raise _e.EngineError(self.last_error)
+
+
+def gene_block_weights(block_lengths, keep, multiplicity=None):
+    """Site weights of a gene-wise jackknife / bootstrap replicate over ONE concatenated alignment: the
+    supermatrix of MSAConcatenator.concatenate (MSAConcatenator.java:78-189) lays the genes out one block after another;
+    instead of concatenating half of the genes afresh for every support tree (PhylogenomicPipeline2.java:1227-1275) the
+    replicate is the weight 1 on the columns of the genes in `keep` and 0 elsewhere (`multiplicity[g]` instead of 1 for a
+    gene drawn several times).  -> int32 weight per column, for B200MLRunner.setSiteWeights / Alignment(site_weights=...)"""
+    block_lengths = np.asarray(block_lengths, np.int64)
+    w_gene = np.zeros(len(block_lengths), np.int32)
+    for g in keep:
+        w_gene[g] += 1 if multiplicity is None else int(multiplicity[g])
+    return np.repeat(w_gene, block_lengths).astype(np.int32)
+
+
+class JavaRandom:
+    """java.util.Random (48-bit LCG), so that a seeded run draws the very sets the Java code would"""
+
+    def __init__(self, seed):
+        self.seed = (int(seed) ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def _next(self, bits):
+        self.seed = (self.seed * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        v = self.seed >> (48 - bits)
+        return v - (1 << 32) if v >= (1 << 31) else v               # (int) cast of the Java original
+
+    def nextIntAll(self):
+        """Random.nextInt() without a bound"""
+        return self._next(32)
+
+    def nextInt(self, bound):
+        if bound <= 0:
+            raise ValueError("bound must be positive")
+        if bound & (bound - 1) == 0:
+            return (bound * self._next(31)) >> 31
+        while True:
+            bits = self._next(31)
+            val = bits % bound
+            if bits - val + (bound - 1) < (1 << 31):
+                return val
+
+
+def getRandomSet(length, min_value, max_value, allow_reuse, seed=None):
+    """RandomSetUtils.getRandomSet (RandomSetUtils.java:9-35) with the seed the reference lacks (`new Random()` there makes
+    every PEPR run draw different jackknife gene sets): same rejection loop over a java.util.Random stream; seed None draws a
+    seed from the OS as the reference does.  -> list of ints, or None where the reference returns null"""
+    rng_range = max_value - min_value + 1
+    if not (allow_reuse or rng_range >= length):
+        return None
+    if seed is None:
+        import os
+        seed = int.from_bytes(os.urandom(6), "little")
+    rnd = seed if isinstance(seed, JavaRandom) else JavaRandom(seed)
+    used, out = [False] * rng_range, []
+    for _ in range(length):
+        pos = rnd.nextInt(rng_range)
+        while not allow_reuse and used[pos]:
+            pos = rnd.nextInt(rng_range)
+        used[pos] = True
+        out.append(min_value + pos)
+    return out
+
+
+def support_threads_for_memory(ntax, npatterns, free_bytes, requested):
+    """The RAM throttle of buildConcatenatedTreeWithGeneWiseJackKnifeSupport (PhylogenomicPipeline2.java:1011-1036: `100 L N +
+    2000 L` bytes per FastTree thread against the JVM's free RAM) restated for the engine: a replicate tree needs its own CLV
+    arena of (ntax - 2) x patterns x 640 B (+ 4 B scaling counts and 8 B of parsimony scratch per node and pattern) in HBM, so
+    that many replicate trees fit on one GPU side by side.  -> min(requested, what fits), at least 1 as in the reference"""
+    per_tree = (ntax - 2) * npatterns * 644 + 2 * ntax * npatterns * 8 + ntax * npatterns
+    return max(1, min(int(requested), int(free_bytes // max(per_tree, 1))))
 
 
 class TreeSupportDecorator:

@@ -137,6 +137,103 @@ def test_fasttree_runner_mirror_gives_fasttrees_tree(gpu_ctx, golden):
     r.run()
     labels = [int(x) for x in re.findall(r"\)(\d+)", r.getResult())]
     assert len(labels) == len(g.names) - 3 and all(0 <= v <= 100 for v in labels)
-    r.setConstraints("((T0000,T0001),T0002);")
+    r.setNucleotide(True)
     r.run()
     assert r.getResult() is None and "not supported" in r.last_error
+
+
+def test_fasttree_runner_honours_topological_constraints(gpu_ctx, golden):
+    """`FastTree -constraints` (FastTreeRunner.java:53-83): a constraint tree that contradicts the data's own tree must come out
+    displayed -- at a likelihood cost; the unconstrained part of the tree is still the search's; a constraint tree that agrees
+    with the data changes nothing"""
+    g = golden("search")
+    names = g.names
+    free = _splits(g.meta["fd"]["tree"])
+    # a wrong clade: three taxa that do not form one in the ML tree
+    a, b, c = names[0], names[5], names[11]
+    taxa = sorted(names)
+    assert orc._canon(frozenset([a, b, c]), taxa) not in free
+    others = [n for n in names if n not in (a, b, c)]
+    con_tree = "(((%s,%s),%s),%s);" % (a, c, b, ",".join(others))
+    r = R.B200FastTreeRunner(ctx=gpu_ctx)
+    r.setAlignment(R.SequenceAlignment(names, g.seqs))
+    r.run()
+    lnl_free = r.getLikelihood()
+    r.setConstraintTree(con_tree)
+    r.run()
+    assert r.last_error is None and r.getResult()
+    got = _splits(_strip(r.getResult()))
+    assert orc._canon(frozenset([a, b, c]), taxa) in got and orc._canon(frozenset([a, c]), taxa) in got
+    assert pb.newick_satisfies_constraints(_strip(r.getResult()), names, pb.constraints_from_tree(con_tree))
+    assert r.getLikelihood() < lnl_free - 10                      # the forced clade costs likelihood
+    assert len(got & free) >= len(free) - 6                        # ... and only the neighbourhood of the forced clade changes
+    # through the tree-builder dispatch (PhylogeneticTreeBuilder.buildFastTree passes the constraint tree on)
+    tb = R.B200TreeBuilder(ctx=gpu_ctx)
+    tb.setAlignment(R.SequenceAlignment(names, g.seqs))
+    tb.setTreeBuildingMethod(R.FAST_TREE)
+    tb.setBootstrapReps(0)
+    tb.setConstraintTree(_strip(g.meta["fd"]["tree"]))            # agrees with the data: the ML tree itself
+    tb.run()
+    assert tb.last_error is None and _splits(_strip(tb.getTreeString())) == free
+
+
+def test_tree_builder_dispatch(gpu_ctx, golden):
+    """PhylogeneticTreeBuilder.run (PhylogeneticTreeBuilder.java:97-129): ml / parsimony / parsimony_bl / FastTree reach the
+    engine's runners and hand back what the reference's build* methods hand back; methods off the path are reported"""
+    g = golden("search")
+    aln = R.SequenceAlignment(g.names, g.seqs)
+    out = {}
+    for method in (R.MAXIMUM_LIKELIHOOD, R.PARSIMONY, R.PARSIMONY_BL, R.FAST_TREE):
+        tb = R.B200TreeBuilder(ctx=gpu_ctx)
+        tb.setAlignment(aln)
+        tb.setTreeBuildingMethod(method)
+        tb.setBootstrapReps(0)
+        tb.setMLMatrix("PROTGAMMAWAG")
+        tb.run()
+        assert tb.last_error is None, (method, tb.last_error)
+        out[method] = tb.getTreeString()
+    ref = _splits(g.meta["fd"]["tree"])
+    assert _splits(_strip(out[R.MAXIMUM_LIKELIHOOD])) == ref and _splits(_strip(out[R.FAST_TREE])) == ref
+    assert ":" not in out[R.PARSIMONY] and all(n in out[R.PARSIMONY] for n in g.names)          # RAxML_parsimonyTree: topology only
+    assert _splits(_strip(out[R.PARSIMONY_BL])) == _splits(out[R.PARSIMONY]) and ":" in out[R.PARSIMONY_BL]
+    tb = R.B200TreeBuilder(ctx=gpu_ctx)
+    tb.setAlignment(aln)
+    tb.setTreeBuildingMethod(R.MAXIMUM_LIKELIHOOD)
+    tb.setBootstrapReps(3)
+    tb.run()
+    assert len(re.findall(r"\)(\d+)", tb.getTreeString())) == len(g.names) - 3               # getBestTreeWithSupports
+    tb.setTreeBuildingMethod(R.NEIGHBOR_JOINING)
+    tb.run()
+    assert tb.getTreeString() is None and "not on the accelerated path" in tb.last_error
+
+
+def test_gene_wise_jackknife_as_weight_masks(gpu_ctx, golden):
+    """a gene-wise jackknife replicate as a 0/1 column mask over the ONE resident supermatrix equals the
+    alignment concatenated from the kept genes alone (what PhylogenomicPipeline2.java:1227-1275 builds per replicate): same
+    lnL on a fixed tree to rounding, same `-f e` result, and the replicate tree search runs on the mask directly"""
+    g = golden("wide")
+    L = len(g.seqs[0])
+    blocks = [300] * (L // 300)
+    blocks[-1] += L - sum(blocks)
+    keep = R.getRandomSet(len(blocks) // 2, 0, len(blocks) - 1, False, seed=2024)     # PEPR: half of the genes, no reuse
+    w = R.gene_block_weights(blocks, keep)
+    assert w.sum() == sum(blocks[k] for k in keep)
+    starts = np.concatenate([[0], np.cumsum(blocks)])
+    sub = ["".join(s[starts[k]:starts[k + 1]] for k in sorted(keep)) for s in g.seqs]
+    tree_nwk = g.meta["fe"]["tree"]
+    a_mask = pb.Alignment(gpu_ctx, g.names, g.seqs, alpha=0.8, site_weights=w)
+    a_sub = pb.Alignment(gpu_ctx, g.names, sub, alpha=0.8)
+    t1, t2 = pb.Tree(a_mask, tree_nwk), pb.Tree(a_sub, tree_nwk)
+    l1, l2 = t1.evaluate(), t2.evaluate()
+    assert abs(l1 - l2) <= 1e-11 * abs(l2)
+    t1.close(); t2.close(); a_mask.close(); a_sub.close()
+    res = []
+    for seqs, weights in ((g.seqs, w), (sub, None)):
+        r = R.B200MLRunner(ctx=gpu_ctx)
+        r.setAlignment(R.SequenceAlignment(g.names, seqs))
+        r.setSiteWeights(weights)
+        r.setStartTree(g.meta["tree_in"])
+        r.run()
+        assert r.last_error is None
+        res.append((r.getLikelihood(), r.getAlpha()))
+    assert abs(res[0][0] - res[1][0]) < 1e-3 and abs(res[0][1] - res[1][1]) < 1e-4

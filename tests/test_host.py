@@ -170,3 +170,89 @@ def test_parsimony_start_tree_is_a_valid_good_tree(golden):
     assert nw2 == nw and score2 == score                           # seeded, reproducible
     nw3, _ = pb.parsimony_tree(g.names, g.seqs, 777)
     assert nw3 != nw                                               # the addition order comes from the seed
+
+
+# ---- topological constraints (FastTreeRunner.java:53-83, 243-273), tree-builder dispatch helpers, jackknife masks --------------
+def _splits(newick, names):
+    """non-trivial splits of a newick tree as frozensets of the side without names[0]"""
+    toks = re.findall(r"[(),]|[^(),:;]+(?::[0-9.eE+-]+)?", newick.strip().rstrip(";"))
+    stack, out = [], set()
+    for tk in toks:
+        if tk == "(":
+            stack.append([])
+        elif tk == ")":
+            grp = stack.pop()
+            s = frozenset().union(*grp)
+            if stack:
+                stack[-1].append(s)
+            if 1 < len(s) < len(names) - 1:
+                out.add(s if names[0] not in s else frozenset(names) - s)
+        elif tk != "," and not tk.startswith(":"):
+            nm = tk.split(":")[0]
+            if nm and stack and nm in names:
+                stack[-1].append(frozenset([nm]))
+    return out
+
+
+def test_constraint_alignment_of_a_tree_matches_the_reference_encoder():
+    """getFastTreeConstraintsForTree: taxa sorted, one 0/1 column per node of the tree, 1 = the taxon descends from it"""
+    text = pb.constraints_from_tree("((B:1,A:1):1,(C:1,D:1)0.9:1,E:2);")
+    rows = dict(zip(text.split()[0::2], text.split()[1::2]))
+    assert list(rows) == [">A", ">B", ">C", ">D", ">E"]
+    cols = {"".join(rows[k][j] for k in rows) for j in range(len(rows[">A"]))}
+    # nodes: top (all), (B,A), B, A, (C,D), C, D, E
+    assert cols == {"11111", "11000", "01000", "10000", "00110", "00100", "00010", "00001"}
+
+
+def test_constrained_parsimony_tree_displays_every_split(golden):
+    g = golden("search")
+    names = g.names
+    free, _ = pb.parsimony_tree(names, g.seqs, seed=5)
+    # force two splits the unconstrained tree does not have: taxa 0+5+11 together, and inside it 0+11
+    a, b, c = names[0], names[5], names[11]
+    assert not any(s == frozenset(names) - {a, b, c} or s == frozenset([a, b, c]) for s in _splits(free, names))
+    rows = {n: "00" for n in names}
+    rows[a], rows[b], rows[c] = "11", "10", "11"
+    text = "".join(">%s\n%s\n" % (n, rows[n]) for n in names)
+    for seed in (5, 6, 7):
+        tree, score = pb.parsimony_tree_constrained(names, g.seqs, text, seed=seed)
+        assert pb.newick_satisfies_constraints(tree, names, text)
+        sp = _splits(tree, names)
+        assert (frozenset(names) - {a, b, c}) in sp and (frozenset(names) - {a, c}) in sp
+    assert not pb.newick_satisfies_constraints(free, names, text)
+    # no constraints: the constrained entry point gives the plain tree; partial constraints (unlisted taxa are free) hold too
+    assert pb.parsimony_tree_constrained(names, g.seqs, None, seed=5)[0] == free
+    part = "".join(">%s\n%s\n" % (n, rows[n][0]) for n in names[:14])
+    tree, _ = pb.parsimony_tree_constrained(names, g.seqs, part, seed=9)
+    assert pb.newick_satisfies_constraints(tree, names, part)
+    with pytest.raises(pb.EngineError, match="not in the alignment"):
+        pb.parsimony_tree_constrained(names, g.seqs, ">nobody\n01\n", seed=1)
+    # contradictory splits (AB|CD and AC|BD) cannot both be displayed: the entry point says so instead of returning a tree
+    bad = {n: "--" for n in names}
+    bad[names[0]], bad[names[1]], bad[names[2]], bad[names[3]] = "11", "10", "01", "00"
+    with pytest.raises(pb.EngineError, match="contradictory"):
+        pb.parsimony_tree_constrained(names, g.seqs, "".join(">%s\n%s\n" % (n, bad[n]) for n in names), seed=1)
+
+
+def test_java_random_and_seeded_random_sets():
+    """RandomSetUtils.getRandomSet draws from `new Random()`; the mirror takes a seed and reproduces java.util.Random"""
+    from pepr_b200 import runner
+    r = runner.JavaRandom(42)
+    assert r.nextIntAll() == -1170105035                      # new Random(42).nextInt()
+    r = runner.JavaRandom(42)
+    assert [r.nextInt(10) for _ in range(10)] == [0, 3, 8, 4, 0, 5, 5, 8, 9, 3]
+    s1 = runner.getRandomSet(20, 0, 39, False, seed=12345)
+    assert s1 == runner.getRandomSet(20, 0, 39, False, seed=12345) and len(set(s1)) == 20 and all(0 <= v <= 39 for v in s1)
+    assert runner.getRandomSet(5, 3, 6, False, seed=1) is None         # range too small without reuse: null in the reference
+    assert len(runner.getRandomSet(9, 3, 6, True, seed=1)) == 9
+
+
+def test_gene_block_weights_and_memory_throttle():
+    from pepr_b200 import runner
+    w = runner.gene_block_weights([3, 2, 4], [0, 2])
+    assert w.dtype == np.int32 and w.tolist() == [1, 1, 1, 0, 0, 1, 1, 1, 1]
+    assert runner.gene_block_weights([2, 2], [1, 1]).tolist() == [0, 0, 2, 2]             # a gene drawn twice (bootstrap over genes)
+    # C4: a 500 x 250k replicate tree needs ~81 GB -> two fit in 180 GB, not three
+    assert runner.support_threads_for_memory(500, 249975, 180e9, 8) == 2
+    assert runner.support_threads_for_memory(2000, 1000000, 180e9, 8) == 1              # never below one, as in the reference
+    assert runner.support_threads_for_memory(100, 95933, 180e9, 4) == 4
