@@ -118,7 +118,9 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
     out.nsites = nsites;
     ColumnSorter cs{ntax, nsites, chars, {}};
     for (int ch = 0; ch < 256; ++ch) cs.lut[ch] = (uint8_t)residue_code((unsigned char)ch);
-    const int threads = nsites >= 20000 ? crunch_threads() : 1;
+    // ranks that share the sort are processes of one box: together they should not ask for more threads than it has cores
+    int threads = nsites >= 20000 ? crunch_threads() : 1;
+    if (share != nullptr && nranks > 1) threads = std::max(1, std::min(threads, (int)std::thread::hardware_concurrency() / nranks));
     const bool timing = getenv("PEPRML_CRUNCH_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now();
@@ -129,24 +131,42 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
             t0 = t1;
         }
     };
-    std::vector<int64_t> order;
-    order.reserve(nsites);
-    for (int64_t s = 0; s < nsites; ++s)
-        if (!site_w || site_w[s] > 0) order.push_back(s);
-    const int64_t n = (int64_t)order.size();
-    std::vector<int64_t> tmp(order.size());
-    std::vector<uint8_t> fresh(order.size(), 1);
+    // level 0 by hand, so that its (up to 23) buckets can be sorted by different threads: the columns with positive weight are
+    // counted per chunk and first residue, then every chunk scatters its columns to its own places (stable: chunk order = column
+    // order) -- two parallel passes over row 0 instead of building an index list first
+    const int64_t chunk0 = 1 << 16, nchunk0 = (nsites + chunk0 - 1) / chunk0;
+    std::vector<int64_t> cnt0((size_t)nchunk0 * kCodes, 0);
+    parallel_for(nchunk0, threads, [&](int64_t b) {
+        int64_t* cnt = cnt0.data() + (size_t)b * kCodes;
+        for (int64_t s = b * chunk0; s < std::min(nsites, (b + 1) * chunk0); ++s)
+            if (!site_w || site_w[s] > 0) ++cnt[cs.lut[chars[s]]];
+    });
+    int64_t count[kCodes + 1] = {0};
+    for (int64_t b = 0; b < nchunk0; ++b)
+        for (int c = 0; c < kCodes; ++c) count[c + 1] += cnt0[(size_t)b * kCodes + c];
+    for (int c = 0; c < kCodes; ++c) count[c + 1] += count[c];
+    const int64_t n = count[kCodes];
+    {
+        int64_t run[kCodes];
+        for (int c = 0; c < kCodes; ++c) run[c] = count[c];
+        for (int64_t b = 0; b < nchunk0; ++b)
+            for (int c = 0; c < kCodes; ++c) {
+                const int64_t k = cnt0[(size_t)b * kCodes + c];
+                cnt0[(size_t)b * kCodes + c] = run[c];
+                run[c] += k;
+            }
+    }
+    std::vector<int64_t> order((size_t)n), tmp((size_t)n);
+    std::vector<uint8_t> fresh((size_t)n, 1);
     lap("setup");
     {
-        // level 0 by hand, so that its (up to 23) buckets can be sorted by different threads
-        int64_t count[kCodes + 1] = {0};
-        for (int64_t i = 0; i < n; ++i) ++count[cs.lut[chars[order[i]]] + 1];
-        for (int c = 0; c < kCodes; ++c) count[c + 1] += count[c];
-        int64_t pos[kCodes];
-        for (int c = 0; c < kCodes; ++c) pos[c] = count[c];
-        for (int64_t i = 0; i < n; ++i) tmp[pos[cs.lut[chars[order[i]]]]++] = order[i];
-        order.swap(tmp);
+        parallel_for(nchunk0, threads, [&](int64_t b) {
+            int64_t* pos = cnt0.data() + (size_t)b * kCodes;
+            for (int64_t s = b * chunk0; s < std::min(nsites, (b + 1) * chunk0); ++s)
+                if (!site_w || site_w[s] > 0) order[pos[cs.lut[chars[s]]]++] = s;
+        });
         lap("level 0");
+        int64_t pos[kCodes];
         // buckets of this rank: all of them, or -- when the ranks share the sort -- its part of a greedy balanced split
         bool mine[kCodes];
         for (int c = 0; c < kCodes; ++c) mine[c] = true;

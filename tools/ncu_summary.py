@@ -11,7 +11,7 @@ import sys
 
 def short(name):
     name = re.sub(r"void |pml::|\(anonymous namespace\)::|<unnamed>::|unnamed>::", "", name)
-    name = re.sub(r"\(bool\)", "", name)
+    name = re.sub(r"\((?:bool|int)\)", "", name)
     return re.sub(r"\(.*$", "", name).strip()
 
 
