@@ -333,3 +333,52 @@ def test_two_trees_on_one_alignment_do_not_see_each_others_state(gpu_ctx, golden
         assert abs(x - y) <= 1e-9 * max(1.0, abs(y)), (a1, want)
     assert a0 != a1 and b0 != a1
     fresh.close(); ta.close(); tb.close(); aln.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntax", [3, 4, 5, 6])
+def test_smallest_trees_where_cherries_meet(gpu_ctx, golden, ntax):
+    """3 to 6 taxa: every inner node is a (folded) cherry or next to one -- cherry against tip, cherry against cherry, cherry as a
+    child and as the far end -- including the cases where a folded cherry has to be stored after all.  lnL and derivatives on
+    EVERY branch against the CPU oracle, the oracle's own `-f e` optimum within its stopping tolerance."""
+    g = golden("small")
+    names, seqs = g.names[:ntax], g.seqs[:ntax]
+    shapes = {3: "(%s,%s,%s);", 4: "((%s,%s),%s,%s);", 5: "((%s,%s),(%s,%s),%s);", 6: "((%s,%s),(%s,%s),(%s,%s));"}
+    nwk = shapes[ntax] % tuple(names)
+    pat, w, _ = orc.compress(orc.encode(seqs))
+    m = orc.Model()
+    ot = orc.Tree(nwk, names)
+    aln = pb.Alignment(gpu_ctx, names, seqs, alpha=0.7)
+    tree = pb.Tree(aln, nwk)
+    rng = np.random.default_rng(ntax)
+    lens = {}
+    for e in range(tree.num_branches):
+        a, b, _ = tree.branch(e)
+        lens[e] = float(rng.uniform(0.02, 0.6))
+        tree.set_branch(e, lens[e])
+    # the oracle numbers its branches differently: match them by their two end nodes' leaf sets through unique lengths
+    for oe in range(ot.nedge):
+        ot.set_bl(oe, 0.0)
+    want_nwk = tree.newick()
+    ot = orc.Tree(want_nwk.replace("):0.0;", ");"), names)
+    want = orc.evaluate(m, ot, pat, w, 0.7)
+    got = tree.evaluate()
+    assert abs(got - want) <= 1e-10 * abs(want)
+    olen = {round(ot.get_bl(oe), 12): oe for oe in range(ot.nedge)}
+    for e in range(tree.num_branches):
+        oe = olen[round(lens[e], 12)]
+        for t in (lens[e], 0.3):
+            gl, g1, g2 = tree.branch_derivs(e, t)
+            wl, w1, w2 = orc.branch_derivs(m, ot, pat, w, 0.7, oe, t)
+            assert abs(gl - wl) <= 1e-10 * abs(wl) and abs(g1 - w1) <= 1e-8 * max(1.0, abs(w1)) and abs(g2 - w2) <= 1e-8 * max(1.0, abs(w2))
+    tree.invalidate()
+    assert abs(tree.evaluate() - want) <= 1e-10 * abs(want)
+    lnl, alpha = tree.optimize(True, 0.1)
+    olnl, oalpha = orc.optimize(m, ot, pat, w, 0.7, True, 0.1)
+    assert lnl >= olnl - 0.1 and lnl >= want - 1e-9
+    if ntax >= 4:
+        node = ntax                                                   # first inner node
+        for keep in tree.neighbors(node):
+            tg, sc = tree.score_spr_candidates(node, keep, 3)
+            assert np.all(np.isfinite(sc))
+    tree.close(); aln.close()
