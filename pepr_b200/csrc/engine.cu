@@ -1461,7 +1461,7 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
             c->dev_free(d_fresh);
             return ok;
         };
-        crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks, &share);
+        crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks, &share, true);  // own block now, the rest on demand
     } else {
         crunch_patterns(ntax, nsites, chars, site_weights, a->pat, c->rank, c->nranks);  // codes of this rank's block only
     }
@@ -1476,7 +1476,8 @@ int pml_aln_load(pml_ctx* c, int ntax, int64_t nsites, const char* const* names,
     for (int t = 0; t < ntax; ++t)
         std::memcpy(hc.data() + (size_t)t * a->npad, a->pat.codes.data() + (size_t)t * a->pat.codes_n, a->nloc);
     std::vector<int32_t> hw(a->npad, 0);
-    std::copy(a->pat.weight.begin() + a->p0, a->pat.weight.begin() + a->p0 + a->nloc, hw.begin());
+    if (a->pat.full) std::copy(a->pat.weight.begin() + a->p0, a->pat.weight.begin() + a->p0 + a->nloc, hw.begin());
+    else std::copy(a->pat.own_weight.begin(), a->pat.own_weight.end(), hw.begin());
     bool ok = c->cuda(c->dev_alloc(&a->d_codes, hc.size()), "codes alloc") &&
               c->cuda(c->dev_alloc(&a->d_weights, sizeof(int32_t) * a->npad), "weights alloc") &&
               c->cuda(c->dev_alloc(&a->d_wcustom, sizeof(int32_t) * a->npad), "weights alloc") &&
@@ -1544,6 +1545,7 @@ int pml_aln_dims(const pml_aln* a, int* ntax, int64_t* nsites, int64_t* npat, in
 
 int pml_aln_patterns(const pml_aln* a, int32_t* weights, int64_t* site_to_pattern) {
     if (!a) return PML_EINVAL;
+    finish_patterns(const_cast<pml_aln*>(a)->pat);
     if (weights) std::copy(a->pat.weight.begin(), a->pat.weight.end(), weights);
     if (site_to_pattern) std::copy(a->pat.site_to_pat.begin(), a->pat.site_to_pat.end(), site_to_pattern);
     return PML_OK;
@@ -1674,6 +1676,7 @@ int pml_evaluate(pml_tree* t, const int32_t* weights, double* lnl, double* per_s
     adopt_model(t);
     const int rc = evaluate_branch(t, t->topo.edge[0][0], weights, lnl);
     if (rc != PML_OK || !per_site) return rc;
+    finish_patterns(a->pat);
     std::vector<double> pp(a->npad);
     if (!c->cuda(cudaMemcpy(pp.data(), a->d_site_lnl, sizeof(double) * a->npad, cudaMemcpyDeviceToHost), "site lnL download"))
         return PML_ENODEVICE;
@@ -1947,6 +1950,7 @@ int64_t pml_constraints_from_tree(const char* newick, char* buf, size_t cap) {
 
 int pml_bootstrap_weights(const pml_aln* a, int64_t* seed, int nrep, int32_t* out) {
     if (!a || !seed || nrep < 0 || !out) return PML_EINVAL;
+    finish_patterns(const_cast<pml_aln*>(a)->pat);
     bootstrap_replicates(seed, a->pat.weight, nrep, out);
     return PML_OK;
 }
@@ -1970,6 +1974,7 @@ int pml_bootstrap_trees(pml_aln* a, int64_t weight_seed, int64_t parsimony_seed,
     pml_ctx* c = a->ctx;
     if (!c->bind()) return PML_ENODEVICE;
     if (!(eps > 0.0)) eps = 0.1;
+    finish_patterns(a->pat);
     const int64_t np = a->pat.npat;
     // the WHOLE weight stream is drawn (it is sequential by construction), so replicate r carries the same weights whatever
     // the sharding; only this share's vectors are kept
@@ -2058,9 +2063,10 @@ int pml_crunch_patterns_sharded(int nranks, int ntax, int64_t nsites, const uint
                 if (--ex.arrived == 0) ex.order.clear();
                 return true;
             };
-            crunch_patterns(ntax, nsites, chars, site_weights, pats[r], r, nranks, &share);
+            crunch_patterns(ntax, nsites, chars, site_weights, pats[r], r, nranks, &share, true);
         });
     for (auto& th : pool) th.join();
+    for (auto& p : pats) finish_patterns(p);
     const Patterns& p0 = pats[0];
     for (int r = 1; r < nranks; ++r)
         if (pats[r].npat != p0.npat || pats[r].weight != p0.weight || pats[r].site_to_pat != p0.site_to_pat || pats[r].first != p0.first)

@@ -112,8 +112,54 @@ struct ColumnSorter {
 
 }  // namespace
 
+namespace {
+// pattern index of every sorted column = running count of boundaries; weights, site -> pattern, representatives (two parallel
+// passes over chunks of the sorted column list)
+void fill_patterns(Patterns& out, const std::vector<int64_t>& order, const std::vector<uint8_t>& fresh, const int32_t* site_w, int threads) {
+    const int64_t n = (int64_t)order.size();
+    const int64_t chunk = 1 << 15, nchunks = (n + chunk - 1) / chunk;
+    std::vector<int64_t> base(nchunks + 1, 0);
+    parallel_for(nchunks, threads, [&](int64_t b) {
+        int64_t cnt = 0;
+        for (int64_t k = b * chunk; k < std::min(n, (b + 1) * chunk); ++k) cnt += fresh[k];
+        base[b + 1] = cnt;
+    });
+    for (int64_t b = 0; b < nchunks; ++b) base[b + 1] += base[b];
+    out.npat = base[nchunks];
+    out.site_to_pat.assign(out.nsites, -1);
+    out.first.assign(out.npat, 0);
+    out.weight.assign(out.npat, 0);
+    std::vector<int64_t>& first = out.first;
+    parallel_for(nchunks, threads, [&](int64_t b) {
+        int64_t p = base[b] - 1;
+        const int64_t lo = b * chunk, hi = std::min(n, (b + 1) * chunk);
+        // a pattern may straddle chunk boundaries: every chunk adds its share of a pattern's weight with one atomic add
+        int64_t acc = 0;
+        for (int64_t k = lo; k < hi; ++k) {
+            const int64_t s = order[k];
+            if (fresh[k]) {
+                if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
+                acc = 0;
+                first[++p] = s;
+            }
+            acc += site_w ? site_w[s] : 1;
+            out.site_to_pat[s] = p;
+        }
+        if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
+    });
+    out.full = true;
+}
+}  // namespace
+
+void finish_patterns(Patterns& p) {
+    if (p.full) return;
+    fill_patterns(p, p.sorted_cols, p.sorted_fresh, p.col_weight.empty() ? nullptr : p.col_weight.data(), p.nsites >= 20000 ? crunch_threads() : 1);
+    std::vector<int64_t>().swap(p.sorted_cols);
+    std::vector<uint8_t>().swap(p.sorted_fresh);
+}
+
 void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank, int nranks,
-                     const CrunchShare* share) {
+                     const CrunchShare* share, bool lazy) {
     out.ntax = ntax;
     out.nsites = nsites;
     ColumnSorter cs{ntax, nsites, chars, {}};
@@ -204,42 +250,55 @@ void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32
         }
     }
     lap("exchange");
-    // pattern index of every sorted column = running count of boundaries (two parallel passes over chunks)
-    const int64_t chunk = 1 << 15, nchunks = (n + chunk - 1) / chunk;
-    std::vector<int64_t> base(nchunks + 1, 0);
-    parallel_for(nchunks, threads, [&](int64_t b) {
-        int64_t cnt = 0;
-        for (int64_t k = b * chunk; k < std::min(n, (b + 1) * chunk); ++k) cnt += fresh[k];
-        base[b + 1] = cnt;
-    });
-    for (int64_t b = 0; b < nchunks; ++b) base[b + 1] += base[b];
-    out.npat = base[nchunks];
-    out.site_to_pat.assign(nsites, -1);
-    std::vector<int64_t> first(out.npat);  // representative column of each pattern
-    out.weight.assign(out.npat, 0);
-    parallel_for(nchunks, threads, [&](int64_t b) {
-        int64_t p = base[b] - 1;
-        const int64_t lo = b * chunk, hi = std::min(n, (b + 1) * chunk);
-        // a pattern may straddle chunk boundaries: every chunk adds its share of a pattern's weight with one atomic add
-        int64_t acc = 0;
-        for (int64_t k = lo; k < hi; ++k) {
-            const int64_t s = order[k];
-            if (fresh[k]) {
-                if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
-                acc = 0;
-                first[++p] = s;
+    if (lazy && nranks > 1) {
+        // this rank's pattern block only: count the boundaries (parallel), then one walk over the block's own columns
+        const int64_t chunk = 1 << 15, nchunks = (n + chunk - 1) / chunk;
+        std::vector<int64_t> base(nchunks + 1, 0);
+        parallel_for(nchunks, threads, [&](int64_t b) {
+            int64_t cnt = 0;
+            for (int64_t k = b * chunk; k < std::min(n, (b + 1) * chunk); ++k) cnt += fresh[k];
+            base[b + 1] = cnt;
+        });
+        for (int64_t b = 0; b < nchunks; ++b) base[b + 1] += base[b];
+        out.npat = base[nchunks];
+        out.codes_p0 = out.npat * rank / nranks;
+        out.codes_n = out.npat * (rank + 1) / nranks - out.codes_p0;
+        out.own_weight.assign((size_t)out.codes_n, 0);
+        out.own_first.assign((size_t)out.codes_n, 0);
+        if (out.codes_n > 0) {
+            // the chunk in which pattern codes_p0 starts, then forward to its first column
+            int64_t b = std::upper_bound(base.begin(), base.end(), out.codes_p0) - base.begin() - 1;
+            int64_t k = b * chunk, p = base[b] - 1;
+            for (; k < n; ++k) {
+                if (fresh[k] && ++p == out.codes_p0) break;
             }
-            acc += site_w ? site_w[s] : 1;
-            out.site_to_pat[s] = p;
+            --p;
+            for (; k < n; ++k) {
+                if (fresh[k]) {
+                    if (++p >= out.codes_p0 + out.codes_n) break;
+                    out.own_first[(size_t)(p - out.codes_p0)] = order[k];
+                }
+                out.own_weight[(size_t)(p - out.codes_p0)] += site_w ? site_w[order[k]] : 1;
+            }
         }
-        if (acc) __atomic_fetch_add(&out.weight[p], (int32_t)acc, __ATOMIC_RELAXED);
-    });
-    out.npat = (int64_t)first.size();
+        lap("own block");
+        gather_codes(ntax, nsites, chars, out.own_first, 0, out.codes_n, out.codes);
+        lap("codes");
+        out.full = false;
+        out.weight.clear();
+        out.site_to_pat.clear();
+        out.first.clear();
+        out.sorted_cols.swap(order);
+        out.sorted_fresh.swap(fresh);
+        if (site_w) out.col_weight.assign(site_w, site_w + nsites);
+        else out.col_weight.clear();
+        return;
+    }
+    fill_patterns(out, order, fresh, site_w, threads);
     lap("weights");
     out.codes_p0 = out.npat * rank / nranks;
     out.codes_n = out.npat * (rank + 1) / nranks - out.codes_p0;
-    gather_codes(ntax, nsites, chars, first, out.codes_p0, out.codes_n, out.codes);
-    out.first.swap(first);
+    gather_codes(ntax, nsites, chars, out.first, out.codes_p0, out.codes_n, out.codes);
     lap("codes");
 }
 

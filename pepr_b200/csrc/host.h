@@ -20,6 +20,16 @@ struct Patterns {
     std::vector<int32_t> weight;       // npat
     std::vector<int64_t> site_to_pat;  // nsites, -1 for dropped columns
     std::vector<int64_t> first;        // npat: a representative column of every pattern
+    // A rank that shares the sort with others (crunch_patterns(..., lazy)) finishes only ITS pattern block at load time:
+    // own_weight / own_first cover patterns [codes_p0, codes_p0 + codes_n), weight / site_to_pat / first stay empty (full ==
+    // false) until somebody asks for them (finish_patterns: per-site output, bootstrap weights, pml_aln_patterns) -- the passes
+    // over ALL columns are what every one of N processes would otherwise repeat at every load.
+    bool full = true;
+    std::vector<int32_t> own_weight;
+    std::vector<int64_t> own_first;
+    std::vector<int64_t> sorted_cols;   // kept for finish_patterns
+    std::vector<uint8_t> sorted_fresh;
+    std::vector<int32_t> col_weight;    // the caller's column weights (empty: all 1)
 };
 // column sort + duplicate merge in the reference's order (raxmlHPC sitesort/sitecombcrunch: lexicographic by taxon row)
 // rank / nranks: keep the residue codes of that rank's contiguous pattern block only (the sort itself is always global)
@@ -29,7 +39,9 @@ struct Patterns {
 // does it with one NCCL allreduce each); everything after the sort is cheap and identical on every rank.
 using CrunchShare = std::function<bool(int64_t* order, uint8_t* fresh, int64_t n)>;
 void crunch_patterns(int ntax, int64_t nsites, const uint8_t* chars, const int32_t* site_w, Patterns& out, int rank = 0,
-                     int nranks = 1, const CrunchShare* share = nullptr);
+                     int nranks = 1, const CrunchShare* share = nullptr, bool lazy = false);
+// fills weight / site_to_pat / first of a lazily crunched alignment (no-op when already full)
+void finish_patterns(Patterns& p);
 // the code rows of patterns [p0, p0 + n) of an alignment crunched elsewhere (first: representative column per pattern)
 void gather_codes(int ntax, int64_t nsites, const uint8_t* chars, const std::vector<int64_t>& first, int64_t p0, int64_t n,
                   std::vector<uint8_t>& codes);
