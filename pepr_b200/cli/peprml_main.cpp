@@ -7,7 +7,9 @@
 // RAxML_result.<n>, RAxML_log.<n>, RAxML_perSiteLLs.<n>, RAxML_bipartitions.<n>, RAxML_bipartitionsBranchLabels.<n>,
 // RAxML_bestTree.<n>, RAxML_parsimonyTree.<n>, RAxML_bootstrap.<n>, <aln>.BS<k>.  Flags honoured: -f d|a|e|g|n|b|j,
 // -m PROTGAMMAWAG, -s, -n, -t, -z, -a, -b, -x, -p, -#/-N, -e, -y, -T (accepted: the pattern-parallel workers of -T are the
-// GPU's SMs here), -w.  `-f d` = parsimony start tree + lazy-SPR hill climbing + model optimisation; `-f a -x seed -N k` =
+// GPU's SMs here), -w.  PEPRML_GPUS=n spreads ONE call over n GPUs of the box the way `-T n` spreads raxmlHPC-PTHREADS over n
+// cores (RAxMLRunner.java:130-132): the alignment patterns are sharded over a pml_group_create group, one host thread per GPU
+// makes the same calls, rank 0 writes the files; results are the single-GPU results (sums are added in rank order).  `-f d` = parsimony start tree + lazy-SPR hill climbing + model optimisation; `-f a -x seed -N k` =
 // k bootstrap replicates (raxmlHPC's weight stream, a quick search each) + ML search + supports drawn on the ML tree.
 #include <sys/stat.h>
 
@@ -17,8 +19,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "peprml.h"
@@ -77,6 +82,26 @@ std::string tree_string(pml_tree* t) {
     return s;
 }
 
+// rendezvous of the rank threads of one call (PEPRML_GPUS > 1)
+class Meeting {
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0, generation = 0;
+    const int n;
+
+public:
+    explicit Meeting(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lock(mu);
+        const int gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+        } else cv.wait(lock, [&] { return generation != gen; });
+    }
+};
+
 double tree_length(pml_tree* t) {
     double sum = 0.0;
     for (int e = 0; e < pml_tree_num_branches(t); ++e) {
@@ -125,7 +150,8 @@ int main(int argc, char** argv) {
     if (exists(info_path)) die("RAxML output files with the run ID <" + a.name + "> already exist", 1);  // raxmlHPC refuses too
 
     const auto t_start = std::chrono::steady_clock::now();
-    std::ofstream info(info_path);
+    std::ofstream info_file(info_path);
+    std::ostream& info = info_file;
     info << "\n\nThis is " << pml_version() << ", answering for RAxML's command line.\n\n";
 
     if (a.f == "b") {  // draw bipartition support of the -z trees on the -t tree; host-only integer path
@@ -162,8 +188,26 @@ int main(int argc, char** argv) {
     }
 
     if (a.aln.empty()) die("-s alignment is required");
-    pml_ctx* ctx = nullptr;
-    if (pml_ctx_create(0, 0, 1, nullptr, &ctx) != PML_OK) die(std::string("cannot create GPU context: ") + pml_last_error(nullptr), 3);
+    int ngpu = 1;
+    if (const char* g = std::getenv("PEPRML_GPUS")) ngpu = std::max(1, std::atoi(g));
+    std::vector<pml_ctx*> ctxs((size_t)ngpu, nullptr);
+    if (ngpu == 1) {
+        if (pml_ctx_create(0, 0, 1, nullptr, &ctxs[0]) != PML_OK) die(std::string("cannot create GPU context: ") + pml_last_error(nullptr), 3);
+    } else {
+        std::vector<int> ids((size_t)ngpu);
+        for (int i = 0; i < ngpu; ++i) ids[i] = i;
+        if (pml_group_create(ids.data(), ngpu, ctxs.data()) != PML_OK)
+            die(std::string("cannot create a group of ") + std::to_string(ngpu) + " GPUs: " + pml_last_error(nullptr), 3);
+    }
+    std::ofstream nowhere;  // never opened: swallows what the ranks other than 0 would write
+    Meeting meeting(ngpu);
+    std::vector<std::vector<double>> per_site_of((size_t)ngpu);  // -f g: every rank holds the values of its own patterns' columns
+    // one rank of the call: every rank makes the same engine calls (a branch pass waits for its peers' sums), rank 0 owns the files
+    auto work = [&](int rank) {
+    pml_ctx* ctx = ctxs[(size_t)rank];
+    const bool lead = rank == 0;
+    std::ostream& info = lead ? static_cast<std::ostream&>(info_file) : nowhere;
+    auto out_file = [&](const std::string& path) { return lead ? std::ofstream(path) : std::ofstream(); };
     pml_aln* aln = nullptr;
     check(ctx, pml_aln_load_phylip(ctx, a.aln.c_str(), a.weights.empty() ? nullptr : a.weights.c_str(), &aln), "alignment");
     int ntax;
@@ -197,7 +241,7 @@ int main(int argc, char** argv) {
             }
         }
         for (int r = 0; r < a.reps; ++r) {
-            std::ofstream out(a.aln + ".BS" + std::to_string(r));
+            std::ofstream out = out_file(a.aln + ".BS" + std::to_string(r));
             out << ntax << " " << nsites << "\n";
             for (int t = 0; t < ntax; ++t) {
                 out << pml_aln_name(aln, t) << " ";
@@ -206,7 +250,7 @@ int main(int argc, char** argv) {
                 out << "\n";
             }
         }
-        return 0;
+        return;
     }
 
     if (a.f == "d" || a.f == "a" || a.f == "o") {
@@ -228,15 +272,15 @@ int main(int argc, char** argv) {
             pml_tree* t = nullptr;
             check(ctx, pml_tree_start_parsimony(aln, a.pseed, nullptr, &t), "parsimony start tree");
             std::string s = tree_string(t);
-            std::ofstream(dir + "RAxML_parsimonyTree." + a.name) << s << "\n";
-            return 0;
+            out_file(dir + "RAxML_parsimonyTree." + a.name) << s << "\n";
+            return;
         }
         std::vector<std::string> boots;
         if (a.f == "a") {
             std::vector<int32_t> W((size_t)npat * a.reps);
             int64_t seed = a.bseed;
             check(ctx, pml_bootstrap_weights(aln, &seed, a.reps, W.data()), "bootstrap weights");
-            std::ofstream bs(dir + "RAxML_bootstrap." + a.name);
+            std::ofstream bs = out_file(dir + "RAxML_bootstrap." + a.name);
             for (int r = 0; r < a.reps; ++r) {
                 pml_tree* t = search_tree(W.data() + (size_t)r * npat, a.pseed + 1 + r, 1, false, nullptr, nullptr);
                 boots.push_back(tree_string(t));
@@ -247,12 +291,12 @@ int main(int argc, char** argv) {
         double lnl = 0.0, alpha = 1.0;
         pml_tree* t = search_tree(nullptr, a.pseed, 10, true, &lnl, &alpha);
         const std::string best = tree_string(t);
-        std::ofstream(dir + "RAxML_result." + a.name) << best << "\n";
-        std::ofstream(dir + "RAxML_bestTree." + a.name) << best << "\n";
+        out_file(dir + "RAxML_result." + a.name) << best << "\n";
+        out_file(dir + "RAxML_bestTree." + a.name) << best << "\n";
         char buf[64];
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
         std::snprintf(buf, sizeof buf, "%.6f", lnl);
-        std::ofstream(dir + "RAxML_log." + a.name) << secs << " " << buf << "\n";
+        out_file(dir + "RAxML_log." + a.name) << secs << " " << buf << "\n";
         info << "Final GAMMA-based Score of best tree " << buf << "\n";
         info << "Final GAMMA  likelihood: " << buf << "\n";
         std::snprintf(buf, sizeof buf, "%.6f", alpha);
@@ -268,12 +312,11 @@ int main(int argc, char** argv) {
             std::string out((size_t)n, '\0');
             pml_support_tree(best.c_str(), ptr.data(), (int)ptr.size(), 1, out.data(), (size_t)n);
             out.resize(std::strlen(out.c_str()));
-            std::ofstream(dir + "RAxML_bipartitions." + a.name) << out << "\n";
+            out_file(dir + "RAxML_bipartitions." + a.name) << out << "\n";
         }
         pml_tree_free(t);
         pml_aln_free(aln);
-        pml_ctx_destroy(ctx);
-        return 0;
+        return;
     }
 
     std::vector<std::string> trees;
@@ -286,10 +329,10 @@ int main(int argc, char** argv) {
         trees = read_trees(a.trees);
     } else die("unsupported algorithm -f " + a.f, 2);
 
-    std::ofstream result(dir + "RAxML_result." + a.name), logf(dir + "RAxML_log." + a.name);
+    std::ofstream result = out_file(dir + "RAxML_result." + a.name), logf = out_file(dir + "RAxML_log." + a.name);
     std::ofstream persite;
     if (a.f == "g") {
-        persite.open(dir + "RAxML_perSiteLLs." + a.name);
+        if (lead) persite.open(dir + "RAxML_perSiteLLs." + a.name);
         persite << "  " << trees.size() << "  " << nsites << "\n";
     }
     char buf[64];
@@ -306,14 +349,22 @@ int main(int argc, char** argv) {
         std::snprintf(buf, sizeof buf, "%.6f", lnl);
         logf << secs << " " << buf << "\n";
         if (a.f == "g") {
-            std::vector<double> ps((size_t)nsites);
+            std::vector<double>& ps = per_site_of[(size_t)rank];
+            ps.assign((size_t)nsites, 0.0);
             check(ctx, pml_evaluate(t, nullptr, &lnl, ps.data()), "per-site lnL");
-            persite << "tr" << (i + 1) << "\t";
-            for (int64_t s = 0; s < nsites; ++s) {
-                std::snprintf(buf, sizeof buf, "%.6f ", ps[s]);
-                persite << buf;
+            meeting.wait();  // a column's value is non-zero on exactly one rank: rank 0 adds the ranks' vectors
+            if (lead) {
+                char cell[64];
+                persite << "tr" << (i + 1) << "\t";
+                for (int64_t s = 0; s < nsites; ++s) {
+                    double v = 0.0;
+                    for (int r = 0; r < ngpu; ++r) v += per_site_of[(size_t)r][(size_t)s];
+                    std::snprintf(cell, sizeof cell, "%.6f ", v);
+                    persite << cell;
+                }
+                persite << "\n";
             }
-            persite << "\n";
+            meeting.wait();
         }
         if (a.f == "n") info << "Tree " << i << " Likelihood " << buf << " Tree-Length " << tree_length(t) << "\n";
         if (i + 1 == trees.size()) {
@@ -328,6 +379,13 @@ int main(int argc, char** argv) {
         pml_tree_free(t);
     }
     pml_aln_free(aln);
-    pml_ctx_destroy(ctx);
+    };
+    if (ngpu == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int r = 0; r < ngpu; ++r) pool.emplace_back(work, r);
+        for (auto& th : pool) th.join();
+    }
+    for (pml_ctx* c : ctxs) pml_ctx_destroy(c);
     return 0;
 }

@@ -69,8 +69,9 @@ def test_runner_bootstrap_weights_and_supports(gpu_ctx, golden):
     assert _labels(got) == _labels(g.meta["fb"]["bipartitions"])
 
 
-def _run_cli(args, cwd):
-    return subprocess.run([CLI] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+def _run_cli(args, cwd, env=None):
+    return subprocess.run([CLI] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                          env=dict(os.environ, **(env or {})))
 
 
 def test_cli_f_e_writes_raxml_files(tmp_path, golden):
@@ -246,3 +247,39 @@ def test_runner_parsimony_with_branch_lengths_is_y_then_f_e(gpu_ctx, golden):
     r3.setParsimonyOnly(True)
     r3.run()
     assert r3.getParsimonyTree() == ptree and r3.getBestTree() == "" and r3.getLikelihood() is None
+
+
+def test_cli_spreads_one_call_over_several_gpus(tmp_path, golden):
+    """PEPRML_GPUS=2: what `-T n` is for raxmlHPC-PTHREADS (RAxMLRunner.java:130-132) -- one call, the patterns sharded over a
+    group of GPUs inside the one process, rank 0 writing the files.  Same lnL, alpha, tree and per-site lnL as the one-GPU
+    call (the sums are added shard by shard, so agreement is to rounding, not to the bit), and the tree search (`-f d`,
+    parsimony scans + lazy SPR in lock step) ends on the same tree."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = golden("wide")
+    from pepr_b200 import synth
+    synth.write_phylip(str(tmp_path / "w.phy"), g.names, g.seqs)
+    (tmp_path / "w.nwk").write_text(g.meta["tree_in"] + "\n")
+    out = {}
+    for tag, env in (("one", {}), ("two", {"PEPRML_GPUS": "2"})):
+        r = _run_cli(["-f", "g", "-m", "PROTGAMMAWAG", "-s", "w.phy", "-n", tag, "-z", "w.nwk", "-T", "2"], tmp_path, env=env)
+        assert r.returncode == 0, r.stderr
+        info = (tmp_path / ("RAxML_info." + tag)).read_text()
+        lnl = float(re.search(r"Final GAMMA\s+likelihood: (\S+)", info).group(1))
+        alpha = float(re.search(r"alpha: (\S+)", info).group(1))
+        ps = np.array([float(x) for x in (tmp_path / ("RAxML_perSiteLLs." + tag)).read_text().split("\n")[1].split("\t")[1].split()])
+        out[tag] = (lnl, alpha, ps, (tmp_path / ("RAxML_result." + tag)).read_text().strip())
+    a, b = out["one"], out["two"]
+    assert abs(a[0] - b[0]) < 1e-3 and abs(a[1] - b[1]) < 1e-4 and np.abs(a[2] - b[2]).max() < 1e-4
+    la = [float(x) for x in re.findall(r":([0-9.]+)", a[3])]
+    lb = [float(x) for x in re.findall(r":([0-9.]+)", b[3])]
+    assert len(la) == len(lb) and np.allclose(la, lb, atol=1e-5)
+    s = golden("search")
+    synth.write_phylip(str(tmp_path / "s.phy"), s.names, s.seqs)
+    trees = {}
+    for tag, env in (("d1", {}), ("d2", {"PEPRML_GPUS": "2"})):
+        r = _run_cli(["-f", "d", "-m", "PROTGAMMAWAG", "-s", "s.phy", "-n", tag, "-p", "12345"], tmp_path, env=env)
+        assert r.returncode == 0, r.stderr
+        trees[tag] = re.sub(r":[0-9.eE+-]+", "", (tmp_path / ("RAxML_bestTree." + tag)).read_text().strip())
+    assert trees["d1"] == trees["d2"]
