@@ -565,6 +565,9 @@ def main():
                        "taxa": NTAX, "sites_per_gpu": sites, "patterns": npat, "partition": "sites (pattern blocks)",
                        "collective": ctx.collective,
                        "cache": "CLV working set %.1f GB per GPU >> 126 MB L2 (inputs larger than L2)" % ((NTAX - 2) * npat_local * 640 / 1e9),
+                       "cherries": "inner nodes with two tip children are never stored: their consumers form them from two tip look-ups "
+                                   "(a folded update counts as a site-update whenever a stored one would have been recomputed)",
+                       "launches_per_step": launches / args.steps,
                        "final_lnl": lnl, "final_alpha": alpha},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
