@@ -157,6 +157,11 @@ int pml_profile_end(pml_ctx *, double ms[PML_NKINDS], int64_t launches[PML_NKIND
  * first CTA the clock cycles spent in each pipeline phase (12 warps x 8 counters: wait data, fragments + wait turn, MMAs,
  * products, wait slot, store, tiles, prologue) */
 int pml_trace_enable(pml_ctx *, int on);
+/* profiling aid: between begin and read every CLV / fused launch leaves six %globaltimer stamps (ns): CTA 0 enters, its
+ * dependency wait returns, its first MMA turn, its last tile leaves the MMA warps, (fused) the last CTA has drawn its ticket,
+ * (fused) the result is published.  read returns the number of launches captured (stamps: n x 6, kinds: n) and ends the capture. */
+int pml_timeline_begin(pml_ctx *);
+int pml_timeline_read(pml_ctx *, uint64_t *stamps, int32_t *kinds, int cap);
 int pml_trace_read(pml_ctx *, int64_t out[96]);
 
 /* stopwatch on the context's stream: start records an event, stop records another, synchronises and returns the

@@ -151,6 +151,15 @@ struct pml_ctx {
     int trace_newview_tips = -1;  // -1: every CLV kernel, 0 / 1: only those with that many tip children
     bool profiling = false;
     std::vector<Timed> timed;
+    // pml_timeline_begin/read (profiling aid): six %globaltimer stamps per CLV / fused launch, in launch order
+    static constexpr int kTimelineCap = 16384;
+    unsigned long long* d_timeline = nullptr;
+    std::vector<int> timeline_kinds;
+    unsigned long long* timeline_slot(int kind) {
+        if (!d_timeline || (int)timeline_kinds.size() >= kTimelineCap) return nullptr;
+        timeline_kinds.push_back(kind);
+        return d_timeline + 6 * (timeline_kinds.size() - 1);
+    }
     std::vector<cudaEvent_t> spare_events;
     cudaEvent_t event() {
         cudaEvent_t e;
@@ -423,7 +432,9 @@ void launch_newview(pml_tree* t, const NewviewOp& nv, bool count = true) {
     pml_ctx* c = a->ctx;
     const int ntip = (nv.left.clv == nullptr) + (nv.right.clv == nullptr);
     const int tk = c->tick(newview_kind(nv.left, nv.right), a->nloc);
-    launch_newview_mma(nv, a->npad, c->sms, c->stream);
+    NewviewOp timed_nv = nv;
+    timed_nv.timeline = c->timeline_slot(newview_kind(nv.left, nv.right));
+    launch_newview_mma(timed_nv, a->npad, c->sms, c->stream);
     c->tock(tk);
     ++t->launches;
     if (count) t->site_updates[2 - ntip] += a->nloc;
@@ -595,8 +606,11 @@ double branch_launch_sides(pml_tree* t, const Side& sa, const Side& sb, int e, c
     // kinds: see launch_newview
     const int fused_kind = fused ? 13 + 3 * (newview_kind(nv->left, nv->right) - 1) + far_index(args.a) : 0;
     const int tk = c->tick(fused ? fused_kind : (site_lnl ? 9 : 6) + far_index(args.a), a->nloc);
-    if (fused) launch_fused(*nv, args, a->npad, c->sms, c->stream);
-    else launch_branch_mma(args, a->npad, c->sms, c->stream);
+    if (fused) {
+        NewviewOp timed_nv = *nv;
+        timed_nv.timeline = c->timeline_slot(fused_kind);
+        launch_fused(timed_nv, args, a->npad, c->sms, c->stream);
+    } else launch_branch_mma(args, a->npad, c->sms, c->stream);
     c->tock(tk);
     t->launches += 1;
     t->prepared_branch = keep_table ? e : -1;
@@ -1290,6 +1304,7 @@ void pml_ctx_destroy(pml_ctx* c) {
     if (c->d_mail) cudaFree(c->d_mail);
     if (c->d_peer_lost) cudaFree(c->d_peer_lost);
     if (c->d_trace_buf) cudaFree(c->d_trace_buf);
+    if (c->d_timeline) cudaFree(c->d_timeline);
     for (auto& t : c->timed) { cudaEventDestroy(t.t0); cudaEventDestroy(t.t1); }
     for (auto e : c->spare_events) cudaEventDestroy(e);
     delete c;
@@ -1321,6 +1336,25 @@ int pml_trace_enable(pml_ctx* c, int on) {
 int pml_trace_read(pml_ctx* c, int64_t out[96]) {
     if (!c || !out || !c->d_trace_buf || !c->bind() || !c->sync()) return PML_EINVAL;
     return c->cuda(cudaMemcpy(out, c->d_trace_buf, 96 * sizeof(long long), cudaMemcpyDeviceToHost), "trace read") ? PML_OK : PML_ENODEVICE;
+}
+
+int pml_timeline_begin(pml_ctx* c) {
+    if (!c || !c->bind() || !c->sync()) return PML_EINVAL;
+    const size_t bytes = sizeof(unsigned long long) * 6 * pml_ctx::kTimelineCap;
+    if (!c->d_timeline && !c->cuda(cudaMalloc(&c->d_timeline, bytes), "timeline alloc")) return PML_ENOMEM;
+    cudaMemset(c->d_timeline, 0, bytes);
+    c->timeline_kinds.clear();
+    return PML_OK;
+}
+
+int pml_timeline_read(pml_ctx* c, uint64_t* stamps, int32_t* kinds, int cap) {
+    if (!c || !c->d_timeline || !c->bind() || !c->sync()) return PML_EINVAL;
+    const int n = std::min<int>(cap, (int)c->timeline_kinds.size());
+    if (stamps && n > 0 && !c->cuda(cudaMemcpy(stamps, c->d_timeline, sizeof(uint64_t) * 6 * n, cudaMemcpyDeviceToHost), "timeline read")) return PML_ENODEVICE;
+    if (kinds) std::copy(c->timeline_kinds.begin(), c->timeline_kinds.begin() + n, kinds);
+    cudaFree(c->d_timeline);   // one capture per begin: launches stop being stamped
+    c->d_timeline = nullptr;
+    return n;
 }
 
 int pml_timer_start(pml_ctx* c) {

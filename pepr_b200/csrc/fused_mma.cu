@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
+    const bool tl = op.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tl) op.timeline[0] = global_timer_ns();
     pdl_launch_dependents();
     // ---- static model constants first (before the dependency wait and before any bulk load is queued) ----------------
     double pre[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
+    if (tl) op.timeline[1] = global_timer_ns();
     // lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
     constexpr int kRounds = Plan::kBranches / 2;
     double my_len[kRounds];
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         if (lane == 0) ticket = atomicAdd(args.ticket, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket != gridDim.x - 1) return;
+        if (op.timeline && lane == 0) op.timeline[4] = global_timer_ns();
         __threadfence();
         double r3[3] = {0.0, 0.0, 0.0};
         for (int i = lane; i < (int)gridDim.x; i += 32) {
@@ -444,6 +448,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             args.result[3] = tt;
             *args.ticket = 0;
             publish_result(args.pub, r3, tt, lost);
+            if (op.timeline) op.timeline[5] = global_timer_ns();
         }
         return;
     }
@@ -453,10 +458,12 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         // -------------------------------------------------------------------------------------------- NV group
         const bool tr = op.trace != nullptr && blockIdx.x == 0 && lane == 0;
         mma_turn_init(0);
+        if (tl) op.timeline[2] = global_timer_ns();
         for (int n = 0; n <= cta_tiles; ++n) {
             if (n == cta_tiles) {  // one empty turn at the end: the BR group is one tile behind
                 mma_turn_begin(0);
                 mma_turn_end(0);
+                if (tl) op.timeline[3] = global_timer_ns();
                 break;
             }
             const int slot = n % kFDepth;

@@ -45,6 +45,10 @@ struct NewviewOp {
     double* out;
     int32_t* out_scale;
     long long* trace;  // optional (profiling aid): per warp of CTA 0, cycles spent in each phase of the pipeline
+    // optional (profiling aid, pml_timeline_*): six %globaltimer stamps of this launch -- [0] CTA 0 enters, [1] its dependency
+    // wait returns, [2] its first MMA turn, [3] its last tile is through the MMA warps, [4] fused kernel: the last CTA has drawn
+    // its ticket, [5] fused kernel: the result is published
+    unsigned long long* timeline;
 };
 
 // the children ordered tip < cherry < inner (their product commutes exactly): the CLV kernels exist for that order only

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     // model constants are requested before the producer queues the first tiles (see branch_mma.cu)
     const int stid = warp < kProducerWarp ? threadIdx.x : threadIdx.x - 32;  // rank among the staging threads
     pmat::ModelRegs regs{};
+    const bool tl = op.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tl) op.timeline[0] = global_timer_ns();
     pdl_launch_dependents();
     if (warp != kProducerWarp) regs = pmat::model_prefetch<kStagers>(op.dm, stid);
     // P matrices: MMA warp w builds category w & 3 of the branches at positions (w >> 2), (w >> 2) + 2, ... of the list
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
+    if (tl) op.timeline[1] = global_timer_ns();
     if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
     // the lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
     constexpr int kRounds = Plan::kBranches / 2;
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     const int rounds = (cta_tiles + kMmaGroups - 1) / kMmaGroups;
     if (op.trace && blockIdx.x == 0 && lane == 0) op.trace[warp * 8 + 7] += clock64() - t_entry;  // prologue
     mma_turn_init(grp);
+    if (tl) op.timeline[2] = global_timer_ns();
     for (int j = 0; j < rounds; ++j) {
         const int n = j * kMmaGroups + grp;
         if (n >= cta_tiles) {  // no tile left for this group: keep the MMA token moving
@@ -373,6 +377,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             row[6] += 1;
         }
     }
+    if (tl) op.timeline[3] = global_timer_ns();
 }
 
 // ---------------------------------------------------------------------------------------------- tip-tip -----
