@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         // a pair of tiles (one per MMA group) = 32 rows = one row per lane
         const int e = warp - kMmaWarps, half = lane >> 4, r = lane & 15;
         double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;
+        const PublishEarly early = publish_prefetch(args.pub, tt);  // while the tiles are still streaming
         const int pairs = (cta_tiles + 1) / 2;
         if (tr) args.trace[warp * 8 + 7] += clock64() - t_entry;  // entry -> loop
         for (int q = e; q < pairs; q += kEpiWarps) {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         // CTA partials, then the CTA that draws the last ticket adds all of them in a fixed order
         if (lane < 3) {
             args.partials[(int64_t)lane * gridDim.x + blockIdx.x] = s_fin[lane] + s_fin[3 + lane];
-            __threadfence();
+            fence_acq_rel_gpu();
         }
         __syncwarp();
         unsigned int ticket = 0;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         }
         if (ticket != gridDim.x - 1) return;
         const long long f3c = args.trace ? clock64() : 0;
-        __threadfence();
+        fence_acq_rel_gpu();
         double r3[3] = {0.0, 0.0, 0.0};  // lane-strided, then a shuffle tree -- the same order every run
         for (int i = lane; i < (int)gridDim.x; i += 32) {
 #pragma unroll
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
             args.result[2] = r3[2];
             args.result[3] = tt;
             *args.ticket = 0;
-            publish_result(args.pub, r3, tt, lost);
+            publish_result(args.pub, r3, tt, lost, early);
             if (args.trace) {
                 args.trace[88] += clock64() - f3c;  // last CTA: final sum, NR step, publication
                 args.trace[89] += 1;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
 
 __global__ void k_publish(const double* result, Publish pub) {
     const double r[3] = {result[0], result[1], result[2]};
-    publish_result(pub, r, result[3]);
+    publish_result(pub, r, result[3], false, publish_prefetch(pub, result[3]));
 }
 
 template <int KA, bool kStore>

@@ -355,6 +355,16 @@ bool upload_model(pml_aln* a) {
     std::memcpy(h->rates, a->rates, sizeof a->rates);
     for (int i = 0; i < kStates; ++i)
         for (int k = 0; k < kStates; ++k) h->piV[i][k] = es.pi[i] * es.V[i][k];
+    for (int code = 0; code < kCodes; ++code)
+        for (int k = 0; k < kStates; ++k) {
+            double acc = 0.0;  // same summation order as the kernels used when they built the table themselves
+            if (code < 20) acc = h->piV[code][k];
+            else if (code == 20) acc = h->piV[2][k] + h->piV[3][k];
+            else if (code == 21) acc = h->piV[5][k] + h->piV[6][k];
+            else
+                for (int i = 0; i < kStates; ++i) acc += h->piV[i][k];
+            h->tipvec[code][k] = acc;
+        }
     ++a->model_epoch;  // every tree of this alignment drops its views before it plans again (adopt_model)
     return c->cuda(cudaMemcpyAsync(a->d_model, h, sizeof(DeviceModel), cudaMemcpyHostToDevice, c->stream), "model upload");
 }

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     pdl_launch_dependents();
     // ---- static model constants first (before the dependency wait and before any bulk load is queued) ----------------
     double pre[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-    double pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0;
+    double pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0, pre_tip[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int c_p = warp & 3;  // MMA warp w builds category w & 3 of the branches at positions (w >> 2), (w >> 2) + 2, ... (Plan::branch_id)
     if (warp != kProducerWarp) {
 #pragma unroll
@@ -149,9 +149,21 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 pre[2][q] = (&dm->piV[0][0])[idx];
             }
         }
-        if (stid < kCats * 24 && stid % 24 < kStates) {
-            pre_lambda = dm->lambda[stid % 24];
-            pre_rate = dm->rates[stid / 24];
+        // the 96 threads that build no matrix (helper warps, warp 11) take the exponentials and the tip vector: on the MMA warps
+        // those exponentials (FP64 library code next to the other warps' DMMAs) delayed three of the eight matrix builders
+        if (stid >= kMmaWarps * 32) {
+            const int j = stid - kMmaWarps * 32;
+            if (j % 24 < kStates) {
+                pre_lambda = dm->lambda[j % 24];
+                pre_rate = dm->rates[j / 24];
+            }
+            if (kTipY) {
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int idx = j + q * 96;
+                    pre_tip[q] = idx < kCodes * kStates ? (&dm->tipvec[0][0])[idx] : 0.0;
+                }
+            }
         }
         if (warp < kMmaWarps && lane < kStates) lr = dm->lambda[lane] * dm->rates[c_p];
     }
@@ -250,12 +262,20 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     }
 
     // ---- prologue of every other warp ----------------------------------------------------------------------------------
-    if (stid < kCats * 24) {
+    if (stid >= kMmaWarps * 32) {
+        const int j = stid - kMmaWarps * 32;   // 0 .. 95 = kCats * 24
         const double a = pre_lambda * pre_rate;
-        const double e = stid % 24 < kStates ? exp(a * tt) : 0.0;
-        s_exp[stid] = e;
-        s_exp[kCats * 24 + stid] = a * e;
-        s_exp[2 * kCats * 24 + stid] = a * a * e;
+        const double e = j % 24 < kStates ? exp(a * tt) : 0.0;
+        s_exp[j] = e;
+        s_exp[kCats * 24 + j] = a * e;
+        s_exp[2 * kCats * 24 + j] = a * a * e;
+        if (kTipY) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int idx = j + q * 96;
+                if (idx < kCodes * kStates) s_tipy[(idx / kStates) * kTipVecPad + idx % kStates] = pre_tip[q];
+            }
+        }
     }
     double fragL[3][5], fragR[3][5];  // NV group: P fragments of the two children;  BR group: pi V (y end) and Vinv (x end)
     double* s_x = s_prod;             // fragment exchange: [branch 0 / 1][category][15][32]
@@ -279,19 +299,6 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
                 pmat::tiles_to_fragments(acc, lane, frag);
                 pmat::fragments_to_smem(frag, lane, s_x + (id * kCats + c_p) * pmat::kFragSlotDoubles);
             }
-        }
-    }
-    if (kTipY) {
-        // tipvec[code][k] = sum over the residues the code allows of pi_i V[i][k]  (s_piv is in place since the __syncthreads above)
-        for (int idx = stid; idx < kCodes * kStates; idx += kStagers) {
-            const int code = idx / kStates, k = idx % kStates;
-            double acc = 0.0;
-            if (code < 20) acc = s_piv[code * kStates + k];
-            else if (code == 20) acc = s_piv[2 * kStates + k] + s_piv[3 * kStates + k];
-            else if (code == 21) acc = s_piv[5 * kStates + k] + s_piv[6 * kStates + k];
-            else
-                for (int i = 0; i < kStates; ++i) acc += s_piv[i * kStates + k];
-            s_tipy[code * kTipVecPad + k] = acc;
         }
     }
     named_barrier(kStageBarrier, kStagers);
@@ -326,6 +333,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         // warp e stores the tiles n = e, e+2, ... of the new CLV and finishes the row sums of the tile pairs q = e, e+2, ...
         const int e = warp - kMmaWarps;
         double sum_l = 0.0, sum_d1 = 0.0, sum_d2 = 0.0;
+        const PublishEarly early = publish_prefetch(args.pub, tt);  // while the tiles are still streaming
         int pending[2] = {-1, -1};  // product slots whose bulk store may still be reading shared memory
         auto release_stores = [&]() {
             if (lane == 0 && (pending[0] >= 0 || pending[1] >= 0)) {
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         // CTA partials, then the CTA that draws the last ticket adds all of them in a fixed order (branch_mma.cu)
         if (lane < 3) {
             args.partials[(int64_t)lane * gridDim.x + blockIdx.x] = s_fin[lane] + s_fin[3 + lane];
-            __threadfence();
+            fence_acq_rel_gpu();
         }
         __syncwarp();
         unsigned int ticket = 0;
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket != gridDim.x - 1) return;
         if (op.timeline && lane == 0) op.timeline[4] = global_timer_ns();
-        __threadfence();
+        fence_acq_rel_gpu();
         double r3[3] = {0.0, 0.0, 0.0};
         for (int i = lane; i < (int)gridDim.x; i += 32) {
 #pragma unroll
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             args.result[2] = r3[2];
             args.result[3] = tt;
             *args.ticket = 0;
-            publish_result(args.pub, r3, tt, lost);
+            publish_result(args.pub, r3, tt, lost, early);
             if (op.timeline) op.timeline[5] = global_timer_ns();
         }
         return;

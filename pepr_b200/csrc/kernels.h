@@ -18,6 +18,7 @@ struct DeviceModel {
     double pi[kStates];
     double rates[kCats];
     double piV[kStates][kStates];   // pi_i * V[i][k]
+    double tipvec[kCodes][kStates]; // sum over the residues a code allows of pi_i V[i][k]: the eigen-space vector of a tip end
 };
 
 // one side of a branch: an inner node's CLV (+ cumulative scaling counts), a tip's residue codes, or a CHERRY -- an inner
@@ -69,9 +70,14 @@ __host__ __device__ inline double nr_clamp_length(double t) {
     z = z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
     return -log(z);
 }
-__host__ __device__ inline int nr_step(double t, double d1t, double d2t, double* t_new) {
-    double z = exp(-t);
-    z = z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
+// z of a length, brought into the NR range (the device takes it while the pass is still running: it needs the length only)
+__host__ __device__ inline double nr_z(double t) {
+    const double z = exp(-t);
+    return z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
+}
+__host__ __device__ inline int nr_step_z(double z, double d1t, double d2t, double* t_new);
+__host__ __device__ inline int nr_step(double t, double d1t, double d2t, double* t_new) { return nr_step_z(nr_z(t), d1t, d2t, t_new); }
+__host__ __device__ inline int nr_step_z(double z, double d1t, double d2t, double* t_new) {
     const double d1 = -d1t, d2 = d2t;  // derivatives in lz = log z = -t
     if (d2 >= 0.0 && z < kZmax) {
         *t_new = -log(0.37 * z + 0.63);
@@ -148,17 +154,34 @@ struct Publish {
     int* poison;
 };
 #ifdef __CUDACC__
+// What the publishing thread can fetch while the pass is still running (after the dependency wait): the poison flag -- only a
+// launch that has completed can have raised it -- and z of the length the sums are taken at.  Both used to sit, a dependent
+// global load and an exponential, between the last CTA's sum and the store of the new length.
+struct PublishEarly {
+    int poison;
+    double z;
+};
+__device__ __forceinline__ PublishEarly publish_prefetch(const Publish& pub, double t) {
+    PublishEarly e{0, 0.0};
+    if (pub.len) {
+        e.poison = *reinterpret_cast<volatile int*>(pub.poison);
+        e.z = nr_z(t);
+    }
+    return e;
+}
+// release / acquire around the ticket of the last-CTA sum (cheaper than the sequentially consistent __threadfence)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // tail of a branch pass on one thread: NR step (optional) and publication; r = {lnL, d1, d2}, t = the length they were taken at
-__device__ __forceinline__ void publish_result(const Publish& pub, const double r[3], double t, bool comm_lost = false) {
+__device__ __forceinline__ void publish_result(const Publish& pub, const double r[3], double t, bool comm_lost, const PublishEarly& early) {
     double t_new = t;
     int status = kNrNone;
     if (comm_lost) {
         status = kNrCommLost;
         if (pub.poison) *pub.poison = 1;
     } else if (pub.len) {
-        if (*pub.poison) status = kNrSkipped;
+        if (early.poison) status = kNrSkipped;
         else {
-            status = nr_step(t, r[1], r[2], &t_new);
+            status = nr_step_z(early.z, r[1], r[2], &t_new);
             *pub.len = t_new;
             if (status == kNrRetry) *pub.poison = 1;
         }
