@@ -197,7 +197,10 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             my_len[r] = *src * (id < 2 ? op.len_scale : 1.0);
         }
     }
-    const double t_raw = args.t_ptr ? *args.t_ptr : args.t;
+    // the length the sums are taken at is needed by the warps that build no matrix only (exponentials, publication): the MMA
+    // warps do not wait for its load and for the exponential + logarithm that bring it into the NR range
+    const bool wants_t = warp >= kMmaWarps && warp != kProducerWarp;
+    const double t_raw = (args.t_ptr && wants_t) ? *args.t_ptr : args.t;
     if (warp != kProducerWarp) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         }
     }
     // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
-    const double tt = args.t_ptr ? nr_clamp_length(t_raw) : t_raw;
+    const double tt = (args.t_ptr && wants_t) ? nr_clamp_length(t_raw) : t_raw;
     __syncthreads();
 
     const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
