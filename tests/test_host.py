@@ -256,3 +256,11 @@ def test_gene_block_weights_and_memory_throttle():
     assert runner.support_threads_for_memory(500, 249975, 180e9, 8) == 2
     assert runner.support_threads_for_memory(2000, 1000000, 180e9, 8) == 1              # never below one, as in the reference
     assert runner.support_threads_for_memory(100, 95933, 180e9, 4) == 4
+
+
+def test_branch_lengths_are_printed_like_java_double_tostring():
+    """TreeSupportDecorator output goes through AdvancedTree.getTreeString -> Double.toString: shortest repr that round-trips,
+    plain notation in [1e-3, 1e7), `d.dddE±n` outside it, always a fractional digit"""
+    t = "((A:0.1,B:0.0001):1.0E7,(C:123456789,D:0.001):9999999,(E:2,F:1e-5):12345.678,G:0.30000000000000004);"
+    out = pb.support_tree(t, [t], as_percent=False)
+    assert out == "((A:0.1,B:1.0E-4)1:1.0E7,(C:1.23456789E8,D:0.001)1:9999999.0,(E:2.0,F:1.0E-5)1:12345.678,G:0.30000000000000004)1;"
