@@ -51,5 +51,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, verbose=False):
+    """Experiment aid: the engine compiled with extra -D flags into pepr_b200/variants/libpeprml_<name>.so (git-ignored; loaded
+    instead of the product library when PEPRML_LIB points at it, see engine.lib)."""
+    out_dir = os.path.join(HERE, "variants")
+    obj_dir = os.path.join(HERE, "build", "var_" + name)
+    os.makedirs(out_dir, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "libpeprml_%s.so" % name)
+    objs, jobs = [], []
+    for s in SOURCES:
+        o = os.path.join(obj_dir, s + ".o")
+        cmd = [NVCC] + ARCH + COMMON + ["-D" + d for d in defines] + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        jobs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(o)
+    for cmd, job in jobs:
+        if job.wait() != 0:
+            raise subprocess.CalledProcessError(job.returncode, cmd)
+    subprocess.run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl", "-lpthread"], check=True)
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # python -m pepr_b200.build --variant er1 PML_EARLY_RELEASE=1 ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose=True))
+        sys.exit(0)
+
     build(force="--force" in sys.argv, verbose=True)

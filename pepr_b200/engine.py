@@ -34,7 +34,7 @@ def lib():
     """loads pepr_b200/libpeprml.so; raises if it has not been built (python -m pepr_b200.build)"""
     global _LIB
     if _LIB is None:
-        so = os.path.join(HERE, "libpeprml.so")
+        so = os.environ.get("PEPRML_LIB") or os.path.join(HERE, "libpeprml.so")  # PEPRML_LIB: an experiment build (build.build_variant)
         if not os.path.exists(so):
             raise EngineError("pepr_b200/libpeprml.so is missing: run `python -m pepr_b200.build` (nvcc, sm_100a); "
                               "there is no CPU fallback")
