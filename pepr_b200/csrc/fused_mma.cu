@@ -212,9 +212,10 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             }
         }
     }
-    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
-    const double tt = (args.t_ptr && wants_t) ? nr_clamp_length(t_raw) : t_raw;
     __syncthreads();
+    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first -- behind the
+    // barrier: ahead of it this exponential + logarithm of the helper warps held up the warps that build the matrices
+    const double tt = (args.t_ptr && wants_t) ? nr_clamp_length(t_raw) : t_raw;
 
     const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 

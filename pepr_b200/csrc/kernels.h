@@ -157,17 +157,49 @@ struct Publish {
 // What the publishing thread can fetch while the pass is still running (after the dependency wait): the poison flag -- only a
 // launch that has completed can have raised it -- and z of the length the sums are taken at.  Both used to sit, a dependent
 // global load and an exponential, between the last CTA's sum and the store of the new length.
+// ... and, since the step is taken in t = -log z (below), the three lengths it can end on without knowing the derivatives: the
+// exponential and the logarithms of the guarded step leave the tail of the pass (2.8 k clk on one thread behind the last CTA's
+// sum) for the time the tiles stream.
 struct PublishEarly {
     int poison;
-    double z;
+    double z;        // z of the length the sums are taken at
+    double t;        // that length (already inside the NR range)
+    double t_lo;     // -log min(0.25 z + 0.75, zmax): the shortest length the step may end on
+    double t_retry;  // -log(0.37 z + 0.63): where the derivatives are taken again after a bad curvature
 };
+constexpr double kTmax = 34.538776394910684;  // -log kZmin
 __device__ __forceinline__ PublishEarly publish_prefetch(const Publish& pub, double t) {
-    PublishEarly e{0, 0.0};
+    PublishEarly e{0, 0.0, t, 0.0, 0.0};
     if (pub.len) {
         e.poison = *reinterpret_cast<volatile int*>(pub.poison);
         e.z = nr_z(t);
+        const double cap = 0.25 * e.z + 0.75;
+        e.t_lo = -log(cap < kZmax ? cap : kZmax);
+        e.t_retry = -log(0.37 * e.z + 0.63);
     }
     return e;
+}
+// nr_step_z in t = -log z: z exp(step) is t - step, the clamps of z become clamps of t (same decisions; the new length differs
+// from -log(z exp(step)) by rounding only)
+__device__ __forceinline__ int nr_step_t(const PublishEarly& e, double d1t, double d2t, double* t_new) {
+    const double d1 = -d1t, d2 = d2t;  // derivatives in lz = log z = -t
+    if (d2 >= 0.0 && e.z < kZmax) {
+        *t_new = e.t_retry;
+        return kNrRetry;
+    }
+    double t = e.t;
+    if (d2 < 0.0) {
+        const double step = -d1 / d2;
+        if (step < 100.0) {
+            t = e.t - step;
+            t = t > kTmax ? kTmax : t;
+            t = t < e.t_lo ? e.t_lo : t;
+        } else {
+            t = e.t_lo;
+        }
+    }
+    *t_new = t;
+    return kNrDone;
 }
 // release / acquire around the ticket of the last-CTA sum (cheaper than the sequentially consistent __threadfence)
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
@@ -181,7 +213,7 @@ __device__ __forceinline__ void publish_result(const Publish& pub, const double 
     } else if (pub.len) {
         if (early.poison) status = kNrSkipped;
         else {
-            status = nr_step_z(early.z, r[1], r[2], &t_new);
+            status = nr_step_t(early, r[1], r[2], &t_new);
             *pub.len = t_new;
             if (status == kNrRetry) *pub.poison = 1;
         }
