@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     }
     if (tid < kCats * 24) {
         const double a = pre_lambda * pre_rate;
-        const double e = tid % 24 < kStates ? exp(a * tt) : 0.0;
+        const double e = tid % 24 < kStates ? pmat::exp_neg(a * tt) : 0.0;
         s_exp[tid] = e;
         s_exp[kCats * 24 + tid] = a * e;
         s_exp[2 * kCats * 24 + tid] = a * a * e;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         named_barrier(kStageBarrier, kStagers);  // V and Vinv are in place
         if (warp < kMmaWarps) {
             double acc[3][3][2];
-            pmat::build_p_tiles(s_v, exp(lr * tip_len), lane, acc);
+            pmat::build_p_tiles(s_v, pmat::exp_neg(lr * tip_len), lane, acc);
             pmat::tiles_to_lookup(acc, lane, warp & 3, s_tip + (warp >> 2) * kCodes * kTipPad, kTipPad);
         }
     }

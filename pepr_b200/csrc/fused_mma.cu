@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     if (stid >= kMmaWarps * 32) {
         const int j = stid - kMmaWarps * 32;   // 0 .. 95 = kCats * 24
         const double a = pre_lambda * pre_rate;
-        const double e = j % 24 < kStates ? exp(a * tt) : 0.0;
+        const double e = j % 24 < kStates ? pmat::exp_neg(a * tt) : 0.0;
         s_exp[j] = e;
         s_exp[kCats * 24 + j] = a * e;
         s_exp[2 * kCats * 24 + j] = a * a * e;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         for (int r = 0; r < kRounds; ++r) {
             const int id = Plan::branch_id(2 * r + (warp >> 2));
             double acc[3][3][2];
-            pmat::build_p_tiles(s_model, exp(lr * my_len[r]), lane, acc);
+            pmat::build_p_tiles(s_model, pmat::exp_neg(lr * my_len[r]), lane, acc);
             double* table = nullptr;
             if (id == 0 && kTipL) table = s_tabL;
             else if (id == 1 && kTipR) table = s_tabR;

@@ -65,11 +65,11 @@ void configure_mma_kernels();
 //   otherwise z *= exp(-d1/d2) when that exponent is < 100, capped at 0.25 z + 0.75 and at zmax (kNrDone)
 constexpr double kZmin = 1.0e-15, kZmax = 1.0 - 1.0e-6;
 enum NrStatus : int { kNrNone = 0, kNrDone = 1, kNrRetry = 2, kNrSkipped = 3 };
-__host__ __device__ inline double nr_clamp_length(double t) {
-    double z = exp(-t);
-    z = z < kZmin ? kZmin : (z > kZmax ? kZmax : z);
-    return -log(z);
-}
+// the same bounds on t = -log z (kTmax = -log kZmin, kTmin = -log kZmax).  Clamping t itself is what clamping z and taking the
+// logarithm again does, without the exponential and the logarithm (3 k clk at the head of every branch pass) and without
+// moving a length that is already inside the range by a rounding error.
+constexpr double kTmax = 34.538776394910684, kTmin = 1.000000500029089e-06;
+__host__ __device__ inline double nr_clamp_length(double t) { return t > kTmax ? kTmax : (t < kTmin ? kTmin : t); }
 // z of a length, brought into the NR range (the device takes it while the pass is still running: it needs the length only)
 __host__ __device__ inline double nr_z(double t) {
     const double z = exp(-t);
@@ -167,7 +167,6 @@ struct PublishEarly {
     double t_lo;     // -log min(0.25 z + 0.75, zmax): the shortest length the step may end on
     double t_retry;  // -log(0.37 z + 0.63): where the derivatives are taken again after a bad curvature
 };
-constexpr double kTmax = 34.538776394910684;  // -log kZmin
 __device__ __forceinline__ PublishEarly publish_prefetch(const Publish& pub, double t) {
     PublishEarly e{0, 0.0, t, 0.0, 0.0};
     if (pub.len) {

@@ -107,6 +107,27 @@ __device__ __forceinline__ void build_p(const double* s_model, int tid, double* 
     }
 }
 
+// exp(x) for the arguments of this path, x = lambda_k r_c t <= 0 (an eigenvalue "0" may come out as a few ulp above it).
+// The library exponential is a chain of ~35 dependent FP64 instructions, and a dependent FP64 instruction takes ~40 clk here:
+// 1,440 clk measured between "length arrived" and "exponentials done" in every launch's prologue, a quarter of it.  This one
+// has a chain of ten: Cody-Waite reduction by ln 2, then exp(r) = 1 + r + r^2 q(r) with q of degree 11 (Taylor; |r| <= 0.347:
+// truncation 4e-18) evaluated by Estrin's scheme, then the power of two through the exponent bits.  Relative error
+// <= 1.4 x 2^-53 over [-708, 0] (checked against 200-bit arithmetic); below -708 the result is 0 (the library gives < 3e-308).
+__device__ __forceinline__ double exp_neg(double x) {
+    if (!(x > -708.0)) return 0.0;
+    const double n = rint(x * 1.4426950408889634);
+    double r = fma(-n, 6.93147180369123816490e-01, x);
+    r = fma(-n, 1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p0 = fma(1.0 / 6.0, r, 0.5), p1 = fma(1.0 / 120.0, r, 1.0 / 24.0), p2 = fma(1.0 / 5040.0, r, 1.0 / 720.0);
+    const double p3 = fma(1.0 / 362880.0, r, 1.0 / 40320.0), p4 = fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
+    const double p5 = fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
+    const double q0 = fma(p1, r2, p0), q1 = fma(p3, r2, p2), q2 = fma(p5, r2, p4);
+    const double q = fma(q2, r8, fma(q1, r4, q0));
+    const double e = fma(r2, q, r) + 1.0;
+    return e * __hiloint2double(((int)n + 1023) << 20, 0);
+}
+
 // ---- the same product on the FP64 tensor path, one warp per (branch, category) ---------------------------------------
 // P_c = W * Vinv with W[i][k] = V[i][k] e_c[k] as 3 x 3 tiles of m8n8k4 (45 DMMA, nine independent accumulator chains):
 // the eight MMA warps of a CLV kernel build the eight matrices of a launch in ~1,500 cycles (FMA version above: ~3,200),
