@@ -183,24 +183,34 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // where this warp's branch lengths live and what they are multiplied by: kernel parameters, brought into registers AHEAD of
+    // the dependency wait (left to the compiler their constant-bank reads sit behind it, in front of the loads they address)
+    constexpr int kRounds = Plan::kBranches / 2;
+    const double* len_src[kRounds];
+    double len_mul[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int id = Plan::branch_id(2 * r + (warp >> 2));
+        len_src[r] = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
+                     : id == 4 ? op.right.len1 : id == 5 ? op.right.len2 : id == 6 ? args.a.len1 : args.a.len2;
+        len_mul[r] = id < 2 ? op.len_scale : 1.0;
+        asm volatile("" : "+l"(len_src[r]), "+d"(len_mul[r]));
+    }
+    const double* t_src = args.t_ptr;
+    asm volatile("" : "+l"(t_src));
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     if (tl) op.timeline[1] = global_timer_ns();
-    // lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
-    constexpr int kRounds = Plan::kBranches / 2;
+    // lengths are requested before the model constants (in flight since the kernel started) are consumed, and nothing ahead of
+    // the CTA barrier waits for them: one latency, not two
     double my_len[kRounds];
     if (warp < kMmaWarps) {
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int id = Plan::branch_id(2 * r + (warp >> 2));
-            const double* src = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
-                                : id == 4 ? op.right.len1 : id == 5 ? op.right.len2 : id == 6 ? args.a.len1 : args.a.len2;
-            my_len[r] = *src * (id < 2 ? op.len_scale : 1.0);
-        }
+        for (int r = 0; r < kRounds; ++r) my_len[r] = *len_src[r];
     }
     // the length the sums are taken at is needed by the warps that build no matrix only (exponentials, publication): the MMA
-    // warps do not wait for its load and for the exponential + logarithm that bring it into the NR range
+    // warps do not wait for its load
     const bool wants_t = warp >= kMmaWarps && warp != kProducerWarp;
-    const double t_raw = (args.t_ptr && wants_t) ? *args.t_ptr : args.t;
+    const double t_raw = (t_src && wants_t) ? *t_src : args.t;
     if (warp != kProducerWarp) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -213,9 +223,12 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         }
     }
     __syncthreads();
-    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first -- behind the
-    // barrier: ahead of it this exponential + logarithm of the helper warps held up the warps that build the matrices
-    const double tt = (args.t_ptr && wants_t) ? nr_clamp_length(t_raw) : t_raw;
+    if (warp < kMmaWarps) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) my_len[r] *= len_mul[r];
+    }
+    // the length the sums are taken at: the device copy of the branch length is brought into the NR range first
+    const double tt = (t_src && wants_t) ? nr_clamp_length(t_raw) : t_raw;
 
     const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 

@@ -82,6 +82,21 @@ struct SmemPlan {
 };
 
 // at least one child is not a tip (the tip-tip case has its own kernel below, used only where a cherry must be stored)
+// PML_TL_PROBE_A / _B (profiling builds only): two more %globaltimer stamps of thread 0 in the prologue, written to the timeline
+// slots a CLV launch does not use ([4], [5]).  Points: 1 after the CTA barrier, 2 exponentials done, 3 matrix tiles done,
+// 4 table / fragments stored, 5 after the first stage barrier, 6 after the second.  Stores only: nothing waits for them.
+#ifndef PML_TL_PROBE_A
+#define PML_TL_PROBE_A 0
+#endif
+#ifndef PML_TL_PROBE_B
+#define PML_TL_PROBE_B 0
+#endif
+#define PML_TL_POINT(k)                                                   \
+    do {                                                                  \
+        if (PML_TL_PROBE_A == (k) && tl) op.timeline[4] = global_timer_ns(); \
+        if (PML_TL_PROBE_B == (k) && tl) op.timeline[5] = global_timer_ns(); \
+    } while (0)
+
 template <int KL, int KR>
 __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op, int ntiles) {
     using Plan = SmemPlan<KL, KR>;
@@ -126,23 +141,36 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // where this warp's branch lengths live and what they are multiplied by: kernel parameters, brought into registers AHEAD of
+    // the dependency wait (left to the compiler their constant-bank reads sit behind it, in front of the loads they address)
+    constexpr int kRounds = Plan::kBranches / 2;
+    const double* len_src[kRounds];
+    double len_mul[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;  // 0, 1: the update's branches; 2, 3 / 4, 5: cherry tips
+        len_src[r] = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
+                     : id == 4 ? op.right.len1 : op.right.len2;
+        len_mul[r] = id < 2 ? op.len_scale : 1.0;
+        asm volatile("" : "+l"(len_src[r]), "+d"(len_mul[r]));
+    }
     pdl_wait();  // from here on the kernel touches what its predecessors wrote: branch lengths, CLVs, scaling counts
     if (tl) op.timeline[1] = global_timer_ns();
     if (op.trace) t_entry = clock64();  // the cycle trace starts once the predecessor has drained
-    // the lengths are requested before the model constants (in flight since the kernel started) are consumed: one latency, not two
-    constexpr int kRounds = Plan::kBranches / 2;
+    // the lengths are requested before the model constants (in flight since the kernel started) are consumed, and nothing ahead
+    // of the CTA barrier waits for them: one latency, not two
     double my_len[kRounds];
     if (warp < kMmaWarps) {
 #pragma unroll
-        for (int r = 0; r < kRounds; ++r) {
-            const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;  // 0, 1: the update's branches; 2, 3 / 4, 5: cherry tips
-            const double* src = id == 0 ? op.len_left : id == 1 ? op.len_right : id == 2 ? op.left.len1 : id == 3 ? op.left.len2
-                                : id == 4 ? op.right.len1 : op.right.len2;
-            my_len[r] = *src * (id < 2 ? op.len_scale : 1.0);
-        }
+        for (int r = 0; r < kRounds; ++r) my_len[r] = *len_src[r];
     }
     if (warp != kProducerWarp) pmat::matrices_to_smem<kStagers>(regs, stid, s_model);  // V and Vinv
     __syncthreads();
+    PML_TL_POINT(1);
+    if (warp < kMmaWarps) {
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) my_len[r] *= len_mul[r];
+    }
 
     // tiles of this CTA: n = 0 .. cta_tiles-1  <->  global tile blockIdx.x + n * gridDim.x ; MMA group n % 2, product slot n % 4
     const int cta_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -201,7 +229,9 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
 #ifdef PML_PROLOGUE_PROBES
             if (trp && r == 0) probe[0] = clock64() - t_entry + (long long)(e_lane == 12345.678);
 #endif
+            if (r == 0 && e_lane != 12345.678) PML_TL_POINT(2);
             pmat::build_p_tiles(s_model, e_lane, lane, acc);
+            if (r == 0 && acc[2][2][1] != 12345.678) PML_TL_POINT(3);
 #ifdef PML_PROLOGUE_PROBES
             if (trp && r == 0) probe[1] = clock64() - t_entry + (long long)(acc[2][2][1] == 12345.678);
 #endif
@@ -220,6 +250,10 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             __syncwarp();
             if (trp && r == 0) probe[2] = clock64() - t_entry;
 #endif
+            if (PML_TL_PROBE_A == 4 || PML_TL_PROBE_B == 4) {
+                __syncwarp();
+                if (r == 0) PML_TL_POINT(4);
+            }
         }
     }
     named_barrier(kStageBarrier, kStagers);
@@ -231,11 +265,13 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     }
 #endif
     if (trp) op.trace[92] += clock64() - t_entry;
+    PML_TL_POINT(5);
     if (warp < kMmaWarps) {
         if (!kTipL) pmat::fragments_from_smem(fragL, lane, s_x + c_p * pmat::kFragSlotDoubles);
         if (!kTipR) pmat::fragments_from_smem(fragR, lane, s_x + (kCats + c_p) * pmat::kFragSlotDoubles);
     }
     named_barrier(kStageBarrier, kStagers);  // the product slots are free for their real purpose
+    PML_TL_POINT(6);
     if (warp > kProducerWarp) return;
 
     if (warp >= kMmaWarps) {
