@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
     constexpr int kStagers = kProducerWarp * 32;  // every warp but the producer
     const int tid = threadIdx.x;
     double pre_vinv[2] = {0.0, 0.0}, pre_piv[2] = {0.0, 0.0}, pre_v[2] = {0.0, 0.0}, pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0;
+    pmat::ExtraB xb{};
     pdl_launch_dependents();
     if (warp != kProducerWarp) {
 #pragma unroll
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         }
         // cherry end: MMA warp w builds the look-up of tip (w >> 2) for category w & 3; lane k < 20 holds lambda_k * r_c
         if (kChA && warp < kMmaWarps && lane < kStates) lr = dm->lambda[lane] * dm->rates[warp & 3];
+        if (kChA && warp < kMmaWarps) xb = pmat::extra_b(dm, lane);
         if (tid < kCats * 24 && tid % 24 < kStates) {
             pre_lambda = dm->lambda[tid % 24];
             pre_rate = dm->rates[tid / 24];
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kThreadsBranch, 1) k_branch_mma(BranchArgs arg
         named_barrier(kStageBarrier, kStagers);  // V and Vinv are in place
         if (warp < kMmaWarps) {
             double acc[3][3][2];
-            pmat::build_p_tiles(s_v, pmat::exp_neg(lr * tip_len), lane, acc);
+            pmat::build_p_tiles(s_v, pmat::exp_neg(lr * tip_len), lane, xb, acc);
             pmat::tiles_to_lookup(acc, lane, warp & 3, s_tip + (warp >> 2) * kCodes * kTipPad, kTipPad);
         }
     }

@@ -365,6 +365,14 @@ bool upload_model(pml_aln* a) {
                 for (int i = 0; i < kStates; ++i) acc += h->piV[i][k];
             h->tipvec[code][k] = acc;
         }
+    for (int k = 0; k < kStates; ++k) {
+        double all = 0.0;
+        for (int j = 0; j < kStates; ++j) all += es.Vinv[k][j];
+        h->vinv_codes[k][0] = es.Vinv[k][2] + es.Vinv[k][3];
+        h->vinv_codes[k][1] = es.Vinv[k][5] + es.Vinv[k][6];
+        h->vinv_codes[k][2] = all;
+        h->vinv_codes[k][3] = 0.0;
+    }
     ++a->model_epoch;  // every tree of this alignment drops its views before it plans again (adopt_model)
     return c->cuda(cudaMemcpyAsync(a->d_model, h, sizeof(DeviceModel), cudaMemcpyHostToDevice, c->stream), "model upload");
 }

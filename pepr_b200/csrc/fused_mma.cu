@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     // ---- static model constants first (before the dependency wait and before any bulk load is queued) ----------------
     double pre[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
     double pre_lambda = 0.0, pre_rate = 0.0, lr = 0.0, pre_tip[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    pmat::ExtraB xb{};
     const int c_p = warp & 3;  // MMA warp w builds category w & 3 of the branches at positions (w >> 2), (w >> 2) + 2, ... (Plan::branch_id)
     if (warp != kProducerWarp) {
 #pragma unroll
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
             }
         }
         if (warp < kMmaWarps && lane < kStates) lr = dm->lambda[lane] * dm->rates[c_p];
+        if (warp < kMmaWarps && Plan::kTablesL + Plan::kTablesR + Plan::kTablesY > 0) xb = pmat::extra_b(dm, lane);
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < kFDepth; ++i) {
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
         for (int r = 0; r < kRounds; ++r) {
             const int id = Plan::branch_id(2 * r + (warp >> 2));
             double acc[3][3][2];
-            pmat::build_p_tiles(s_model, pmat::exp_neg(lr * my_len[r]), lane, acc);
+            pmat::build_p_tiles(s_model, pmat::exp_neg(lr * my_len[r]), lane, xb, acc);
             double* table = nullptr;
             if (id == 0 && kTipL) table = s_tabL;
             else if (id == 1 && kTipR) table = s_tabR;

@@ -19,6 +19,9 @@ struct DeviceModel {
     double rates[kCats];
     double piV[kStates][kStates];   // pi_i * V[i][k]
     double tipvec[kCodes][kStates]; // sum over the residues a code allows of pi_i V[i][k]: the eigen-space vector of a tip end
+    // Vinv[k][.] summed over the residues of the ambiguity codes 20 (B = N|D), 21 (Z = Q|E), 22 (undetermined), then 0: three more
+    // columns for the matrix product that builds P(t), which then delivers a tip's look-up rows of those codes by itself
+    double vinv_codes[kStates][4];
 };
 
 // one side of a branch: an inner node's CLV (+ cumulative scaling counts), a tip's residue codes, or a CHERRY -- an inner

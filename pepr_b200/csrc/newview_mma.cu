@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     const int c_p = warp & 3;
     double lr = 0.0;
     if (warp < kMmaWarps && lane < kStates) lr = op.dm->lambda[lane] * op.dm->rates[c_p];
+    pmat::ExtraB xb{};
+    if (warp < kMmaWarps && Plan::kTablesL + Plan::kTablesR > 0) xb = pmat::extra_b(op.dm, lane);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kMmaGroups * kDepth; ++i) {
             mbar_init(in_full + i, 1);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             if (trp && r == 0) probe[0] = clock64() - t_entry + (long long)(e_lane == 12345.678);
 #endif
             if (r == 0 && e_lane != 12345.678) PML_TL_POINT(2);
-            pmat::build_p_tiles(s_model, e_lane, lane, acc);
+            pmat::build_p_tiles(s_model, e_lane, lane, xb, acc);
             if (r == 0 && acc[2][2][1] != 12345.678) PML_TL_POINT(3);
 #ifdef PML_PROLOGUE_PROBES
             if (trp && r == 0) probe[1] = clock64() - t_entry + (long long)(acc[2][2][1] == 12345.678);

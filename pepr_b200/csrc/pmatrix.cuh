@@ -140,7 +140,21 @@ __device__ __forceinline__ void dmma_p(double& d0, double& d1, double a, double 
 // acc[nt][jt] = P_c[nt*8 + g][jt*8 + 2t + {0,1}] for lane = 4g + t.  e_lane = exp(lambda_k r_c t) held by lane k (< 20):
 // the warp computes its own twenty exponentials, so nothing but V and Vinv (static, staged before the dependency wait) has to
 // be in shared memory.
-__device__ __forceinline__ void build_p_tiles(const double* s_model, double e_lane, int lane, double (&acc)[3][3][2]) {
+// Columns 20, 21, 22 of the padded product are not wasted: with DeviceModel::vinv_codes as three more columns of Vinv they come
+// out as P_c summed over the residues of the ambiguity codes B, Z and "undetermined" -- the three rows of a tip's look-up table
+// that used to be added up with FP64 SIMT instructions and shuffles next to the other warps' DMMAs (0.68 us for a table against
+// 0.12 us for a set of fragments).  extra_b() fetches a lane's share of those columns (static: before the dependency wait).
+struct ExtraB {
+    double v[5];  // for k = 4 ks + t: column 16 + g of the extended Vinv (g = 4, 5, 6; 0 elsewhere)
+};
+__device__ __forceinline__ ExtraB extra_b(const DeviceModel* dm, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    ExtraB x;
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) x.v[ks] = (g >= 4 && g < 7) ? dm->vinv_codes[4 * ks + t][g - 4] : 0.0;
+    return x;
+}
+__device__ __forceinline__ void build_p_tiles(const double* s_model, double e_lane, int lane, const ExtraB& xb, double (&acc)[3][3][2]) {
     const double* s_V = s_model;
     const double* s_Vinv = s_model + kMat;
     const int g = lane >> 2, t = lane & 3;
@@ -157,7 +171,7 @@ __device__ __forceinline__ void build_p_tiles(const double* s_model, double e_la
         for (int q = 0; q < 3; ++q) {
             const int ij = q * 8 + g;
             a[q] = ij < kStates ? s_V[ij * kStates + k] * e : 0.0;
-            b[q] = ij < kStates ? s_Vinv[k * kStates + ij] : 0.0;
+            b[q] = ij < kStates ? s_Vinv[k * kStates + ij] : (q == 2 ? xb.v[ks] : 0.0);
         }
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt)
@@ -190,35 +204,22 @@ __device__ __forceinline__ void tiles_to_smem(const double (&acc)[3][3][2], int 
         }
 }
 // accumulators -> the 23 x 80 look-up of a tip on that branch, tip[code][c*20 + i] = sum_j P_c[i][j] indicator(code)[j], written
-// straight from the warp that built the matrix (category c): residue codes are single columns of P_c, B = N|D (columns 2, 3),
-// Z = Q|E (columns 5, 6), undetermined = the row sum.  Rows padded to `pad` doubles.
+// straight from the warp that built the matrix (category c): residue codes are single columns of P_c, and columns 20 - 22 of the
+// extended product (build_p_tiles) are the rows of B = N|D, Z = Q|E and "undetermined".  Rows padded to `pad` doubles.
 __device__ __forceinline__ void tiles_to_lookup(const double (&acc)[3][3][2], int lane, int c, double* table, int pad) {
-    const int g = lane >> 2, t = lane & 3, quad = lane & ~3;
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int nt = 0; nt < 3; ++nt) {
         const int i = nt * 8 + g;
-        const bool row_ok = i < kStates;
-        double* col = table + c * kStates + i;
-        double sum = 0.0;
+        if (i < kStates) {
+            double* col = table + c * kStates + i;
 #pragma unroll
-        for (int jt = 0; jt < 3; ++jt)
+            for (int jt = 0; jt < 3; ++jt)
 #pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                const int j = jt * 8 + 2 * t + x;
-                if (j < kStates) {
-                    if (row_ok) col[j * pad] = acc[nt][jt][x];
-                    sum += acc[nt][jt][x];
+                for (int x = 0; x < 2; ++x) {
+                    const int j = jt * 8 + 2 * t + x;
+                    if (j < kCodes) col[j * pad] = acc[nt][jt][x];
                 }
-            }
-        const double q5 = __shfl_sync(0xffffffffu, acc[nt][0][1], quad | 2), e6 = __shfl_sync(0xffffffffu, acc[nt][0][0], quad | 3);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        if (row_ok) {
-            if (t == 1) col[20 * pad] = acc[nt][0][0] + acc[nt][0][1];
-            if (t == 0) {
-                col[21 * pad] = q5 + e6;
-                col[22 * pad] = sum;
-            }
         }
     }
 }
