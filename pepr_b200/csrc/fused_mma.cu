@@ -301,11 +301,15 @@ __global__ void __launch_bounds__(kThreadsFused, 1) k_fused(NewviewOp op, Branch
     if (warp < kMmaWarps) {
         // an inner or cherry child's matrix leaves the accumulators as B fragments for the NV warp of its category; every tip's
         // matrix -- a tip child's or a cherry's -- goes straight into its look-up table
+        // the exponentials of all rounds first: their dependency chains run side by side instead of one per round
+        double e_round[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) e_round[r] = pmat::exp_neg(lr * my_len[r]);
 #pragma unroll
         for (int r = 0; r < kRounds; ++r) {
             const int id = Plan::branch_id(2 * r + (warp >> 2));
             double acc[3][3][2];
-            pmat::build_p_tiles(s_model, pmat::exp_neg(lr * my_len[r]), lane, xb, acc);
+            pmat::build_p_tiles(s_model, e_round[r], lane, xb, acc);
             double* table = nullptr;
             if (id == 0 && kTipL) table = s_tabL;
             else if (id == 1 && kTipR) table = s_tabR;

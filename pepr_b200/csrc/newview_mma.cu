@@ -223,11 +223,15 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     long long probe[3] = {0, 0, 0};  // warp 0 of CTA 0, first round: exponentials done | matrix tiles done | table / fragments stored
 #endif
     if (warp < kMmaWarps) {
+        // the exponentials of all rounds first: their dependency chains run side by side instead of one per round
+        double e_round[kRounds];
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) e_round[r] = pmat::exp_neg(lr * my_len[r]);
 #pragma unroll
         for (int r = 0; r < kRounds; ++r) {
             const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;
             double acc[3][3][2];
-            const double e_lane = pmat::exp_neg(lr * my_len[r]);
+            const double e_lane = e_round[r];
 #ifdef PML_PROLOGUE_PROBES
             if (trp && r == 0) probe[0] = clock64() - t_entry + (long long)(e_lane == 12345.678);
 #endif
