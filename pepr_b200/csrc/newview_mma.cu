@@ -219,9 +219,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
     if (trp) op.trace[90] += clock64() - t_entry;
     double fragL[3][5], fragR[3][5];
     double* s_x = s_prod;  // fragment exchange: [branch 0 / 1][category][15][32]
-#ifdef PML_PROLOGUE_PROBES
-    long long probe[3] = {0, 0, 0};  // warp 0 of CTA 0, first round: exponentials done | matrix tiles done | table / fragments stored
-#endif
     if (warp < kMmaWarps) {
         // the exponentials of all rounds first: their dependency chains run side by side instead of one per round
         double e_round[kRounds];
@@ -232,15 +229,9 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
             const int pos = 2 * r + (warp >> 2), id = (pos < 2 || kChL) ? pos : pos + 2;
             double acc[3][3][2];
             const double e_lane = e_round[r];
-#ifdef PML_PROLOGUE_PROBES
-            if (trp && r == 0) probe[0] = clock64() - t_entry + (long long)(e_lane == 12345.678);
-#endif
-            if (r == 0 && e_lane != 12345.678) PML_TL_POINT(2);
+            if (r == 0 && e_lane != 12345.678) PML_TL_POINT(2);  // (the comparisons tie a stamp to the value it follows; no code without probes)
             pmat::build_p_tiles(s_model, e_lane, lane, xb, acc);
             if (r == 0 && acc[2][2][1] != 12345.678) PML_TL_POINT(3);
-#ifdef PML_PROLOGUE_PROBES
-            if (trp && r == 0) probe[1] = clock64() - t_entry + (long long)(acc[2][2][1] == 12345.678);
-#endif
             double* table = nullptr;
             if (id == 0 && kTipL) table = s_tabL;
             else if (id == 1 && kTipR) table = s_tabR;
@@ -252,10 +243,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
                 pmat::tiles_to_fragments(acc, lane, frag);
                 pmat::fragments_to_smem(frag, lane, s_x + (id * kCats + c_p) * pmat::kFragSlotDoubles);
             }
-#ifdef PML_PROLOGUE_PROBES
-            __syncwarp();
-            if (trp && r == 0) probe[2] = clock64() - t_entry;
-#endif
             if (PML_TL_PROBE_A == 4 || PML_TL_PROBE_B == 4) {
                 __syncwarp();
                 if (r == 0) PML_TL_POINT(4);
@@ -263,13 +250,6 @@ __global__ void __launch_bounds__(kThreadsNewview, 1) k_newview_mma(NewviewOp op
         }
     }
     named_barrier(kStageBarrier, kStagers);
-#ifdef PML_PROLOGUE_PROBES
-    if (trp) {
-        op.trace[93] += probe[0];
-        op.trace[94] += probe[1];
-        op.trace[95] += probe[2];
-    }
-#endif
     if (trp) op.trace[92] += clock64() - t_entry;
     PML_TL_POINT(5);
     if (warp < kMmaWarps) {

@@ -25,8 +25,6 @@ for _ in range(3):
 out = np.zeros(96, np.int64)
 L.pml_trace_read(ctx.h, out.ctypes.data_as(C.c_void_p))
 print("prologue probes (cycles after pdl_wait, per launch): init sync %.0f, model in smem %.0f, P built %.0f" % tuple(out[90:93] / max(out[70], 1)))
-if out[93]:
-    print("  first round on warp 0 (PML_PROLOGUE_PROBES build): exponentials done %.0f, matrix tiles done %.0f, table / fragments stored %.0f" % tuple(out[93:96] / max(out[70], 1)))
 out = out.reshape(12, 8)
 print("phase: wait_data frags+turn mma products wait_slot store  (cycles per tile), tiles")
 for w in range(8):
