@@ -164,6 +164,14 @@ int pml_timeline_begin(pml_ctx *);
 int pml_timeline_read(pml_ctx *, uint64_t *stamps, int32_t *kinds, int cap);
 int pml_trace_read(pml_ctx *, int64_t out[96]);
 
+/* host builds of two pieces of the device arithmetic, for CPU tests of what DESIGN.md claims about them (no GPU needed):
+ * pml_debug_exp_neg is the exponential the kernels use for lambda_k r_c t <= 0 (pmatrix.cuh: relative error <= 1.4 x 2^-53 on
+ * [-708, 0], 0 below); pml_debug_nr_step is raxmlHPC's guarded Newton-Raphson step on a branch of length t with derivatives
+ * d1, d2 (topLevelMakenewz), stated on z = exp(-t) (in_t = 0, the reference rule) or as the device runs it, on t (in_t = 1);
+ * returns the step's status (1 done, 2 bad curvature: derivatives again at *t_new) and the new length. */
+double pml_debug_exp_neg(double x);
+int pml_debug_nr_step(double t, double d1, double d2, int in_t, double *t_new);
+
 /* stopwatch on the context's stream: start records an event, stop records another, synchronises and returns the
  * device milliseconds in between (host control flow between the two is included, as it should be for a step time) */
 int pml_timer_start(pml_ctx *);

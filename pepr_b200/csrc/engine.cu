@@ -25,6 +25,7 @@
 #include "host.h"
 #include "kernels.h"
 #include "model.h"
+#include "pmatrix.cuh"
 
 using namespace pml;
 
@@ -1389,6 +1390,14 @@ int pml_timer_stop(pml_ctx* c, double* ms) {
         return PML_ENODEVICE;
     *ms = f;
     return PML_OK;
+}
+
+// host builds of two pieces of device arithmetic, so that what DESIGN claims about them is a CPU test (tests/test_host.py)
+double pml_debug_exp_neg(double x) { return pmat::exp_neg(x); }
+int pml_debug_nr_step(double t, double d1, double d2, int in_t, double* t_new) {
+    if (!t_new) return PML_EINVAL;
+    const double tc = nr_clamp_length(t);
+    return in_t ? nr_step_t(nr_early(tc), d1, d2, t_new) : nr_step_z(nr_z(tc), d1, d2, t_new);
 }
 
 int pml_kind_info(int kind, char* name, size_t cap, int* bytes_per_pattern, int* dmma_per_tile) {

@@ -156,7 +156,6 @@ struct Publish {
     double* len;    // nullptr: no NR step
     int* poison;
 };
-#ifdef __CUDACC__
 // What the publishing thread can fetch while the pass is still running (after the dependency wait): the poison flag -- only a
 // launch that has completed can have raised it -- and z of the length the sums are taken at.  Both used to sit, a dependent
 // global load and an exponential, between the last CTA's sum and the store of the new length.
@@ -170,20 +169,16 @@ struct PublishEarly {
     double t_lo;     // -log min(0.25 z + 0.75, zmax): the shortest length the step may end on
     double t_retry;  // -log(0.37 z + 0.63): where the derivatives are taken again after a bad curvature
 };
-__device__ __forceinline__ PublishEarly publish_prefetch(const Publish& pub, double t) {
-    PublishEarly e{0, 0.0, t, 0.0, 0.0};
-    if (pub.len) {
-        e.poison = *reinterpret_cast<volatile int*>(pub.poison);
-        e.z = nr_z(t);
-        const double cap = 0.25 * e.z + 0.75;
-        e.t_lo = -log(cap < kZmax ? cap : kZmax);
-        e.t_retry = -log(0.37 * e.z + 0.63);
-    }
+__host__ __device__ inline PublishEarly nr_early(double t) {
+    PublishEarly e{0, nr_z(t), t, 0.0, 0.0};
+    const double cap = 0.25 * e.z + 0.75;
+    e.t_lo = -log(cap < kZmax ? cap : kZmax);
+    e.t_retry = -log(0.37 * e.z + 0.63);
     return e;
 }
 // nr_step_z in t = -log z: z exp(step) is t - step, the clamps of z become clamps of t (same decisions; the new length differs
 // from -log(z exp(step)) by rounding only)
-__device__ __forceinline__ int nr_step_t(const PublishEarly& e, double d1t, double d2t, double* t_new) {
+__host__ __device__ inline int nr_step_t(const PublishEarly& e, double d1t, double d2t, double* t_new) {
     const double d1 = -d1t, d2 = d2t;  // derivatives in lz = log z = -t
     if (d2 >= 0.0 && e.z < kZmax) {
         *t_new = e.t_retry;
@@ -202,6 +197,15 @@ __device__ __forceinline__ int nr_step_t(const PublishEarly& e, double d1t, doub
     }
     *t_new = t;
     return kNrDone;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ PublishEarly publish_prefetch(const Publish& pub, double t) {
+    PublishEarly e{0, 0.0, t, 0.0, 0.0};
+    if (pub.len) {
+        e = nr_early(t);
+        e.poison = *reinterpret_cast<volatile int*>(pub.poison);
+    }
+    return e;
 }
 // release / acquire around the ticket of the last-CTA sum (cheaper than the sequentially consistent __threadfence)
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }

@@ -113,7 +113,7 @@ __device__ __forceinline__ void build_p(const double* s_model, int tid, double* 
 // has a chain of ten: Cody-Waite reduction by ln 2, then exp(r) = 1 + r + r^2 q(r) with q of degree 11 (Taylor; |r| <= 0.347:
 // truncation 4e-18) evaluated by Estrin's scheme, then the power of two through the exponent bits.  Relative error
 // <= 1.4 x 2^-53 over [-708, 0] (checked against 200-bit arithmetic); below -708 the result is 0 (the library gives < 3e-308).
-__device__ __forceinline__ double exp_neg(double x) {
+__host__ __device__ __forceinline__ double exp_neg(double x) {
     if (!(x > -708.0)) return 0.0;
     const double n = rint(x * 1.4426950408889634);
     double r = fma(-n, 6.93147180369123816490e-01, x);
@@ -125,7 +125,14 @@ __device__ __forceinline__ double exp_neg(double x) {
     const double q0 = fma(p1, r2, p0), q1 = fma(p3, r2, p2), q2 = fma(p5, r2, p4);
     const double q = fma(q2, r8, fma(q1, r4, q0));
     const double e = fma(r2, q, r) + 1.0;
+#ifdef __CUDA_ARCH__
     return e * __hiloint2double(((int)n + 1023) << 20, 0);
+#else  // host build of the same arithmetic (pml_debug_exp_neg: the accuracy claim above is a CPU test)
+    const unsigned long long bits = (unsigned long long)((int)n + 1023) << 52;
+    double scale;
+    __builtin_memcpy(&scale, &bits, sizeof scale);
+    return e * scale;
+#endif
 }
 
 // ---- the same product on the FP64 tensor path, one warp per (branch, category) ---------------------------------------

@@ -264,3 +264,53 @@ def test_branch_lengths_are_printed_like_java_double_tostring():
     t = "((A:0.1,B:0.0001):1.0E7,(C:123456789,D:0.001):9999999,(E:2,F:1e-5):12345.678,G:0.30000000000000004);"
     out = pb.support_tree(t, [t], as_percent=False)
     assert out == "((A:0.1,B:1.0E-4)1:1.0E7,(C:1.23456789E8,D:0.001)1:9999999.0,(E:2.0,F:1.0E-5)1:12345.678,G:0.30000000000000004)1;"
+
+
+def test_device_exponential_accuracy_on_host_build():
+    """pmatrix.cuh exp_neg (the exponential of the P(t) and exponential-table prologues), host build of the same arithmetic:
+    relative error <= 1.4 x 2^-53 on [-708, 0] against 60-digit arithmetic, exactly 1 at 0, exactly 0 below -708."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    L = ctypes.CDLL(os.path.join(ROOT, "pepr_b200", "libpeprml.so"))
+    L.pml_debug_exp_neg.restype = ctypes.c_double
+    L.pml_debug_exp_neg.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([-rng.random(4000) * 708.0, -rng.random(3000) * 3.0, -rng.random(1000) * 1e-4, -10.0 ** rng.uniform(-300, -5, 500),
+                         [0.0, -0.34657359027997264, -0.3465735902799727, -707.999, 3e-16]])
+    worst = 0.0
+    for x in xs:
+        got, ref = Decimal(L.pml_debug_exp_neg(float(x))), Decimal(float(x)).exp()
+        worst = max(worst, float(abs(got - ref) / ref))
+    assert worst <= 1.4 * 2.0 ** -53, worst
+    assert L.pml_debug_exp_neg(0.0) == 1.0
+    assert L.pml_debug_exp_neg(-708.5) == 0.0 and L.pml_debug_exp_neg(-1e4) == 0.0
+
+
+def test_guarded_newton_step_on_t_makes_the_decisions_of_the_rule_on_z():
+    """kernels.h nr_step_t (what the device runs) against nr_step_z (raxmlHPC's update stated on z = exp(-t)): same status, same
+    new length up to rounding -- ordinary steps, bad curvature, the step cap 0.25 z + 0.75, exponent >= 100, zmin and zmax."""
+    L = ctypes.CDLL(os.path.join(ROOT, "pepr_b200", "libpeprml.so"))
+    L.pml_debug_nr_step.argtypes = [ctypes.c_double] * 3 + [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+
+    def both(t, d1, d2):
+        out = []
+        for in_t in (0, 1):
+            tn = ctypes.c_double()
+            out.append((L.pml_debug_nr_step(t, d1, d2, in_t, ctypes.byref(tn)), tn.value))
+        return out
+
+    rng = np.random.default_rng(11)
+    cases = [(0.1, -50.0, -800.0), (0.1, 50.0, -800.0), (0.1, 5.0, 3.0), (1e-7, 1.0, -1.0), (30.0, -1e5, -1.0), (0.5, 1e6, -1.0),
+             (0.5, -150.0, -1.0), (1e-9, 0.0, 1.0), (40.0, 1.0, -1.0), (0.2, 0.0, -1.0)]
+    for _ in range(5000):
+        cases.append((float(10.0 ** rng.uniform(-7, 1.5)), float(rng.normal() * 10.0 ** rng.uniform(-3, 5)),
+                      float(rng.normal() * 10.0 ** rng.uniform(-3, 5))))
+    statuses = set()
+    for t, d1, d2 in cases:
+        (sz, tz), (st, tt) = both(t, d1, d2)
+        assert sz == st, (t, d1, d2, sz, st)
+        assert abs(tz - tt) <= 1e-12 * max(1.0, abs(tz)) + 1e-16, (t, d1, d2, tz, tt)
+        if st == 1:  # a finished step ends inside the NR range (a retry point 0.37 z + 0.63 may lie above zmax: the next pass clamps it)
+            assert 1.0e-6 <= tt <= 34.538776394910684 + 1e-12
+        statuses.add(st)
+    assert statuses == {1, 2}
