@@ -112,7 +112,8 @@ __device__ __forceinline__ void build_p(const double* s_model, int tid, double* 
 // 1,440 clk measured between "length arrived" and "exponentials done" in every launch's prologue, a quarter of it.  This one
 // has a chain of ten: Cody-Waite reduction by ln 2, then exp(r) = 1 + r + r^2 q(r) with q of degree 11 (Taylor; |r| <= 0.347:
 // truncation 4e-18) evaluated by Estrin's scheme, then the power of two through the exponent bits.  Relative error
-// <= 1.4 x 2^-53 over [-708, 0] (checked against 200-bit arithmetic); below -708 the result is 0 (the library gives < 3e-308).
+// <= 1.4 x 2^-53 over [-708, 0] (tests/test_host.py, against 60-digit arithmetic); below -708 -- and for a NaN -- the result is 0
+// (the library gives < 3e-308 there).
 __host__ __device__ __forceinline__ double exp_neg(double x) {
     if (!(x > -708.0)) return 0.0;
     const double n = rint(x * 1.4426950408889634);
